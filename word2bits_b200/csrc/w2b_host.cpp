@@ -1,0 +1,300 @@
+// libw2b host side (no CUDA): corpus reader + vocabulary, shard-start resolution,
+// unigram boundaries, expTable, vector-file writer.  These replace the reference's
+// host glue (src/word2bits.cpp:112-301, :560-576, :614-618) with identical results;
+// the text is read once through mmap and tokenised into an int32 id stream instead of
+// being re-parsed with fgetc by every thread in every epoch (:396).
+#include <fcntl.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "w2b.h"
+#include "w2b_internal.h"
+
+void w2b_unigram_bounds(const int64_t *cn, int64_t V, int32_t *start) {
+  const double N = (double)W2B_TABLE_SIZE;
+  double total = 0;
+  for (int64_t a = 0; a < V; ++a) total += pow((double)cn[a], 0.75);
+  double d1 = pow((double)cn[0], 0.75) / total;  // cumulative share of words 0..i
+  int64_t a = 0;                                  // next table slot to examine
+  start[0] = 0;
+  int64_t i = 0;
+  for (; i + 1 < V; ++i) {
+    // The reference assigns slot a to word i and only then tests a/1e8 > d1 (:121-125):
+    // word i keeps every slot up to and including the first one that passes the test.
+    // Jump close with the closed form, then settle with the reference's own comparison.
+    const int64_t guess = (int64_t)(d1 * N) - 2;  // the test is monotone in a
+    if (guess > a) a = guess;
+    while (a < W2B_TABLE_SIZE && !((double)a / N > d1)) ++a;
+    if (a >= W2B_TABLE_SIZE) break;
+    ++a;
+    start[i + 1] = (int32_t)a;
+    d1 += pow((double)cn[i + 1], 0.75) / total;
+  }
+  for (int64_t j = i + 1; j <= V; ++j) start[j] = W2B_TABLE_SIZE;
+}
+
+void w2b_exptable(float *out) {
+  for (int i = 0; i < 1000; ++i) {
+    float e = expf((i / (float)1000 * 2 - 1) * 6);
+    out[i] = e / (e + 1);
+  }
+}
+
+// ----------------------------------------------------------------------------- tokeniser
+namespace {
+
+constexpr int kMaxWord = 4096;  // MAX_STRING :29
+constexpr int64_t kCkptEvery = 4096;
+
+// One ReadWord call (:131-155) over the mapped file.  false at EOF; a word cut short by
+// EOF is dropped, as both callers of the reference do (:279, :180).
+inline bool next_token(const uint8_t *buf, int64_t n, int64_t &pos, char *word, int &len, int64_t &begin) {
+  int a = 0;
+  while (pos < n) {
+    const int ch = buf[pos++];
+    if (ch == 13) continue;
+    if (ch == ' ' || ch == '\t' || ch == '\n') {
+      if (a > 0) {
+        if (ch == '\n') --pos;  // the newline is read again as </s>
+        word[a] = 0;
+        len = (int)strlen(word);  // an embedded NUL ends the C string, as in the reference
+        return true;
+      }
+      if (ch == '\n') {
+        memcpy(word, "</s>", 5);
+        len = 4;
+        begin = pos - 1;
+        return true;
+      }
+      continue;
+    }
+    if (a == 0) begin = pos - 1;
+    word[a++] = (char)ch;
+    if (a >= kMaxWord - 1) --a;
+  }
+  return false;
+}
+
+inline uint64_t hash_bytes(const char *s, int len) {
+  uint64_t h = 1469598103934665603ULL;
+  for (int i = 0; i < len; ++i) h = (h ^ (uint8_t)s[i]) * 1099511628211ULL;
+  return h;
+}
+
+struct WordMap {
+  std::vector<uint32_t> slot;   // entry index + 1, 0 = empty
+  std::vector<uint64_t> off;    // arena offset per entry
+  std::vector<uint32_t> wlen;
+  std::vector<int64_t> count;
+  std::string arena;
+  uint64_t mask = 0;
+
+  WordMap() { slot.assign(1u << 16, 0); mask = slot.size() - 1; }
+  const char *str(uint32_t e) const { return arena.data() + off[e]; }
+  void grow() {
+    std::vector<uint32_t> ns(slot.size() * 2, 0);
+    const uint64_t m = ns.size() - 1;
+    for (uint32_t e = 0; e < off.size(); ++e) {
+      uint64_t h = hash_bytes(str(e), (int)wlen[e]) & m;
+      while (ns[h]) h = (h + 1) & m;
+      ns[h] = e + 1;
+    }
+    slot.swap(ns);
+    mask = m;
+  }
+  int64_t find(const char *w, int len) const {
+    uint64_t h = hash_bytes(w, len) & mask;
+    while (slot[h]) {
+      const uint32_t e = slot[h] - 1;
+      if ((int)wlen[e] == len && !memcmp(str(e), w, len)) return e;
+      h = (h + 1) & mask;
+    }
+    return -1;
+  }
+  uint32_t insert(const char *w, int len) {
+    if ((off.size() + 1) * 2 > slot.size()) grow();
+    const uint32_t e = (uint32_t)off.size();
+    off.push_back(arena.size());
+    wlen.push_back((uint32_t)len);
+    count.push_back(0);
+    arena.append(w, len);
+    arena.push_back('\0');
+    uint64_t h = hash_bytes(w, len) & mask;
+    while (slot[h]) h = (h + 1) & mask;
+    slot[h] = e + 1;
+    return e;
+  }
+};
+
+}  // namespace
+
+struct w2b_corpus {
+  const uint8_t *buf = nullptr;
+  int64_t file_size = 0;
+  int fd = -1;
+  WordMap map;
+  std::vector<int32_t> final_id;  // map entry -> vocab id or -1
+  std::vector<const char *> words;
+  std::vector<int64_t> cn;
+  int64_t train_words = 0;
+  std::vector<int32_t> ids;
+  // every kCkptEvery raw tokens: byte offset of the token and #in-vocab tokens before it
+  std::vector<int64_t> ck_begin, ck_comp;
+};
+
+extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out) {
+  *out = nullptr;
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    w2b_set_error("ERROR: training data file not found!");  // :272
+    return W2B_EIO;
+  }
+  struct stat st;
+  fstat(fd, &st);
+  w2b_corpus *c = new w2b_corpus();
+  c->fd = fd;
+  c->file_size = st.st_size;  // == ftell at EOF, :299
+  if (st.st_size > 0) {
+    void *m = mmap(nullptr, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) {
+      close(fd);
+      delete c;
+      w2b_set_error("mmap failed for %s", path);
+      return W2B_EIO;
+    }
+    madvise(m, st.st_size, MADV_SEQUENTIAL);
+    c->buf = (const uint8_t *)m;
+  }
+  // pass 1: provisional ids in first-appearance order, </s> first (:276)
+  WordMap &map = c->map;
+  map.insert("</s>", 4);
+  std::vector<uint32_t> raw;
+  raw.reserve((size_t)(c->file_size / 5 + 16));
+  std::vector<int64_t> ck_begin_raw;
+  char word[kMaxWord];
+  int len = 0;
+  int64_t pos = 0, begin = 0;
+  while (next_token(c->buf, c->file_size, pos, word, len, begin)) {
+    int64_t e = map.find(word, len);
+    if (e < 0) e = map.insert(word, len);
+    map.count[e]++;
+    if ((int64_t)raw.size() % kCkptEvery == 0) ck_begin_raw.push_back(begin);
+    raw.push_back((uint32_t)e);
+  }
+  // SortVocab (:215-242): </s> pinned at 0, the rest by count descending, ties in
+  // first-appearance order (what glibc's qsort yields here; asserted against the
+  // reference in tests), then the min_count cut.
+  const size_t m = map.off.size();
+  std::vector<uint32_t> order(m);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin() + 1, order.end(),
+                   [&](uint32_t a, uint32_t b) { return map.count[a] > map.count[b]; });
+  c->final_id.assign(m, -1);
+  for (size_t k = 0; k < m; ++k) {
+    const uint32_t e = order[k];
+    if (map.count[e] < min_count && k != 0) continue;
+    c->final_id[e] = (int32_t)c->words.size();
+    c->words.push_back(nullptr);  // arena may still move: fixed up below
+    c->cn.push_back(map.count[e]);
+    c->train_words += map.count[e];
+  }
+  for (size_t e = 0; e < m; ++e)
+    if (c->final_id[e] >= 0) c->words[c->final_id[e]] = map.str((uint32_t)e);
+  // compact to the in-vocab stream, remembering where every checkpoint lands in it
+  c->ids.reserve(raw.size());
+  for (size_t t = 0; t < raw.size(); ++t) {
+    if ((int64_t)t % kCkptEvery == 0) {
+      c->ck_begin.push_back(ck_begin_raw[t / kCkptEvery]);
+      c->ck_comp.push_back((int64_t)c->ids.size());
+    }
+    const int32_t id = c->final_id[raw[t]];
+    if (id >= 0) c->ids.push_back(id);
+  }
+  *out = c;
+  return W2B_OK;
+}
+
+extern "C" void w2b_corpus_free(w2b_corpus *c) {
+  if (!c) return;
+  if (c->buf) munmap((void *)c->buf, c->file_size);
+  if (c->fd >= 0) close(c->fd);
+  delete c;
+}
+
+extern "C" int64_t w2b_corpus_vocab_size(const w2b_corpus *c) { return (int64_t)c->words.size(); }
+extern "C" int64_t w2b_corpus_train_words(const w2b_corpus *c) { return c->train_words; }
+extern "C" int64_t w2b_corpus_file_size(const w2b_corpus *c) { return c->file_size; }
+extern "C" const char *w2b_corpus_word(const w2b_corpus *c, int64_t i) { return c->words[i]; }
+extern "C" const int64_t *w2b_corpus_counts(const w2b_corpus *c) { return c->cn.data(); }
+extern "C" int64_t w2b_corpus_num_tokens(const w2b_corpus *c) { return (int64_t)c->ids.size(); }
+extern "C" const int32_t *w2b_corpus_tokens(const w2b_corpus *c) { return c->ids.data(); }
+
+extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int32_t *first) {
+  if (n < 1) {
+    w2b_set_error("shard count must be >= 1");
+    return W2B_EINVAL;
+  }
+  char word[kMaxWord];
+  for (int i = 0; i < n; ++i) {
+    const int64_t off = c->file_size / (int64_t)n * (int64_t)i;  // :377
+    int64_t pos = off, begin = 0;
+    int len = 0;
+    first[i] = -1;
+    if (!next_token(c->buf, c->file_size, pos, word, len, begin)) {
+      start[i] = (int64_t)c->ids.size();
+      continue;
+    }
+    const int64_t e = c->map.find(word, len);
+    if (e >= 0) first[i] = c->final_id[e];
+    // index of the first regular in-vocab token that begins at or after `pos`:
+    // restart from the last checkpoint at or before it and count forward
+    size_t k = std::upper_bound(c->ck_begin.begin(), c->ck_begin.end(), pos) - c->ck_begin.begin();
+    if (k == 0) {
+      start[i] = 0;
+      continue;
+    }
+    --k;
+    int64_t p2 = c->ck_begin[k], comp = c->ck_comp[k], b2 = 0;
+    int l2 = 0;
+    for (;;) {
+      if (!next_token(c->buf, c->file_size, p2, word, l2, b2)) break;
+      if (b2 >= pos) break;
+      const int64_t e2 = c->map.find(word, l2);
+      if (e2 >= 0 && c->final_id[e2] >= 0) ++comp;
+    }
+    start[i] = comp;
+  }
+  return W2B_OK;
+}
+
+extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
+                                 int binary) {
+  FILE *fo = fopen(path, "wb");
+  if (!fo) {
+    w2b_set_error("cannot open %s for writing", path);
+    return W2B_EIO;
+  }
+  static char iobuf[1 << 20];
+  setvbuf(fo, iobuf, _IOFBF, sizeof iobuf);
+  fprintf(fo, "%lld %lld\n", (long long)V, (long long)D);
+  for (int64_t a = 0; a < V; ++a) {
+    fprintf(fo, "%s ", c->words[a]);
+    const float *row = vec + a * D;
+    if (binary) fwrite(row, sizeof(float), D, fo);
+    else
+      for (int64_t b = 0; b < D; ++b) fprintf(fo, "%lf ", row[b]);
+    fprintf(fo, "\n");
+  }
+  fclose(fo);
+  return W2B_OK;
+}
