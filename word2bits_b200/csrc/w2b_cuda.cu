@@ -16,6 +16,7 @@
 #include "w2b.h"
 #include "w2b_internal.h"
 #include "w2b_kernels.cuh"
+#include "w2b_ring.cuh"
 
 using namespace w2b;
 
@@ -86,6 +87,9 @@ struct w2b_ctx {
   w2b_config cfg;
   int nlocal = 0;  // shards owned by this context
   int vec = 4, ncol = 0, threads = 0, group = 9;
+  bool ring = false;       // production TMA-ring kernel usable for this configuration
+  int ring_nu = 0, ring_nv = 0, ring_g = 13, ring_threads = 0;
+  size_t ring_smem = 0;
   int sm_count = 0;
   long long train_words = 0;
   float *d_u = nullptr, *d_v = nullptr, *d_keep = nullptr, *d_exptab = nullptr, *d_alpha = nullptr;
@@ -161,6 +165,43 @@ static apply_fn pick_apply(const w2b_ctx *c) {
   W2B_PICK(0) W2B_PICK(1) W2B_PICK(2) W2B_PICK(9)
 #undef W2B_PICK
   return nullptr;
+}
+
+typedef void (*ring_fn)(TrainParams, int, int);
+static ring_fn pick_ring(const w2b_ctx *c) {
+  const int bm = bm_of(c->cfg.bitlevel);
+#define W2B_PICK(BM) \
+  if (bm == BM) return c->ring_g == 7 ? (ring_fn)train_ring_kernel<BM, 7> : (ring_fn)train_ring_kernel<BM, 13>;
+  W2B_PICK(0) W2B_PICK(1) W2B_PICK(2) W2B_PICK(9)
+#undef W2B_PICK
+  return nullptr;
+}
+
+// Ring kernel geometry: u-ring holds one full window plus slack, v-ring up to 4 groups,
+// shrunk to what 227 KB of shared memory allows (>= 2 groups or the ring kernel is off).
+static void plan_ring(w2b_ctx *c) {
+  c->ring = false;
+  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
+  const int G = (c->cfg.negative + 1 <= 7) ? 7 : 13;
+  const int ncw = (c->ncol + 31) / 32;
+  if (ncw + 1 > 16) return;  // kernel is compiled for <= 512 threads (D <= 1920)
+  const long long D = c->cfg.layer1_size;
+  const size_t cap = 227 * 1024;
+  int nu = 2 * c->cfg.window + 4;
+  int nv = c->cfg.ring_rows > 0 ? c->cfg.ring_rows : 4 * G;
+  while (nv >= 2 * G && ring_layout(D, nu, nv).total > cap) --nv;
+  if (nv < 2 * G) {
+    nu = 2 * c->cfg.window;
+    nv = 4 * G;
+    while (nv >= 2 * G && ring_layout(D, nu, nv).total > cap) --nv;
+    if (nv < 2 * G) return;
+  }
+  c->ring = true;
+  c->ring_g = G;
+  c->ring_nu = nu;
+  c->ring_nv = nv;
+  c->ring_threads = (ncw + 1) * 32;
+  c->ring_smem = ring_layout(D, nu, nv).total;
 }
 
 static size_t dyn_smem(const w2b_ctx *c) {
@@ -241,7 +282,14 @@ extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_train(&tmp), tmp.threads, dyn_smem(&tmp)));
+  plan_ring(&tmp);
+  if (tmp.ring) {
+    ring_fn rf = pick_ring(&tmp);
+    CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp.ring_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rf, tmp.ring_threads, tmp.ring_smem));
+  } else {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_train(&tmp), tmp.threads, dyn_smem(&tmp)));
+  }
   *out = std::max(1, per_sm) * prop.multiProcessorCount;
   return W2B_OK;
 }
@@ -278,6 +326,7 @@ extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
     w2b_set_error("group must be 0, 5, 9 or 13");
     return W2B_EINVAL;
   }
+  plan_ring(c);
   CK(cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -443,6 +492,23 @@ static int stage_slices(w2b_ctx *c, long long want) {
 }
 
 static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
+  if (c->ring) {  // production path: TMA ring kernel, one CTA per shard
+    ring_fn rf = pick_ring(c);
+    CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    p.shard_base = 0;
+    rf<<<c->nlocal, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    acc->kernel_ms += ms;
+    acc->launches += 1;
+    return W2B_OK;
+  }
   train_fn fn = pick_train(c);
   if (!fn) { w2b_set_error("no kernel for this configuration"); return W2B_EINVAL; }
   const size_t smem = dyn_smem(c);

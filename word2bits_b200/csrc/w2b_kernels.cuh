@@ -231,8 +231,9 @@ __device__ inline int build_sentence(const TrainParams &p, const ShardState &sh,
 
 // Window draw, context slots and the 1+negative targets of one position (:428-460).
 // Writes the descriptor; returns the RNG state after the position's draws.
+template <class Desc>
 __device__ inline unsigned long long make_position(const TrainParams &p, int lane, const int *sen, int len,
-                                                   int sp, unsigned long long r, PosDesc *d) {
+                                                   int sp, unsigned long long r, Desc *d) {
   r = lcg(r);
   const int W = p.window;
   int b = (int)(r % (unsigned long long)W);
