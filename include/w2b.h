@@ -77,6 +77,7 @@ typedef struct {
   int32_t plain_store; /* fast mode: 1 = racy load/add/store like the reference, 0 = red.add */
   int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
+  int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed */
 } w2b_config;
 
 typedef struct {

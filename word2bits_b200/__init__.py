@@ -76,12 +76,12 @@ class Trainer:
 
     def __init__(self, corpus=None, *, size=100, window=5, negative=5, bitlevel=1, alpha=0.05, sample=1e-3,
                  reg=0.0, iter=5, threads=None, device=0, mode=MODE_FAST, shard_range=None, group=0,
-                 plain_store=0, resident=True, vocab_size=None, init=True, kernel=0, ring_rows=0):
+                 plain_store=0, resident=True, vocab_size=None, init=True, kernel=0, ring_rows=0, ring_serial=0):
         V = corpus.vocab_size if corpus is not None else vocab_size
         cfg = _lib.Config(vocab_size=V, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
                           alpha=alpha, sample=sample, reg=reg, iter=iter, num_shards=threads or 1,
                           shard_begin=0, shard_end=0, device=device, mode=mode, group=group,
-                          plain_store=plain_store, kernel=kernel, ring_rows=ring_rows)
+                          plain_store=plain_store, kernel=kernel, ring_rows=ring_rows, ring_serial=ring_serial)
         if threads is None:
             n = C.c_int(0)
             check(lib.w2b_suggest_shards(C.byref(cfg), C.byref(n)))

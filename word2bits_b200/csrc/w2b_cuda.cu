@@ -236,6 +236,7 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.shard_base = 0;
   p.train = 1;
   p.plain_store = c->cfg.plain_store;
+  p.serial = c->cfg.ring_serial;
   p.wca_scale = c->nranks;
   return p;
 }

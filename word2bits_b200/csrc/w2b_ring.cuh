@@ -197,11 +197,9 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       ++iters;
       // descriptor slot must have been consumed by every consumer warp
       const int slot = q % kND;
-      if (q >= kND) {
+      if (q >= kND || p.serial) {
         for (;;) {
-          int mn = 0x7fffffff;
-          for (int w = 0; w < ncw; ++w) mn = min(mn, ctl->prog[w]);
-          if (q - mn < kND) break;
+          if (q - ctl->prog[0] < (p.serial ? 1 : kND)) break;
           __nanosleep(64);
         }
       }
@@ -240,9 +238,7 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
           continue;
         }
         for (;;) {
-          int mn = 0x7fffffff;
-          for (int w = 0; w < ncw; ++w) mn = min(mn, ctl->vrel[w]);
-          if (v_alloc + ng - mn <= nv) break;
+          if (v_alloc + ng - ctl->vrel[0] <= nv) break;
           __nanosleep(64);
         }
         if (lane == 0) mbar_expect_tx(&ctl->vbar[slot][gi], (unsigned)ng * rowb);
@@ -259,9 +255,7 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       const int slot = q % kND;
       if (q >= kND) {
         for (;;) {
-          int mn = 0x7fffffff;
-          for (int w = 0; w < ncw; ++w) mn = min(mn, ctl->prog[w]);
-          if (q - mn < kND) break;
+          if (q - ctl->prog[0] < kND) break;
           __nanosleep(64);
         }
       }
@@ -286,15 +280,17 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
   } else {
     // ============================================================== consumer warps
     const bool active = tid < p.ncol;
-    const int colb = tid * 16;                       // byte offset of this thread's float4 in a row
-    const int chunk0 = warp * 512;                   // this warp's column chunk (bytes)
-    const int chunkb = max(0, min(32, p.ncol - warp * 32)) * 16;
+    const int colb = tid * 16;  // byte offset of this thread's float4 in a row
     QParams qp;
     qp.bits = p.bitlevel;
     qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
     double loss = 0.0;
     int rb = 0;
-    int rel = 0, pending = 0;  // lane 0: v slots released / committed-but-unconfirmed
+    // issuer (tid 0) bookkeeping: the v group whose deltas are written but not yet issued,
+    // and the slots committed to the TMA but not yet confirmed read
+    int iss_ng = 0, iss_vs = 0, iss_t0 = 0;
+    const RingDesc *iss_d = nullptr;
+    int rel = 0, unconfirmed = 0;
     for (int q = 0;; ++q) {
       const int slot = q % kND;
       const unsigned par = (unsigned)((q / kND) & 1);
@@ -349,9 +345,24 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
           }
         }
         consumer_bar(nct);
-        if (g0 == 0 && tid == 0) {  // every consumer is past the context phase: u slots are free
-          __threadfence_block();
-          ctl->urel = ctl->urel + cw;
+        // Every consumer is past (a) the context phase of this position when g0 == 0 and
+        // (b) its delta writes of the previous group: the issuer hands that group to the TMA.
+        if (tid == 0) {
+          if (g0 == 0) ctl->urel = ctl->urel + cw;
+          if (iss_ng) {
+            for (int k = 0; k < iss_ng; ++k) {
+              int s = iss_vs + k; if (s >= nv) s -= nv;
+              float *dst = p.v + (long long)iss_d->tg[iss_t0 + k] * p.D;
+              if (p.plain_store) bulk_store(dst, vring + (size_t)s * rowb, rowb);
+              else bulk_reduce_add(dst, vring + (size_t)s * rowb, rowb);
+            }
+            bulk_commit();
+            bulk_wait_read<1>();  // all but the group just committed have left shared memory
+            rel += unconfirmed;
+            unconfirmed = iss_ng;
+            iss_ng = 0;
+            ctl->vrel[0] = rel;
+          }
         }
         if (warp == 0 && lane < ng) {  // reported loss (:480-483), one lane per target
           float f = 0.f;
@@ -379,24 +390,13 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
             }
           }
         }
+        fence_async_smem();  // generic-proxy writes above -> visible to the TMA after the next barrier
         rb ^= 1;
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0 && chunkb > 0) {
-          for (int k = 0; k < ng; ++k) {
-            int s = vs + k; if (s >= nv) s -= nv;
-            float *dst = p.v + (long long)d->tg[g0 + k] * p.D + (chunk0 >> 2);
-            const void *src = vring + (size_t)s * rowb + chunk0;
-            if (p.plain_store) bulk_store(dst, src, (unsigned)chunkb);
-            else bulk_reduce_add(dst, src, (unsigned)chunkb);
-          }
-          bulk_commit();
-          bulk_wait_read<1>();  // everything but the group just committed has left shared memory
-        }
-        if (lane == 0) {
-          rel += pending;
-          pending = ng;
-          ctl->vrel[warp] = rel;
+        if (tid == 0) {
+          iss_ng = ng;
+          iss_vs = vs;
+          iss_t0 = g0;
+          iss_d = d;
         }
         vs += ng; if (vs >= nv) vs -= nv;
       }
@@ -404,23 +404,32 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       unsigned char *eb = errbuf + (size_t)(q & 1) * rowb;
       if (active) *reinterpret_cast<float4 *>(eb + colb) = make_float4(err[0], err[1], err[2], err[3]);
       fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (chunkb > 0) {
-          for (int k = 0; k < cw; ++k)
-            bulk_reduce_add(p.u + (long long)d->ctx[k] * p.D + (chunk0 >> 2), eb + chunk0, (unsigned)chunkb);
-          bulk_commit();
-          bulk_wait_read<1>();
+      consumer_bar(nct);
+      if (tid == 0) {
+        for (int k = 0; k < iss_ng; ++k) {  // last target group of the position
+          int s = iss_vs + k; if (s >= nv) s -= nv;
+          float *dst = p.v + (long long)iss_d->tg[iss_t0 + k] * p.D;
+          if (p.plain_store) bulk_store(dst, vring + (size_t)s * rowb, rowb);
+          else bulk_reduce_add(dst, vring + (size_t)s * rowb, rowb);
         }
-        rel += pending;
-        pending = 0;
-        ctl->vrel[warp] = rel;
+        for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)d->ctx[k] * p.D, eb, rowb);
+        bulk_commit();
+        if (p.serial) {
+          bulk_wait_all();  // debug: all updates of this position are in L2 before the next one is fetched
+          rel += unconfirmed + iss_ng;
+          unconfirmed = 0;
+        } else {
+          bulk_wait_read<1>();
+          rel += unconfirmed;
+          unconfirmed = iss_ng;
+        }
+        iss_ng = 0;
+        ctl->vrel[0] = rel;
         __threadfence_block();
-        ctl->prog[warp] = q + 1;  // done with this descriptor
+        ctl->prog[0] = q + 1;  // every consumer has read this descriptor (it passed the barrier above)
       }
-      __syncwarp();
     }
-    if (lane == 0) bulk_wait_all();
+    if (tid == 0) bulk_wait_all();
     if (warp == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
