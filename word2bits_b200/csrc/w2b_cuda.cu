@@ -167,41 +167,61 @@ static apply_fn pick_apply(const w2b_ctx *c) {
   return nullptr;
 }
 
-typedef void (*ring_fn)(TrainParams, int, int);
-static ring_fn pick_ring(const w2b_ctx *c) {
-  const int bm = bm_of(c->cfg.bitlevel);
-#define W2B_PICK(BM) \
-  if (bm == BM) return c->ring_g == 7 ? (ring_fn)train_ring_kernel<BM, 7> : (ring_fn)train_ring_kernel<BM, 13>;
-  W2B_PICK(0) W2B_PICK(1) W2B_PICK(2) W2B_PICK(9)
-#undef W2B_PICK
+typedef void (*ring_fn)(TrainParams, int, int, int);
+template <int BM>
+static ring_fn ring_by_nj(int nj) {
+  switch (nj) {
+    case 1: return train_ring_kernel<BM, 1>;
+    case 2: return train_ring_kernel<BM, 2>;
+    case 3: return train_ring_kernel<BM, 3>;
+    case 4: return train_ring_kernel<BM, 4>;
+    case 5: return train_ring_kernel<BM, 5>;
+    case 6: return train_ring_kernel<BM, 6>;
+    case 7: return train_ring_kernel<BM, 7>;
+    case 8: return train_ring_kernel<BM, 8>;
+  }
   return nullptr;
 }
+static ring_fn pick_ring(const w2b_ctx *c) {
+  const int nj = (c->ncol + 31) / 32;
+  switch (bm_of(c->cfg.bitlevel)) {
+    case 0: return ring_by_nj<0>(nj);
+    case 1: return ring_by_nj<1>(nj);
+    case 2: return ring_by_nj<2>(nj);
+    default: return ring_by_nj<9>(nj);
+  }
+}
 
-// Ring kernel geometry: u-ring holds one full window plus slack, v-ring up to 4 groups,
-// shrunk to what 227 KB of shared memory allows (>= 2 groups or the ring kernel is off).
+// Ring kernel geometry: the u-ring holds one full window plus slack, the v-ring as many
+// rows as 227 KB of shared memory allow (up to 4 groups).  Lower bounds: 2 groups, and
+// ncw + G + 1 rows so that a slot awaiting its read confirmation can never be needed by
+// the group that contains the confirming warp's next row.
 static void plan_ring(w2b_ctx *c) {
   c->ring = false;
   if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
-  const int G = (c->cfg.negative + 1 <= 7) ? 7 : 13;
+  const int nt = c->cfg.negative + 1;
+  int G = (c->cfg.group > 0 && c->cfg.group <= 16) ? c->cfg.group : 13;
+  if ((nt + G - 1) / G > kMaxGrp) G = (nt + kMaxGrp - 1) / kMaxGrp;
   const int ncw = (c->ncol + 31) / 32;
-  if (ncw + 1 > 16) return;  // kernel is compiled for <= 512 threads (D <= 1920)
+  if (ncw > 8) return;  // kernels are instantiated for D <= 1024
   const long long D = c->cfg.layer1_size;
   const size_t cap = 227 * 1024;
+  const int nv_min = std::max(2 * G, ncw + G + 1);
   int nu = 2 * c->cfg.window + 4;
-  int nv = c->cfg.ring_rows > 0 ? c->cfg.ring_rows : 4 * G;
-  while (nv >= 2 * G && ring_layout(D, nu, nv).total > cap) --nv;
-  if (nv < 2 * G) {
+  int nv = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
+  while (nv >= nv_min && ring_layout(D, nu, nv, ncw).total > cap) --nv;
+  if (nv < nv_min) {
     nu = 2 * c->cfg.window;
     nv = 4 * G;
-    while (nv >= 2 * G && ring_layout(D, nu, nv).total > cap) --nv;
-    if (nv < 2 * G) return;
+    while (nv >= nv_min && ring_layout(D, nu, nv, ncw).total > cap) --nv;
+    if (nv < nv_min) return;
   }
   c->ring = true;
   c->ring_g = G;
   c->ring_nu = nu;
   c->ring_nv = nv;
   c->ring_threads = (ncw + 1) * 32;
-  c->ring_smem = ring_layout(D, nu, nv).total;
+  c->ring_smem = ring_layout(D, nu, nv, ncw).total;
 }
 
 static size_t dyn_smem(const w2b_ctx *c) {
@@ -322,11 +342,7 @@ extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
   c->ncol = (int)((cfg->layer1_size + c->vec - 1) / c->vec);
   c->threads = std::max(32, (c->ncol + 31) / 32 * 32);
   c->group = cfg->group ? cfg->group : (cfg->negative + 1 > 9 ? 13 : (cfg->negative + 1 > 5 ? 9 : 5));
-  if (c->group != 5 && c->group != 9 && c->group != 13) {
-    delete c;
-    w2b_set_error("group must be 0, 5, 9 or 13");
-    return W2B_EINVAL;
-  }
+  if (c->group != 5 && c->group != 9 && c->group != 13) c->group = 9;  // register kernel instantiations
   plan_ring(c);
   CK(cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
@@ -498,7 +514,7 @@ static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
     CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
     CK(cudaEventRecord(c->ev0, c->stream));
     p.shard_base = 0;
-    rf<<<c->nlocal, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv);
+    rf<<<c->nlocal, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv, c->ring_g);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,

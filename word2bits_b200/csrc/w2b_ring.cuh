@@ -5,25 +5,33 @@
 //   * producer warp (last warp): the reference's control flow — learning-rate schedule
 //     (:379-393), sentence builder + sub-sampling (:394-413), shard termination
 //     (:414-423), window draw and negative draws (:428-460) — and, for every position,
-//     one cp.async.bulk (TMA) copy per embedding row into shared-memory rings:
-//     context rows of u into the u-ring, target rows of v (group by group) into the
-//     v-ring.  It runs ahead of the arithmetic by as many rows as the rings hold, which
-//     is what keeps tens of kB per SM in flight on a latency-bound gather.
-//   * consumer warps: thread t owns columns [4t, 4t+4) of every row.  Context average
-//     (:431-449) and error accumulator (:486-488) are private registers; the dim-D dot
-//     (:461-471) is a warp-shuffle tree plus one shared-memory hop per target group.
-//     Updates leave through the TMA as well: each warp overwrites its 512-byte column
-//     chunk of a landed v row with g*context_avg (:489-491) and issues
-//     cp.reduce.async.bulk.global.add.f32 from that slot; the accumulated error goes to
-//     every context row of u (:494-503) the same way from a double-buffered staging row.
-// Flow control: mbarriers (complete_tx) for "rows landed", monotonic shared counters for
-// "slots free again" (published after cp.async.bulk.wait_group.read).
+//     one cp.async.bulk (TMA) copy per embedding row into shared-memory rings: context
+//     rows of u into the u-ring, target rows of v (group by group) into the v-ring.  It
+//     runs ahead of the arithmetic by as many rows as the rings hold, which is what keeps
+//     tens of kB per SM in flight on a latency-bound gather.
+//   * consumer warps, two phases per position:
+//       context phase  (:431-449) thread t owns float4 column t of the cw landed u rows:
+//                      quantize, sum in row order, divide by cw, publish context_avg in
+//                      shared memory.
+//       target phase   (:450-492) one WARP per landed v row (rows dealt round-robin):
+//                      lane l holds float4 columns l, l+32, ... of context_avg in
+//                      registers, reads the row, quantizes, dots (4 independent FMA chains
+//                      + one 5-step shuffle all-reduce per row), gets g from the expTable,
+//                      accumulates g*quantize(v) into its private error registers (:487),
+//                      overwrites the row in place with g*context_avg (:490) and hands the
+//                      slot to the TMA: cp.reduce.async.bulk.global.add.f32, one 4*D-byte
+//                      atomic-add scatter per row.
+//     The per-warp error partials are summed through shared memory into a staging row that
+//     is scattered to every context row of u (:494-503) with the same bulk reduce.
+// Flow control: mbarriers (complete_tx) for "rows landed"; per-slot release counters
+// (bumped after cp.async.bulk.wait_group.read) for "slot free again".
 //
 // Ordering semantics: rows of position p+1.. are fetched before position p's updates
 // land, so a context row shared by neighbouring positions is read one or two updates
 // stale; no update is ever lost (all scatters are atomic adds in L2).  This is the same
-// class of staleness the reference's Hogwild threads have (SURVEY §7 "hard parts");
-// DESIGN.md quantifies it and tests/test_gpu_parity.py holds it to the L3 bars.
+// class of staleness the reference's Hogwild threads have (SURVEY section 7 "hard parts");
+// ring_serial=1 turns the prefetch off for parity work.  DESIGN.md quantifies the effect
+// and tests/test_gpu_parity.py holds it to the L3 bars.
 #pragma once
 #include "w2b_kernels.cuh"
 
@@ -43,10 +51,8 @@ struct RingDesc {
 struct RingCtl {
   unsigned long long ubar[kND];
   unsigned long long vbar[kND][kMaxGrp];
-  volatile int prog[32];  // per consumer warp: positions finished
-  volatile int vrel[32];  // per consumer warp: v slots released
-  volatile int urel;      // u slots released
-  float red[2][16][32];   // [buffer][target in group][warp] partial dots
+  volatile int prog;  // positions whose descriptor is no longer needed
+  volatile int urel;  // u slots released
   double loss_out;
 };
 
@@ -101,9 +107,9 @@ __device__ __forceinline__ void consumer_bar(int nthreads) {
 // Shared-memory carve-up (host and device agree through these helpers).
 struct RingLayout {
   int rowb, nu, nv;
-  size_t off_uring, off_vring, off_err, off_desc, off_sen, off_ctl, total;
+  size_t off_uring, off_vring, off_err, off_avg, off_errp, off_rc, off_desc, off_sen, off_ctl, total;
 };
-__host__ __device__ inline RingLayout ring_layout(long long D, int nu, int nv) {
+__host__ __device__ inline RingLayout ring_layout(long long D, int nu, int nv, int ncw) {
   RingLayout L;
   L.rowb = (int)(D * 4);
   L.nu = nu;
@@ -111,7 +117,10 @@ __host__ __device__ inline RingLayout ring_layout(long long D, int nu, int nv) {
   size_t o = 0;
   L.off_uring = o; o += (size_t)nu * L.rowb;
   L.off_vring = o; o += (size_t)nv * L.rowb;
-  L.off_err = o;   o += (size_t)2 * L.rowb;
+  L.off_err = o;   o += (size_t)2 * L.rowb;      // staging rows for the u scatter (double-buffered)
+  L.off_avg = o;   o += (size_t)L.rowb;          // context_avg
+  L.off_errp = o;  o += (size_t)ncw * L.rowb;    // per-warp error partials
+  L.off_rc = o;    o += sizeof(int) * (size_t)nv;  // per-slot release counters
   o = (o + 15) & ~(size_t)15;
   L.off_desc = o;  o += sizeof(RingDesc) * kND;
   L.off_sen = o;   o += sizeof(int) * kMaxS;
@@ -121,23 +130,26 @@ __host__ __device__ inline RingLayout ring_layout(long long D, int nu, int nv) {
   return L;
 }
 
-template <int BM, int G>
-__global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int nu, int nv) {
+template <int BM, int NJ>
+__global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const RingLayout L = ring_layout(p.D, nu, nv);
-  unsigned char *uring = smem + L.off_uring;
-  unsigned char *vring = smem + L.off_vring;
-  unsigned char *errbuf = smem + L.off_err;
-  RingDesc *desc = reinterpret_cast<RingDesc *>(smem + L.off_desc);
-  int *s_sen = reinterpret_cast<int *>(smem + L.off_sen);
-  RingCtl *ctl = reinterpret_cast<RingCtl *>(smem + L.off_ctl);
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
   const int nct = ncw * 32;
+  const RingLayout L = ring_layout(p.D, nu, nv, ncw);
+  unsigned char *uring = smem + L.off_uring;
+  unsigned char *vring = smem + L.off_vring;
+  unsigned char *errbuf = smem + L.off_err;
+  float4 *s_avg = reinterpret_cast<float4 *>(smem + L.off_avg);
+  float4 *s_errp = reinterpret_cast<float4 *>(smem + L.off_errp);
+  volatile int *s_rc = reinterpret_cast<volatile int *>(smem + L.off_rc);
+  RingDesc *desc = reinterpret_cast<RingDesc *>(smem + L.off_desc);
+  int *s_sen = reinterpret_cast<int *>(smem + L.off_sen);
+  RingCtl *ctl = reinterpret_cast<RingCtl *>(smem + L.off_ctl);
   ShardState *shp = p.shards + p.shard_base + blockIdx.x;
   if (shp->done) return;
   const unsigned rowb = (unsigned)L.rowb;
+  const int D4 = p.ncol;  // float4 columns per row
 
   if (tid == 0) {
     for (int i = 0; i < kND; ++i) {
@@ -145,13 +157,11 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       for (int g = 0; g < kMaxGrp; ++g) mbar_init(&ctl->vbar[i][g], 1);
     }
     ctl->urel = 0;
+    ctl->prog = 0;
     ctl->loss_out = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 32) {
-    ctl->prog[tid] = 0;
-    ctl->vrel[tid] = 0;
-  }
+  for (int i = tid; i < nv; i += blockDim.x) s_rc[i] = 0;
   __syncthreads();
 
   if (warp == ncw) {
@@ -166,7 +176,8 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
     unsigned long long n_pos = 0, n_ctx = 0, n_tgt = 0;
     int q = 0;             // positions enqueued
     const int ngmax = (p.negative + 1 + G - 1) / G;
-    int u_alloc = 0, v_alloc = 0;
+    int u_alloc = 0;
+    int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
     for (;;) {
       if (wc - last > 10000) {  // :379-393
         if (lane == 0) {
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       const int slot = q % kND;
       if (q >= kND || p.serial) {
         for (;;) {
-          if (q - ctl->prog[0] < (p.serial ? 1 : kND)) break;
+          if (q - ctl->prog < (p.serial ? 1 : kND)) break;
           __nanosleep(64);
         }
       }
@@ -237,15 +248,14 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
           if (lane == 0) mbar_expect_tx(&ctl->vbar[slot][gi], 0);
           continue;
         }
-        for (;;) {
-          if (v_alloc + ng - ctl->vrel[0] <= nv) break;
-          __nanosleep(64);
-        }
         if (lane == 0) mbar_expect_tx(&ctl->vbar[slot][gi], (unsigned)ng * rowb);
         __syncwarp();
-        if (lane < ng)
-          bulk_load(vring + (size_t)((v_alloc + lane) % nv) * rowb, p.v + (long long)d->tg[g0 + lane] * p.D, rowb,
-                    &ctl->vbar[slot][gi]);
+        if (lane < ng) {  // each lane waits for its own slot to have been released by its last user
+          const int vi = v_alloc + lane, sl = vi % nv, uses = vi / nv;
+          while (s_rc[sl] < uses) __nanosleep(32);
+          bulk_load(vring + (size_t)sl * rowb, p.v + (long long)d->tg[g0 + lane] * p.D, rowb, &ctl->vbar[slot][gi]);
+        }
+        __syncwarp();
         v_alloc += ng;
       }
       ++q;
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       const int slot = q % kND;
       if (q >= kND) {
         for (;;) {
-          if (q - ctl->prog[0] < kND) break;
+          if (q - ctl->prog < kND) break;
           __nanosleep(64);
         }
       }
@@ -279,162 +289,145 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
     }
   } else {
     // ============================================================== consumer warps
-    const bool active = tid < p.ncol;
-    const int colb = tid * 16;  // byte offset of this thread's float4 in a row
     QParams qp;
     qp.bits = p.bitlevel;
     qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
     double loss = 0.0;
-    int rb = 0;
-    // issuer (tid 0) bookkeeping: the v group whose deltas are written but not yet issued,
-    // and the slots committed to the TMA but not yet confirmed read
-    int iss_ng = 0, iss_vs = 0, iss_t0 = 0;
-    const RingDesc *iss_d = nullptr;
-    int rel = 0, unconfirmed = 0;
+    int prev_slot = -1;                 // lane 0: slot whose reduce is committed but not yet confirmed read
+    const RingDesc *pend_u = nullptr;   // tid 0: position whose u scatter is staged but not yet issued
+    int pend_q = 0;
+    bool lane_on[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) lane_on[j] = (j * 32 + lane) < D4;
+
     for (int q = 0;; ++q) {
       const int slot = q % kND;
       const unsigned par = (unsigned)((q / kND) & 1);
       mbar_wait(&ctl->ubar[slot], par);
       const RingDesc *d = &desc[slot];
-      if (d->exit_flag) break;
-      const int cw = d->cw, nt = d->nt, us0 = d->us0;
-      int vs = d->vs0;
+      const bool fin = d->exit_flag != 0;
+      const int cw = d->cw, nt = d->nt, us0 = d->us0, vs0 = d->vs0;
       const float alpha = d->alpha;
-      // ---- context gather + quantize + average (:431-449)
-      float avg[4] = {0.f, 0.f, 0.f, 0.f};
-      if (active) {
+      // ---- context phase: gather + quantize + average (:431-449), thread per float4 column
+      if (!fin && tid < D4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int k = 0; k < cw; ++k) {
           int s = us0 + k; if (s >= nu) s -= nu;
-          const float4 x = *reinterpret_cast<const float4 *>(uring + (size_t)s * rowb + colb);
-          avg[0] = __fadd_rn(avg[0], quant<BM>(x.x, qp));
-          avg[1] = __fadd_rn(avg[1], quant<BM>(x.y, qp));
-          avg[2] = __fadd_rn(avg[2], quant<BM>(x.z, qp));
-          avg[3] = __fadd_rn(avg[3], quant<BM>(x.w, qp));
+          const float4 x = *reinterpret_cast<const float4 *>(uring + (size_t)s * rowb + tid * 16);
+          a0 = __fadd_rn(a0, quant<BM>(x.x, qp));
+          a1 = __fadd_rn(a1, quant<BM>(x.y, qp));
+          a2 = __fadd_rn(a2, quant<BM>(x.z, qp));
+          a3 = __fadd_rn(a3, quant<BM>(x.w, qp));
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) avg[i] = __fdiv_rn(avg[i], (float)cw);
+        const float fcw = (float)cw;
+        s_avg[tid] = make_float4(__fdiv_rn(a0, fcw), __fdiv_rn(a1, fcw), __fdiv_rn(a2, fcw), __fdiv_rn(a3, fcw));
       }
-      float err[4] = {0.f, 0.f, 0.f, 0.f};
-      // ---- targets (:450-492), G rows per step
-      for (int g0 = 0, gi = 0; g0 < nt; g0 += G, ++gi) {
-        const int ng = min(G, nt - g0);
-        mbar_wait(&ctl->vbar[slot][gi], par);
-        float4 x[G];
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-          if (k < ng && active) {
-            int s = vs + k; if (s >= nv) s -= nv;
-            x[k] = *reinterpret_cast<const float4 *>(vring + (size_t)s * rowb + colb);
-          } else {
-            x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-          if (k < ng) {
-            float pd = 0.f;
-            if (active) {
-              pd = fmaf(avg[0], quant<BM>(x[k].x, qp), pd);
-              pd = fmaf(avg[1], quant<BM>(x[k].y, qp), pd);
-              pd = fmaf(avg[2], quant<BM>(x[k].z, qp), pd);
-              pd = fmaf(avg[3], quant<BM>(x[k].w, qp), pd);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) pd += __shfl_xor_sync(kFull, pd, o);
-            if (lane == 0) ctl->red[rb][k][warp] = pd;
-          }
-        }
-        consumer_bar(nct);
-        // Every consumer is past (a) the context phase of this position when g0 == 0 and
-        // (b) its delta writes of the previous group: the issuer hands that group to the TMA.
-        if (tid == 0) {
-          if (g0 == 0) ctl->urel = ctl->urel + cw;
-          if (iss_ng) {
-            for (int k = 0; k < iss_ng; ++k) {
-              int s = iss_vs + k; if (s >= nv) s -= nv;
-              float *dst = p.v + (long long)iss_d->tg[iss_t0 + k] * p.D;
-              if (p.plain_store) bulk_store(dst, vring + (size_t)s * rowb, rowb);
-              else bulk_reduce_add(dst, vring + (size_t)s * rowb, rowb);
-            }
-            bulk_commit();
-            bulk_wait_read<1>();  // all but the group just committed have left shared memory
-            rel += unconfirmed;
-            unconfirmed = iss_ng;
-            iss_ng = 0;
-            ctl->vrel[0] = rel;
-          }
-        }
-        if (warp == 0 && lane < ng) {  // reported loss (:480-483), one lane per target
-          float f = 0.f;
-          for (int w = 0; w < ncw; ++w) f += ctl->red[rb][lane][w];
-          float dp = (g0 + lane == 0) ? f : -f;
-          loss += (double)logf(sigmoid_report(dp));
-        }
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-          if (k < ng) {
-            float f = 0.f;
-            for (int w = 0; w < ncw; ++w) f += ctl->red[rb][k][w];  // fixed order: deterministic
-            const float g = grad_scalar(f, (g0 + k == 0) ? 1 : 0, alpha, p.exptab);
-            if (active) {
-              err[0] = fmaf(g, quant<BM>(x[k].x, qp), err[0]);  // :487, old v
-              err[1] = fmaf(g, quant<BM>(x[k].y, qp), err[1]);
-              err[2] = fmaf(g, quant<BM>(x[k].z, qp), err[2]);
-              err[3] = fmaf(g, quant<BM>(x[k].w, qp), err[3]);
-              float4 dv = make_float4(g * avg[0], g * avg[1], g * avg[2], g * avg[3]);  // :490
-              if (p.plain_store) {
-                dv.x += x[k].x; dv.y += x[k].y; dv.z += x[k].z; dv.w += x[k].w;
-              }
-              int s = vs + k; if (s >= nv) s -= nv;
-              *reinterpret_cast<float4 *>(vring + (size_t)s * rowb + colb) = dv;  // in place over the landed row
-            }
-          }
-        }
-        fence_async_smem();  // generic-proxy writes above -> visible to the TMA after the next barrier
-        rb ^= 1;
-        if (tid == 0) {
-          iss_ng = ng;
-          iss_vs = vs;
-          iss_t0 = g0;
-          iss_d = d;
-        }
-        vs += ng; if (vs >= nv) vs -= nv;
-      }
-      // ---- scatter the error to every context row (:494-503) from a staging row
-      unsigned char *eb = errbuf + (size_t)(q & 1) * rowb;
-      if (active) *reinterpret_cast<float4 *>(eb + colb) = make_float4(err[0], err[1], err[2], err[3]);
-      fence_async_smem();
-      consumer_bar(nct);
+      consumer_bar(nct);  // A: context_avg visible; u rows consumed; previous staging row complete
       if (tid == 0) {
-        for (int k = 0; k < iss_ng; ++k) {  // last target group of the position
-          int s = iss_vs + k; if (s >= nv) s -= nv;
-          float *dst = p.v + (long long)iss_d->tg[iss_t0 + k] * p.D;
-          if (p.plain_store) bulk_store(dst, vring + (size_t)s * rowb, rowb);
-          else bulk_reduce_add(dst, vring + (size_t)s * rowb, rowb);
+        if (!fin) ctl->urel = ctl->urel + cw;
+        if (pend_u) {  // scatter of the previous position's error to its context rows (:494-503)
+          const unsigned char *eb = errbuf + (size_t)(pend_q & 1) * rowb;
+          for (int k = 0; k < pend_u->cw; ++k) bulk_reduce_add(p.u + (long long)pend_u->ctx[k] * p.D, eb, rowb);
+          bulk_commit();
+          pend_u = nullptr;
+          __threadfence_block();
+          ctl->prog = pend_q + 1;  // that descriptor may be recycled
         }
-        for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)d->ctx[k] * p.D, eb, rowb);
-        bulk_commit();
-        if (p.serial) {
-          bulk_wait_all();  // debug: all updates of this position are in L2 before the next one is fetched
-          rel += unconfirmed + iss_ng;
-          unconfirmed = 0;
-        } else {
-          bulk_wait_read<1>();
-          rel += unconfirmed;
-          unconfirmed = iss_ng;
+      }
+      if (fin) break;
+      // ---- target phase (:450-492): one warp per landed v row
+      float4 a[NJ], e[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        a[j] = lane_on[j] ? s_avg[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int i = warp; i < nt; i += ncw) {
+        mbar_wait(&ctl->vbar[slot][i / G], par);
+        int s = vs0 + i; if (s >= nv) s -= nv;
+        unsigned char *row = vring + (size_t)s * rowb;
+        float4 x[NJ];
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (lane_on[j]) {
+            const float4 t = *reinterpret_cast<const float4 *>(row + (j * 32 + lane) * 16);
+            x[j] = make_float4(quant<BM>(t.x, qp), quant<BM>(t.y, qp), quant<BM>(t.z, qp), quant<BM>(t.w, qp));
+          } else {
+            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          d0 = fmaf(a[j].x, x[j].x, d0);
+          d1 = fmaf(a[j].y, x[j].y, d1);
+          d2 = fmaf(a[j].z, x[j].z, d2);
+          d3 = fmaf(a[j].w, x[j].w, d3);
         }
-        iss_ng = 0;
-        ctl->vrel[0] = rel;
-        __threadfence_block();
-        ctl->prog[0] = q + 1;  // every consumer has read this descriptor (it passed the barrier above)
+        float f = (d0 + d1) + (d2 + d3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(kFull, f, o);  // all lanes get the same sum
+        const float g = grad_scalar(f, i == 0 ? 1 : 0, alpha, p.exptab);
+        if (lane == 0) loss += (double)logf(sigmoid_report(i == 0 ? f : -f));  // :480-483
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          e[j].x = fmaf(g, x[j].x, e[j].x);  // :487, quantized OLD v
+          e[j].y = fmaf(g, x[j].y, e[j].y);
+          e[j].z = fmaf(g, x[j].z, e[j].z);
+          e[j].w = fmaf(g, x[j].w, e[j].w);
+          if (lane_on[j])  // :490 — the update g*context_avg replaces the landed row in its slot
+            *reinterpret_cast<float4 *>(row + (j * 32 + lane) * 16) =
+                make_float4(g * a[j].x, g * a[j].y, g * a[j].z, g * a[j].w);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_reduce_add(p.v + (long long)d->tg[i] * p.D, row, rowb);
+          bulk_commit();
+          if (p.serial) bulk_wait_all(); else bulk_wait_read<1>();
+          // everything this lane committed before the reduce above has left shared memory
+          if (prev_slot >= 0) s_rc[prev_slot] = s_rc[prev_slot] + 1;
+          prev_slot = s;
+          if (p.serial) { s_rc[s] = s_rc[s] + 1; prev_slot = -1; }
+        }
+        __syncwarp();
+      }
+      if (lane == 0 && prev_slot >= 0) {  // confirm this warp's last row of the position right away
+        bulk_wait_read<0>();
+        s_rc[prev_slot] = s_rc[prev_slot] + 1;
+        prev_slot = -1;
+      }
+      // ---- error partials -> staging row (:494-503 is issued after the next barrier A)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (lane_on[j]) s_errp[(size_t)warp * D4 + j * 32 + lane] = e[j];
+      consumer_bar(nct);  // B
+      if (tid < D4) {
+        float4 acc = s_errp[tid];
+        for (int w = 1; w < ncw; ++w) {
+          const float4 t = s_errp[(size_t)w * D4 + tid];
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        *reinterpret_cast<float4 *>(errbuf + (size_t)(q & 1) * rowb + tid * 16) = acc;
+      }
+      fence_async_smem();
+      if (tid == 0) { pend_u = d; pend_q = q; }
+      if (p.serial) {  // parity aid: everything of this position lands before the next one is fetched
+        consumer_bar(nct);
+        if (tid == 0) {
+          const unsigned char *eb = errbuf + (size_t)(q & 1) * rowb;
+          for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)d->ctx[k] * p.D, eb, rowb);
+          bulk_commit();
+          bulk_wait_all();
+          pend_u = nullptr;
+          __threadfence_block();
+          ctl->prog = q + 1;
+        }
       }
     }
-    if (tid == 0) bulk_wait_all();
-    if (warp == 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
-      if (lane == 0) shp->loss = shp->loss + loss;
+    if (lane == 0) {
+      bulk_wait_all();
+      atomicAdd(&ctl->loss_out, loss);
     }
+    consumer_bar(nct);
+    if (tid == 0) shp->loss = shp->loss + ctl->loss_out;
   }
 }
 
