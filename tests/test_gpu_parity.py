@@ -310,5 +310,8 @@ def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
     assert abs(lg - lo) <= 1e-3 * abs(lo)
     if b == 0:
         assert du < 5e-3 and dv < 5e-3, (du, dv)
-    else:
-        assert fu > 0.25 and fv > 0.25  # the reference's own builds: 0.26 within 1e-3 at b=2
+    else:  # b=2 is chaotic (level flips feed back): the reference's own two builds agree within
+        # 1e-3 on only 26 % of the elements here, so hold the trajectories to correlation instead
+        cu = np.corrcoef(u.ravel(), m.u.ravel())[0, 1]
+        cv = np.corrcoef(v.ravel(), m.v.ravel())[0, 1]
+        assert cu > 0.9 and cv > 0.9, (cu, cv)
