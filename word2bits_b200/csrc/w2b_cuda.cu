@@ -220,7 +220,7 @@ static void plan_ring(w2b_ctx *c) {
   c->ring_g = G;
   c->ring_nu = nu;
   c->ring_nv = nv;
-  c->ring_threads = (ncw + 1) * 32;
+  c->ring_threads = (ncw + 2) * 32;  // consumers + loader warp + sampler warp
   c->ring_smem = ring_layout(D, nu, nv, ncw).total;
 }
 

@@ -1,30 +1,33 @@
 // Production kernel of the Word2Bits training path for sm_100a: TMA-staged row rings.
 //
 // One CTA = one corpus shard (one reference thread, src/word2bits.cpp:363-516), split
-// into roles:
-//   * producer warp (last warp): the reference's control flow — learning-rate schedule
-//     (:379-393), sentence builder + sub-sampling (:394-413), shard termination
-//     (:414-423), window draw and negative draws (:428-460) — and, for every position,
-//     one cp.async.bulk (TMA) copy per embedding row into shared-memory rings: context
-//     rows of u into the u-ring, target rows of v (group by group) into the v-ring.  It
-//     runs ahead of the arithmetic by as many rows as the rings hold, which is what keeps
-//     tens of kB per SM in flight on a latency-bound gather.
+// into warp roles that communicate through shared memory:
+//   * sampler warp: the reference's control flow — learning-rate schedule (:379-393),
+//     sentence builder + sub-sampling (:394-413), shard termination (:414-423), window
+//     draw and negative draws (:428-460).  Emits one descriptor per trained position
+//     (context ids, target ids).  The unigram-table lookups of position p+1 are issued
+//     while position p's descriptor is being finished (the draws are replayable by LCG
+//     jump-ahead, so nothing depends on the previous lookups).
+//   * loader warp: for every descriptor, one cp.async.bulk (TMA) copy per embedding row
+//     into shared-memory rings — context rows of u into the u-ring, target rows of v
+//     (group by group) into the v-ring.  It runs ahead of the arithmetic by as many rows
+//     as the rings hold, which keeps tens of kB per SM in flight on a latency-bound gather.
 //   * consumer warps, two phases per position:
 //       context phase  (:431-449) thread t owns float4 column t of the cw landed u rows:
-//                      quantize, sum in row order, divide by cw, publish context_avg in
-//                      shared memory.
+//                      quantize, sum in row order, divide by cw, publish context_avg.
 //       target phase   (:450-492) one WARP per landed v row (rows dealt round-robin):
 //                      lane l holds float4 columns l, l+32, ... of context_avg in
 //                      registers, reads the row, quantizes, dots (4 independent FMA chains
-//                      + one 5-step shuffle all-reduce per row), gets g from the expTable,
-//                      accumulates g*quantize(v) into its private error registers (:487),
+//                      + one 5-step shuffle all-reduce per row), takes g from the expTable,
+//                      accumulates g*quantize(v) into private error registers (:487),
 //                      overwrites the row in place with g*context_avg (:490) and hands the
-//                      slot to the TMA: cp.reduce.async.bulk.global.add.f32, one 4*D-byte
-//                      atomic-add scatter per row.
+//                      slot back to the TMA: cp.reduce.async.bulk.global.add.f32, one
+//                      4*D-byte atomic-add scatter per row.
 //     The per-warp error partials are summed through shared memory into a staging row that
 //     is scattered to every context row of u (:494-503) with the same bulk reduce.
 // Flow control: mbarriers (complete_tx) for "rows landed"; per-slot release counters
-// (bumped after cp.async.bulk.wait_group.read) for "slot free again".
+// (bumped after cp.async.bulk.wait_group.read) for "slot free again"; monotonic counters
+// for descriptors.
 //
 // Ordering semantics: rows of position p+1.. are fetched before position p's updates
 // land, so a context row shared by neighbouring positions is read one or two updates
@@ -37,8 +40,8 @@
 
 namespace w2b {
 
-constexpr int kND = 4;       // descriptor ring depth (positions in flight)
-constexpr int kMaxGrp = 8;   // max target groups per position
+constexpr int kND = 8;      // descriptor ring depth (positions in flight)
+constexpr int kMaxGrp = 8;  // max target groups per position
 
 struct RingDesc {
   int cw, nt, exit_flag, us0, vs0;
@@ -51,8 +54,9 @@ struct RingDesc {
 struct RingCtl {
   unsigned long long ubar[kND];
   unsigned long long vbar[kND][kMaxGrp];
-  volatile int prog;  // positions whose descriptor is no longer needed
-  volatile int urel;  // u slots released
+  volatile int desc_ready;  // descriptors published by the sampler
+  volatile int prog;        // positions whose descriptor is no longer needed by the consumers
+  volatile int urel;        // u slots released
   double loss_out;
 };
 
@@ -61,10 +65,10 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -73,23 +77,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
+      "}" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void bulk_reduce_add(void *dst, const void *src_smem, unsigned bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-               "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+__device__ __forceinline__ void bulk_reduce_add(void *dst, unsigned src_smem, unsigned bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem),
                "r"(bytes)
                : "memory");
 }
@@ -103,8 +101,16 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void consumer_bar(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
-// Shared-memory carve-up (host and device agree through these helpers).
+// Shared-memory carve-up (host and device agree through this helper).
 struct RingLayout {
   int rowb, nu, nv;
   size_t off_uring, off_vring, off_err, off_avg, off_errp, off_rc, off_desc, off_sen, off_ctl, total;
@@ -117,9 +123,9 @@ __host__ __device__ inline RingLayout ring_layout(long long D, int nu, int nv, i
   size_t o = 0;
   L.off_uring = o; o += (size_t)nu * L.rowb;
   L.off_vring = o; o += (size_t)nv * L.rowb;
-  L.off_err = o;   o += (size_t)2 * L.rowb;      // staging rows for the u scatter (double-buffered)
-  L.off_avg = o;   o += (size_t)L.rowb;          // context_avg
-  L.off_errp = o;  o += (size_t)ncw * L.rowb;    // per-warp error partials
+  L.off_err = o;   o += (size_t)2 * L.rowb;        // staging rows for the u scatter (double-buffered)
+  L.off_avg = o;   o += (size_t)L.rowb;            // context_avg
+  L.off_errp = o;  o += (size_t)ncw * L.rowb;      // per-warp error partials
   L.off_rc = o;    o += sizeof(int) * (size_t)nv;  // per-slot release counters
   o = (o + 15) & ~(size_t)15;
   L.off_desc = o;  o += sizeof(RingDesc) * kND;
@@ -130,18 +136,26 @@ __host__ __device__ inline RingLayout ring_layout(long long D, int nu, int nv, i
   return L;
 }
 
+// r mod w for 1 <= w <= 64 with 32-bit arithmetic (the window draw, :429).
+__device__ __forceinline__ int mod_small(unsigned long long r, unsigned w) {
+  const unsigned hi = (unsigned)(r >> 32), lo = (unsigned)r;
+  const unsigned two32 = (0xffffffffu % w + 1u) % w;  // 2^32 mod w
+  return (int)(((hi % w) * two32 + lo % w) % w);
+}
+
 template <int BM, int NJ>
-__global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
+__global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
+  const int ncw = (blockDim.x >> 5) - 2;  // consumer warps; then the loader warp, then the sampler warp
   const int nct = ncw * 32;
   const RingLayout L = ring_layout(p.D, nu, nv, ncw);
-  unsigned char *uring = smem + L.off_uring;
-  unsigned char *vring = smem + L.off_vring;
-  unsigned char *errbuf = smem + L.off_err;
-  float4 *s_avg = reinterpret_cast<float4 *>(smem + L.off_avg);
-  float4 *s_errp = reinterpret_cast<float4 *>(smem + L.off_errp);
+  const unsigned s_base = smem_u32(smem);
+  const unsigned uring = s_base + (unsigned)L.off_uring;
+  const unsigned vring = s_base + (unsigned)L.off_vring;
+  const unsigned errbuf = s_base + (unsigned)L.off_err;
+  const unsigned s_avg = s_base + (unsigned)L.off_avg;
+  const unsigned s_errp = s_base + (unsigned)L.off_errp;
   volatile int *s_rc = reinterpret_cast<volatile int *>(smem + L.off_rc);
   RingDesc *desc = reinterpret_cast<RingDesc *>(smem + L.off_desc);
   int *s_sen = reinterpret_cast<int *>(smem + L.off_sen);
@@ -150,12 +164,15 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
   if (shp->done) return;
   const unsigned rowb = (unsigned)L.rowb;
   const int D4 = p.ncol;  // float4 columns per row
+  const unsigned ubar0 = smem_u32(&ctl->ubar[0]);
+  const unsigned vbar0 = smem_u32(&ctl->vbar[0][0]);
 
   if (tid == 0) {
     for (int i = 0; i < kND; ++i) {
       mbar_init(&ctl->ubar[i], 1);
       for (int g = 0; g < kMaxGrp; ++g) mbar_init(&ctl->vbar[i][g], 1);
     }
+    ctl->desc_ready = 0;
     ctl->urel = 0;
     ctl->prog = 0;
     ctl->loss_out = 0.0;
@@ -164,8 +181,8 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
   for (int i = tid; i < nv; i += blockDim.x) s_rc[i] = 0;
   __syncthreads();
 
-  if (warp == ncw) {
-    // ============================================================== producer warp
+  if (warp == ncw + 1) {
+    // ================================================================ sampler warp
     const ShardState sh = *shp;
     unsigned long long r = sh.rng;
     long long cursor = sh.cursor;
@@ -174,19 +191,25 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
     int len = 0, sp = 0, status = 0, done = 0;
     long long iters = 0;
     unsigned long long n_pos = 0, n_ctx = 0, n_tgt = 0;
-    int q = 0;             // positions enqueued
-    const int ngmax = (p.negative + 1 + G - 1) / G;
-    int u_alloc = 0;
-    int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
+    int q = 0;  // descriptors published
+    const int W = p.window, neg = p.negative;
+    const int negl = neg < 32 ? neg : 32;
+    const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
+    const unsigned long long JAn = c_JA[neg], JCn = c_JC[neg];
+    bool have_pre = false;
+    unsigned long long r1_pre = 0, rd_pre = 0;
+    int t_pre = 0;
+    float alpha_c = *(volatile float *)p.alpha;
     for (;;) {
       if (wc - last > 10000) {  // :379-393
-        if (lane == 0) {
-          unsigned long long delta = (unsigned long long)(wc - last) * (unsigned long long)p.wca_scale;
-          long long wca = (long long)(atomicAdd(p.wca, delta) + delta);
-          float a = __fmul_rn(p.starting_alpha, __fsub_rn(1.f, __fdiv_rn((float)wca, p.alpha_denom)));
-          if ((double)a < (double)p.starting_alpha * 0.0001) a = (float)((double)p.starting_alpha * 0.0001);
-          *(volatile float *)p.alpha = a;
-        }
+        unsigned long long delta = (unsigned long long)(wc - last) * (unsigned long long)p.wca_scale;
+        long long wca = 0;
+        if (lane == 0) wca = (long long)(atomicAdd(p.wca, delta) + delta);
+        wca = __shfl_sync(kFull, wca, 0);
+        float a = __fmul_rn(p.starting_alpha, __fsub_rn(1.f, __fdiv_rn((float)wca, p.alpha_denom)));
+        if ((double)a < (double)p.starting_alpha * 0.0001) a = (float)((double)p.starting_alpha * 0.0001);
+        if (lane == 0) *(volatile float *)p.alpha = a;
+        alpha_c = a;
         last = wc;
       }
       if (len == 0) {
@@ -198,6 +221,10 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
         __syncwarp();
         if (status == 2) break;  // slice exhausted mid-sentence: nothing committed
         r = r2; cursor = c2; wc = w2; len = l2; sp = 0;
+        have_pre = false;
+        // the shared learning rate (:53) is re-read once per sentence: other shards move it
+        // every 10k words each, by ~1e-4 relative per update
+        alpha_c = *(volatile float *)p.alpha;
       }
       if (status == 1 || wc > p.shard_word_limit) {  // :414-423
         if (lane == 0) atomicAdd(p.wca, (unsigned long long)(wc - last) * (unsigned long long)p.wca_scale);
@@ -206,77 +233,98 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
         break;
       }
       ++iters;
-      // descriptor slot must have been consumed by every consumer warp
+      // ---- draws of this position (:428-460)
+      unsigned long long r1, rd;
+      int t = 0;
+      if (have_pre) {
+        r1 = r1_pre; rd = rd_pre; t = t_pre;
+      } else {
+        r1 = lcg(r);
+        rd = r1 * JA1 + JC1;
+        if (lane < negl) t = p.table[(rd >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+      }
+      have_pre = false;
+      const int b = mod_small(r1, (unsigned)W);
+      // descriptor slot: free once every consumer is done with position q - kND
       const int slot = q % kND;
-      if (q >= kND || p.serial) {
-        for (;;) {
-          if (q - ctl->prog < (p.serial ? 1 : kND)) break;
-          __nanosleep(64);
+      while (q - ctl->prog >= (p.serial ? 1 : kND)) __nanosleep(32);
+      RingDesc *d = &desc[slot];
+      const int center = len ? s_sen[sp] : -1;
+      int cw = 0;
+      if (len) {
+        for (int a0 = b; a0 < 2 * W + 1 - b; a0 += 32) {
+          const int a = a0 + lane;
+          const int qq = sp - W + a;
+          const bool ok = (a < 2 * W + 1 - b) && (a != W) && qq >= 0 && qq < len;
+          const unsigned m = __ballot_sync(kFull, ok);
+          if (ok) d->ctx[cw + __popc(m & ((1u << lane) - 1))] = s_sen[qq];
+          cw += __popc(m);
         }
       }
-      RingDesc *d = &desc[slot];
-      r = make_position(p, lane, s_sen, len, sp, r, d);
-      __syncwarp();
-      const int cw = d->cw, nt = d->nt;
+      int nt = 0;
+      if (cw) {
+        const unsigned long long r_after = r1 * JAn + JCn;
+        if (sp + 1 < len) {  // next position of the sentence: its draws are already determined
+          r1_pre = lcg(r_after);
+          rd_pre = r1_pre * JA1 + JC1;
+          t_pre = 0;
+          if (lane < negl) t_pre = p.table[(rd_pre >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+          have_pre = true;
+        }
+        if (lane == 0) d->tg[0] = center;
+        nt = 1;
+        {
+          bool ok = lane < negl;
+          int tt = t;
+          if (ok && tt == 0) tt = (int)(rd % (unsigned long long)(p.V - 1)) + 1;  // :457
+          ok = ok && (tt != center);                                                 // :458
+          const unsigned m = __ballot_sync(kFull, ok);
+          if (ok) d->tg[nt + __popc(m & ((1u << lane) - 1))] = tt;
+          nt += __popc(m);
+        }
+        for (int d0 = 33; d0 <= neg; d0 += 32) {  // negative > 32: remaining draws, not prefetched
+          const int k = d0 + lane;
+          bool ok = k <= neg;
+          int tt = 0;
+          if (ok) {
+            const unsigned long long rd2 = lcg_jump(r1, k);
+            tt = p.table[(rd2 >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+            if (tt == 0) tt = (int)(rd2 % (unsigned long long)(p.V - 1)) + 1;
+            ok = (tt != center);
+          }
+          const unsigned m = __ballot_sync(kFull, ok);
+          if (ok) d->tg[nt + __popc(m & ((1u << lane) - 1))] = tt;
+          nt += __popc(m);
+        }
+        r = r_after;
+      } else {
+        r = r1;
+      }
       ++sp;
       if (sp >= len) len = 0;  // :505-509
       if (cw == 0) continue;   // single-word or empty sentence: one window draw, nothing trained
       n_pos += 1; n_ctx += cw; n_tgt += nt;
-      // ---- context rows -> u-ring
-      for (;;) {
-        if (u_alloc + cw - ctl->urel <= nu) break;
-        __nanosleep(64);
-      }
       if (lane == 0) {
-        d->us0 = u_alloc % nu;
-        d->vs0 = v_alloc % nv;
-        d->alpha = *(volatile float *)p.alpha;
+        d->center = center; d->b = b; d->cw = cw; d->nt = nt;
+        d->alpha = alpha_c;
         d->exit_flag = 0;
-        mbar_expect_tx(&ctl->ubar[slot], (unsigned)cw * rowb);
       }
       __syncwarp();
-      for (int k = lane; k < cw; k += 32)
-        bulk_load(uring + (size_t)((u_alloc + k) % nu) * rowb, p.u + (long long)d->ctx[k] * p.D, rowb,
-                  &ctl->ubar[slot]);
-      u_alloc += cw;
-      // ---- target rows -> v-ring, group by group
-      // (every group barrier of the slot is armed for every position, with 0 bytes when the
-      //  position has fewer groups, so that all barriers of a slot stay on the same phase)
-      for (int g0 = 0, gi = 0; gi < ngmax; g0 += G, ++gi) {
-        const int ng = max(0, min(G, nt - g0));
-        if (ng == 0) {
-          if (lane == 0) mbar_expect_tx(&ctl->vbar[slot][gi], 0);
-          continue;
-        }
-        if (lane == 0) mbar_expect_tx(&ctl->vbar[slot][gi], (unsigned)ng * rowb);
-        __syncwarp();
-        if (lane < ng) {  // each lane waits for its own slot to have been released by its last user
-          const int vi = v_alloc + lane, sl = vi % nv, uses = vi / nv;
-          while (s_rc[sl] < uses) __nanosleep(32);
-          bulk_load(vring + (size_t)sl * rowb, p.v + (long long)d->tg[g0 + lane] * p.D, rowb, &ctl->vbar[slot][gi]);
-        }
-        __syncwarp();
-        v_alloc += ng;
-      }
       ++q;
-    }
-    // tell the consumers to stop (after the descriptor slot is free)
-    {
-      const int slot = q % kND;
-      if (q >= kND) {
-        for (;;) {
-          if (q - ctl->prog < kND) break;
-          __nanosleep(64);
-        }
-      }
       if (lane == 0) {
-        desc[slot].exit_flag = 1;
-        desc[slot].cw = 0;
-        desc[slot].nt = 0;
-        mbar_expect_tx(&ctl->ubar[slot], 0);
+        __threadfence_block();
+        ctl->desc_ready = q;
       }
     }
+    // tell the loader (and through it the consumers) to stop
+    while (q - ctl->prog >= kND) __nanosleep(32);
     if (lane == 0) {
+      RingDesc *d = &desc[q % kND];
+      d->exit_flag = 1;
+      d->cw = 0;
+      d->nt = 0;
+      __threadfence_block();
+      ctl->desc_ready = q + 1;
       shp->rng = r;
       shp->cursor = cursor;
       shp->word_count = wc;
@@ -287,46 +335,100 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       shp->n_ctx = sh.n_ctx + n_ctx;
       shp->n_tgt = sh.n_tgt + n_tgt;
     }
+  } else if (warp == ncw) {
+    // ================================================================= loader warp
+    const int ngmax = (p.negative + 1 + G - 1) / G;
+    int u_alloc = 0;
+    int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
+    for (int q = 0;; ++q) {
+      while (ctl->desc_ready <= q) __nanosleep(32);
+      __threadfence_block();
+      const int slot = q % kND;
+      RingDesc *d = &desc[slot];
+      const unsigned ubar = ubar0 + slot * 8;
+      if (d->exit_flag) {
+        if (lane == 0) mbar_expect_tx(ubar, 0);
+        break;
+      }
+      const int cw = d->cw, nt = d->nt;
+      // ---- context rows -> u-ring
+      while (u_alloc + cw - ctl->urel > nu) __nanosleep(32);
+      if (lane == 0) {
+        d->us0 = u_alloc % nu;
+        d->vs0 = v_alloc % nv;
+        mbar_expect_tx(ubar, (unsigned)cw * rowb);
+      }
+      __syncwarp();
+      for (int k = lane; k < cw; k += 32)
+        bulk_load(uring + (unsigned)((u_alloc + k) % nu) * rowb, p.u + (long long)d->ctx[k] * p.D, rowb, ubar);
+      u_alloc += cw;
+      // ---- target rows -> v-ring, group by group.  Every group barrier of the slot is armed
+      // for every position (0 bytes when the position has fewer groups) so that all barriers
+      // of a descriptor slot stay on the same phase.
+      for (int g0 = 0, gi = 0; gi < ngmax; g0 += G, ++gi) {
+        const int ng = max(0, min(G, nt - g0));
+        const unsigned vbar = vbar0 + (slot * kMaxGrp + gi) * 8;
+        if (lane == 0) mbar_expect_tx(vbar, (unsigned)ng * rowb);
+        __syncwarp();
+        if (lane < ng) {  // each lane waits for its own slot to have been released by its last user
+          const int vi = v_alloc + lane, sl = vi % nv, uses = vi / nv;
+          while (s_rc[sl] < uses) __nanosleep(32);
+          bulk_load(vring + (unsigned)sl * rowb, p.v + (long long)d->tg[g0 + lane] * p.D, rowb, vbar);
+        }
+        __syncwarp();
+        v_alloc += ng;
+      }
+    }
   } else {
     // ============================================================== consumer warps
     QParams qp;
     qp.bits = p.bitlevel;
     qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
     double loss = 0.0;
-    int prev_slot = -1;                 // lane 0: slot whose reduce is committed but not yet confirmed read
-    const RingDesc *pend_u = nullptr;   // tid 0: position whose u scatter is staged but not yet issued
+    int prev_slot = -1;                // lane 0: slot whose reduce is committed but not yet confirmed read
+    const RingDesc *pend_u = nullptr;  // tid 0: position whose u scatter is staged but not yet issued
     int pend_q = 0;
-    bool lane_on[NJ];
+    // lane's float4 columns j*32+lane; columns past the row end are clamped for loads and
+    // masked for stores (their context_avg registers are zero, so they add nothing)
+    bool on[NJ];
+    unsigned coff[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) lane_on[j] = (j * 32 + lane) < D4;
+    for (int j = 0; j < NJ; ++j) {
+      const int c = j * 32 + lane;
+      on[j] = c < D4;
+      coff[j] = (unsigned)(on[j] ? c : D4 - 1) * 16u;
+    }
+    const bool col_on = tid < D4;
+    const unsigned colb = (unsigned)(col_on ? tid : 0) * 16u;
 
     for (int q = 0;; ++q) {
       const int slot = q % kND;
       const unsigned par = (unsigned)((q / kND) & 1);
-      mbar_wait(&ctl->ubar[slot], par);
+      mbar_wait(ubar0 + slot * 8, par);
       const RingDesc *d = &desc[slot];
       const bool fin = d->exit_flag != 0;
       const int cw = d->cw, nt = d->nt, us0 = d->us0, vs0 = d->vs0;
       const float alpha = d->alpha;
       // ---- context phase: gather + quantize + average (:431-449), thread per float4 column
-      if (!fin && tid < D4) {
+      if (!fin && col_on) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int s = us0;
         for (int k = 0; k < cw; ++k) {
-          int s = us0 + k; if (s >= nu) s -= nu;
-          const float4 x = *reinterpret_cast<const float4 *>(uring + (size_t)s * rowb + tid * 16);
+          const float4 x = lds128(uring + (unsigned)s * rowb + colb);
           a0 = __fadd_rn(a0, quant<BM>(x.x, qp));
           a1 = __fadd_rn(a1, quant<BM>(x.y, qp));
           a2 = __fadd_rn(a2, quant<BM>(x.z, qp));
           a3 = __fadd_rn(a3, quant<BM>(x.w, qp));
+          if (++s == nu) s = 0;
         }
         const float fcw = (float)cw;
-        s_avg[tid] = make_float4(__fdiv_rn(a0, fcw), __fdiv_rn(a1, fcw), __fdiv_rn(a2, fcw), __fdiv_rn(a3, fcw));
+        sts128(s_avg + colb, make_float4(__fdiv_rn(a0, fcw), __fdiv_rn(a1, fcw), __fdiv_rn(a2, fcw), __fdiv_rn(a3, fcw)));
       }
       consumer_bar(nct);  // A: context_avg visible; u rows consumed; previous staging row complete
       if (tid == 0) {
         if (!fin) ctl->urel = ctl->urel + cw;
         if (pend_u) {  // scatter of the previous position's error to its context rows (:494-503)
-          const unsigned char *eb = errbuf + (size_t)(pend_q & 1) * rowb;
+          const unsigned eb = errbuf + (unsigned)(pend_q & 1) * rowb;
           for (int k = 0; k < pend_u->cw; ++k) bulk_reduce_add(p.u + (long long)pend_u->ctx[k] * p.D, eb, rowb);
           bulk_commit();
           pend_u = nullptr;
@@ -339,23 +441,21 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
       float4 a[NJ], e[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        a[j] = lane_on[j] ? s_avg[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[j] = lds128(s_avg + coff[j]);
+        if (!on[j]) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int i = warp; i < nt; i += ncw) {
-        mbar_wait(&ctl->vbar[slot][i / G], par);
+        mbar_wait(vbar0 + (slot * kMaxGrp + i / G) * 8, par);
         int s = vs0 + i; if (s >= nv) s -= nv;
-        unsigned char *row = vring + (size_t)s * rowb;
+        const unsigned row = vring + (unsigned)s * rowb;
         float4 x[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) x[j] = lds128(row + coff[j]);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          if (lane_on[j]) {
-            const float4 t = *reinterpret_cast<const float4 *>(row + (j * 32 + lane) * 16);
-            x[j] = make_float4(quant<BM>(t.x, qp), quant<BM>(t.y, qp), quant<BM>(t.z, qp), quant<BM>(t.w, qp));
-          } else {
-            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          x[j] = make_float4(quant<BM>(x[j].x, qp), quant<BM>(x[j].y, qp), quant<BM>(x[j].z, qp), quant<BM>(x[j].w, qp));
           d0 = fmaf(a[j].x, x[j].x, d0);
           d1 = fmaf(a[j].y, x[j].y, d1);
           d2 = fmaf(a[j].z, x[j].z, d2);
@@ -372,9 +472,8 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
           e[j].y = fmaf(g, x[j].y, e[j].y);
           e[j].z = fmaf(g, x[j].z, e[j].z);
           e[j].w = fmaf(g, x[j].w, e[j].w);
-          if (lane_on[j])  // :490 — the update g*context_avg replaces the landed row in its slot
-            *reinterpret_cast<float4 *>(row + (j * 32 + lane) * 16) =
-                make_float4(g * a[j].x, g * a[j].y, g * a[j].z, g * a[j].w);
+          if (on[j])  // :490 — the update g*context_avg replaces the landed row in its slot
+            sts128(row + coff[j], make_float4(g * a[j].x, g * a[j].y, g * a[j].z, g * a[j].w));
         }
         fence_async_smem();
         __syncwarp();
@@ -394,25 +493,25 @@ __global__ void __launch_bounds__(512, 1) train_ring_kernel(TrainParams p, int n
         s_rc[prev_slot] = s_rc[prev_slot] + 1;
         prev_slot = -1;
       }
-      // ---- error partials -> staging row (:494-503 is issued after the next barrier A)
+      // ---- error partials -> staging row (its scatter, :494-503, is issued after the next barrier A)
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
-        if (lane_on[j]) s_errp[(size_t)warp * D4 + j * 32 + lane] = e[j];
+        if (on[j]) sts128(s_errp + (unsigned)warp * rowb + coff[j], e[j]);
       consumer_bar(nct);  // B
-      if (tid < D4) {
-        float4 acc = s_errp[tid];
+      if (col_on) {
+        float4 acc = lds128(s_errp + colb);
         for (int w = 1; w < ncw; ++w) {
-          const float4 t = s_errp[(size_t)w * D4 + tid];
+          const float4 t = lds128(s_errp + (unsigned)w * rowb + colb);
           acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
-        *reinterpret_cast<float4 *>(errbuf + (size_t)(q & 1) * rowb + tid * 16) = acc;
+        sts128(errbuf + (unsigned)(q & 1) * rowb + colb, acc);
       }
       fence_async_smem();
       if (tid == 0) { pend_u = d; pend_q = q; }
       if (p.serial) {  // parity aid: everything of this position lands before the next one is fetched
         consumer_bar(nct);
         if (tid == 0) {
-          const unsigned char *eb = errbuf + (size_t)(q & 1) * rowb;
+          const unsigned eb = errbuf + (unsigned)(q & 1) * rowb;
           for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)d->ctx[k] * p.D, eb, rowb);
           bulk_commit();
           bulk_wait_all();
