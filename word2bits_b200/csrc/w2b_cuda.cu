@@ -205,16 +205,26 @@ static void plan_ring(w2b_ctx *c) {
   const int ncw = (c->ncol + 31) / 32;
   if (ncw > 8) return;  // kernels are instantiated for D <= 1024
   const long long D = c->cfg.layer1_size;
-  const size_t cap = 227 * 1024;
-  const int nv_min = std::max(2 * G, ncw + G + 1);
+  // Small rows: aim for several CTAs per SM (more warps hide the per-row dependency chains);
+  // k CTAs share the 227 KB (minus 1 KB reserved per CTA).  Take the largest k <= 4 whose
+  // share still holds >= 2.5 groups of v rows; big rows (D=800) end up with k = 1.
+  const int nv_min = std::max(2 * G, 3 * ncw + G + 1);  // see "release counters" in w2b_ring.cuh
+  const int nv_good = std::max(nv_min, (5 * G + 1) / 2);
   int nu = 2 * c->cfg.window + 4;
-  int nv = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
-  while (nv >= nv_min && ring_layout(D, nu, nv, ncw).total > cap) --nv;
-  if (nv < nv_min) {
+  int nv = 0;
+  for (int k = 4; k >= 1 && !nv; --k) {
+    const size_t cap = (size_t)(227 * 1024) / k - 1024;
+    int cand = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
+    while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
+    if (cand >= (k > 1 ? nv_good : nv_min)) nv = cand;
+  }
+  if (!nv) {
     nu = 2 * c->cfg.window;
-    nv = 4 * G;
-    while (nv >= nv_min && ring_layout(D, nu, nv, ncw).total > cap) --nv;
-    if (nv < nv_min) return;
+    const size_t cap = (size_t)(227 * 1024) - 1024;
+    int cand = 4 * G;
+    while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
+    if (cand < nv_min) return;
+    nv = cand;
   }
   c->ring = true;
   c->ring_g = G;

@@ -57,6 +57,7 @@ struct RingCtl {
   volatile int desc_ready;  // descriptors published by the sampler
   volatile int prog;        // positions whose descriptor is no longer needed by the consumers
   volatile int urel;        // u slots released
+  float sf[2][W2B_MAX_NEGATIVE + 1];  // +-f of every target of a position (reported loss, :480-483)
   double loss_out;
 };
 
@@ -384,9 +385,10 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
     QParams qp;
     qp.bits = p.bitlevel;
     qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
-    double loss = 0.0;
-    int prev_slot = -1;                // lane 0: slot whose reduce is committed but not yet confirmed read
-    const RingDesc *pend_u = nullptr;  // tid 0: position whose u scatter is staged but not yet issued
+    double loss = 0.0;                 // warp 0: one lane per target
+    int prev0 = -1, prev1 = -1;        // lane 0: slots whose reduce is committed but not yet confirmed read
+    const bool issuer = (warp == ncw - 1) && lane == 0;  // the last warp has the fewest rows: it scatters u
+    const RingDesc *pend_u = nullptr;  // issuer: position whose u scatter is staged but not yet issued
     int pend_q = 0;
     // lane's float4 columns j*32+lane; columns past the row end are clamped for loads and
     // masked for stores (their context_avg registers are zero, so they add nothing)
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         sts128(s_avg + colb, make_float4(__fdiv_rn(a0, fcw), __fdiv_rn(a1, fcw), __fdiv_rn(a2, fcw), __fdiv_rn(a3, fcw)));
       }
       consumer_bar(nct);  // A: context_avg visible; u rows consumed; previous staging row complete
-      if (tid == 0) {
+      if (issuer) {
         if (!fin) ctl->urel = ctl->urel + cw;
         if (pend_u) {  // scatter of the previous position's error to its context rows (:494-503)
           const unsigned eb = errbuf + (unsigned)(pend_q & 1) * rowb;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         }
       }
       if (fin) break;
-      // ---- target phase (:450-492): one warp per landed v row
+      // ---- target phase (:450-492): one warp per landed v row, two rows in flight per warp
       float4 a[NJ], e[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -445,53 +447,80 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         if (!on[j]) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (int i = warp; i < nt; i += ncw) {
+      float *sf = ctl->sf[q & 1];
+      for (int i = warp; i < nt; i += 2 * ncw) {
+        const int i2 = i + ncw;
+        const bool two = i2 < nt;
+        const int ib = two ? i2 : i;  // a lone row is simply read twice; its second copy gets g = 0
         mbar_wait(vbar0 + (slot * kMaxGrp + i / G) * 8, par);
-        int s = vs0 + i; if (s >= nv) s -= nv;
-        const unsigned row = vring + (unsigned)s * rowb;
-        float4 x[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) x[j] = lds128(row + coff[j]);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        if (two) mbar_wait(vbar0 + (slot * kMaxGrp + i2 / G) * 8, par);
+        int sA = vs0 + i; if (sA >= nv) sA -= nv;
+        int sB = vs0 + ib; if (sB >= nv) sB -= nv;
+        const unsigned rowA = vring + (unsigned)sA * rowb, rowB = vring + (unsigned)sB * rowb;
+        float4 xa[NJ], xb[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          x[j] = make_float4(quant<BM>(x[j].x, qp), quant<BM>(x[j].y, qp), quant<BM>(x[j].z, qp), quant<BM>(x[j].w, qp));
-          d0 = fmaf(a[j].x, x[j].x, d0);
-          d1 = fmaf(a[j].y, x[j].y, d1);
-          d2 = fmaf(a[j].z, x[j].z, d2);
-          d3 = fmaf(a[j].w, x[j].w, d3);
+          xa[j] = lds128(rowA + coff[j]);
+          xb[j] = lds128(rowB + coff[j]);
         }
-        float f = (d0 + d1) + (d2 + d3);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(kFull, f, o);  // all lanes get the same sum
-        const float g = grad_scalar(f, i == 0 ? 1 : 0, alpha, p.exptab);
-        if (lane == 0) loss += (double)logf(sigmoid_report(i == 0 ? f : -f));  // :480-483
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          e[j].x = fmaf(g, x[j].x, e[j].x);  // :487, quantized OLD v
-          e[j].y = fmaf(g, x[j].y, e[j].y);
-          e[j].z = fmaf(g, x[j].z, e[j].z);
-          e[j].w = fmaf(g, x[j].w, e[j].w);
-          if (on[j])  // :490 — the update g*context_avg replaces the landed row in its slot
-            sts128(row + coff[j], make_float4(g * a[j].x, g * a[j].y, g * a[j].z, g * a[j].w));
+          xa[j] = make_float4(quant<BM>(xa[j].x, qp), quant<BM>(xa[j].y, qp), quant<BM>(xa[j].z, qp), quant<BM>(xa[j].w, qp));
+          xb[j] = make_float4(quant<BM>(xb[j].x, qp), quant<BM>(xb[j].y, qp), quant<BM>(xb[j].z, qp), quant<BM>(xb[j].w, qp));
+          p0 = fmaf(a[j].x, xa[j].x, p0); r0 = fmaf(a[j].x, xb[j].x, r0);
+          p1 = fmaf(a[j].y, xa[j].y, p1); r1 = fmaf(a[j].y, xb[j].y, r1);
+          p2 = fmaf(a[j].z, xa[j].z, p2); r2 = fmaf(a[j].z, xb[j].z, r2);
+          p3 = fmaf(a[j].w, xa[j].w, p3); r3 = fmaf(a[j].w, xb[j].w, r3);
+        }
+        float fa = (p0 + p1) + (p2 + p3), fb = (r0 + r1) + (r2 + r3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // all lanes end up with the same sums
+          fa += __shfl_xor_sync(kFull, fa, o);
+          fb += __shfl_xor_sync(kFull, fb, o);
+        }
+        const float ga = grad_scalar(fa, i == 0 ? 1 : 0, alpha, p.exptab);
+        const float gb = two ? grad_scalar(fb, 0, alpha, p.exptab) : 0.f;
+        if (lane == 0) {
+          sf[i] = (i == 0) ? fa : -fa;
+          if (two) sf[i2] = -fb;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          e[j].x = fmaf(ga, xa[j].x, fmaf(gb, xb[j].x, e[j].x));  // :487, quantized OLD v
+          e[j].y = fmaf(ga, xa[j].y, fmaf(gb, xb[j].y, e[j].y));
+          e[j].z = fmaf(ga, xa[j].z, fmaf(gb, xb[j].z, e[j].z));
+          e[j].w = fmaf(ga, xa[j].w, fmaf(gb, xb[j].w, e[j].w));
+          if (on[j]) {  // :490 — the update g*context_avg replaces the landed row in its slot
+            sts128(rowA + coff[j], make_float4(ga * a[j].x, ga * a[j].y, ga * a[j].z, ga * a[j].w));
+            if (two) sts128(rowB + coff[j], make_float4(gb * a[j].x, gb * a[j].y, gb * a[j].z, gb * a[j].w));
+          }
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          bulk_reduce_add(p.v + (long long)d->tg[i] * p.D, row, rowb);
+          bulk_reduce_add(p.v + (long long)d->tg[i] * p.D, rowA, rowb);
+          if (two) bulk_reduce_add(p.v + (long long)d->tg[i2] * p.D, rowB, rowb);
           bulk_commit();
           if (p.serial) bulk_wait_all(); else bulk_wait_read<1>();
-          // everything this lane committed before the reduce above has left shared memory
-          if (prev_slot >= 0) s_rc[prev_slot] = s_rc[prev_slot] + 1;
-          prev_slot = s;
-          if (p.serial) { s_rc[s] = s_rc[s] + 1; prev_slot = -1; }
+          // everything this lane committed before the group above has left shared memory
+          if (prev0 >= 0) s_rc[prev0] = s_rc[prev0] + 1;
+          if (prev1 >= 0) s_rc[prev1] = s_rc[prev1] + 1;
+          prev0 = sA;
+          prev1 = two ? sB : -1;
+          if (p.serial) {
+            s_rc[sA] = s_rc[sA] + 1;
+            if (two) s_rc[sB] = s_rc[sB] + 1;
+            prev0 = prev1 = -1;
+          }
         }
         __syncwarp();
       }
-      if (lane == 0 && prev_slot >= 0) {  // confirm this warp's last row of the position right away
+      if (lane == 0) {  // confirm this warp's last rows (and, for the issuer, the u scatter) right away
         bulk_wait_read<0>();
-        s_rc[prev_slot] = s_rc[prev_slot] + 1;
-        prev_slot = -1;
+        if (prev0 >= 0) s_rc[prev0] = s_rc[prev0] + 1;
+        if (prev1 >= 0) s_rc[prev1] = s_rc[prev1] + 1;
+        prev0 = prev1 = -1;
       }
       // ---- error partials -> staging row (its scatter, :494-503, is issued after the next barrier A)
 #pragma unroll
@@ -507,10 +536,12 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         sts128(errbuf + (unsigned)(q & 1) * rowb + colb, acc);
       }
       fence_async_smem();
-      if (tid == 0) { pend_u = d; pend_q = q; }
+      if (warp == 0)  // reported loss (:480-483): one lane per target, off the row loop's critical path
+        for (int k = lane; k < nt; k += 32) loss += (double)logf(sigmoid_report(sf[k]));
+      if (issuer) { pend_u = d; pend_q = q; }
       if (p.serial) {  // parity aid: everything of this position lands before the next one is fetched
         consumer_bar(nct);
-        if (tid == 0) {
+        if (issuer) {
           const unsigned eb = errbuf + (unsigned)(q & 1) * rowb;
           for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)d->ctx[k] * p.D, eb, rowb);
           bulk_commit();
@@ -521,12 +552,12 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         }
       }
     }
-    if (lane == 0) {
-      bulk_wait_all();
-      atomicAdd(&ctl->loss_out, loss);
+    if (lane == 0) bulk_wait_all();
+    if (warp == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
+      if (lane == 0) shp->loss = shp->loss + loss;
     }
-    consumer_bar(nct);
-    if (tid == 0) shp->loss = shp->loss + ctl->loss_out;
   }
 }
 
