@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — Word2Bits training path on B200: words/sec at bitlevel=1 size=800 negative=24.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = every corpus shard advances by --words-per-shard words (whole sentences) of a
+synthetic Zipf(1.0) corpus, V=400k, window 10 — BASELINE.json configs[1].  N>1 is launched
+under torchrun (one rank per GPU): every GPU trains its own shard range on a full replica of
+u/v and the replicas are all-reduce-averaged over NCCL every --sync-every steps.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each field means.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "words/sec training throughput, bitlevel=1 size=800 neg=24; HBM GB/s vs peak"
+V, D, WINDOW, NEG, BITS = 400_000, 800, 10, 24, 1
+SAMPLE, ALPHA = 1e-3, 0.05
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def zipf_cdf(v):
+    p = 1.0 / np.arange(1, v + 1, dtype=np.float64)
+    return np.cumsum(p) / p.sum(), p / p.sum()
+
+
+def synth_ids(n, seed, cdf):
+    """n token ids in [1, V] (id = Zipf rank, so the vocabulary is already count-sorted)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(n, np.int32)
+    step = 1 << 24
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        out[a:b] = np.searchsorted(cdf, rng.random(b - a)).astype(np.int32) + 1
+    np.minimum(out, len(cdf), out=out)
+    return out
+
+
+def expected_counts(total_tokens, pmf):
+    cn = np.maximum(np.rint(pmf * total_tokens), 1).astype(np.int64)
+    return np.concatenate([[0], cn])  # </s> never occurs (text8-style corpus, no newlines)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_position():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_position"])
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (oracle/_ref = the unmodified source
+    compiled as a library, else the C port), all host threads, on a bounded sample of the same
+    workload.  One step = one pass over the sample (the reference's per-epoch thread launch)."""
+    if rank != 0:
+        return None
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    threads = int(os.environ.get("W2B_REF_THREADS", cores))
+    n = int(os.environ.get("W2B_REF_TOKENS", min(12_000_000, 90_000 * threads)))
+    cdf, _ = zipf_cdf(V)
+    ids = synth_ids(n, 4242, cdf)
+    words = np.array([("w%d" % i).encode() for i in range(V + 1)], dtype=object)
+    tmp = tempfile.NamedTemporaryFile(prefix="w2b_ref_", suffix=".txt", delete=False)
+    step = 1 << 20
+    for a in range(0, n, step):
+        tmp.write(b" ".join(words[ids[a:a + step]]) + b" ")
+    tmp.close()
+    iters = args.steps + args.warmup
+    kind = "reference"
+    try:
+        if po.ref_available("o3"):
+            ref = po.Ref("o3")
+            ref.configure(tmp.name, D, WINDOW, NEG, BITS, threads=threads, iters=iters, min_count=1, alpha=ALPHA,
+                          sample=SAMPLE)
+            ref.learn_vocab(); ref.init_net(); ref.init_unigram()
+            words_per_pass = ref.train_words
+            run = ref.train_epoch
+        else:
+            kind = "port"
+            corpus = po.Corpus(tmp.name, 1)
+            model = po.OracleModel(corpus, D, WINDOW, NEG, BITS, shards=threads, iters=iters, alpha=ALPHA, sample=SAMPLE)
+            words_per_pass = corpus.train_words
+            run = model.train_epoch_threads
+        for _ in range(args.warmup):
+            run()
+        t0 = time.time()
+        for _ in range(args.steps):
+            run()
+        dt = time.time() - t0
+    finally:
+        os.unlink(tmp.name)
+    value = words_per_pass * args.steps / dt
+    sample = "%d-token Zipf(1.0) V=%d text sample, %d passes, %s" % (n, V, args.steps, "oracle/_ref (unmodified reference, -O3 x86-64-v3)" if kind == "reference" else "oracle C port")
+    return {"metric": METRIC, "value": value, "unit": "words/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "synthetic Zipf corpus vocab=400k, bitlevel=1, size=800, window=10, negative=24 (CPU, bounded sample)",
+                       "threads": threads},
+            "cpu_baseline": {"value": value, "unit": "words/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "words/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def cpu_baseline_leg():
+    """Bounded (~10-30 s) run of the reference on this host's cores, for the cpu_baseline object."""
+    class A:
+        pass
+    a = A()
+    a.steps, a.warmup, a.gpus = 1, 0, 1
+    out = run_reference(a, 0)
+    return out["cpu_baseline"]
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--words-per-shard", type=int, default=16384)
+    ap.add_argument("--sync-every", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        out = run_reference(args, rank)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+
+    import torch
+    import word2bits_b200 as w2b
+    from word2bits_b200.parallel import DataParallel, exchange_unique_id
+    if not torch.cuda.is_available() or w2b.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- synthetic workload: every rank owns a contiguous 1/world of the corpus (weak scaling)
+    cfg0 = dict(size=D, window=WINDOW, negative=NEG, bitlevel=BITS, alpha=ALPHA, sample=SAMPLE, iter=1, device=local)
+    probe = w2b.Trainer(None, vocab_size=V + 1, threads=None, init=False, **cfg0)
+    S_local = probe.threads
+    probe.close()
+    S = S_local * world
+    B = args.words_per_shard
+    total_steps = args.steps + args.warmup
+    per_shard = int((total_steps + 2) * (B + 1500) * 1.05) + 4096
+    n_local = per_shard * S_local
+    cdf, pmf = zipf_cdf(V)
+    ids = synth_ids(n_local, 42 + rank, cdf)
+    cn = expected_counts(n_local * world, pmf)
+    train_words = int(n_local) * world
+    # global shard table; this rank's shards index into its own token array
+    start = np.zeros(S, np.int64)
+    start[rank * S_local:(rank + 1) * S_local] = np.arange(S_local, dtype=np.int64) * per_shard
+    first = np.full(S, -1, np.int32)
+
+    def make(resident):
+        t = w2b.Trainer(None, vocab_size=V + 1, threads=S, shard_range=(rank * S_local, (rank + 1) * S_local),
+                        init=False, **cfg0)
+        t.set_vocab_counts(cn, train_words)
+        t.set_corpus(ids, start, first, resident)
+        t.init_tables()
+        if world > 1:
+            t.nccl_init(exchange_unique_id(dist, w2b.nccl_unique_id, device="cuda"), rank, world)
+        return t
+
+    def run(t, steps, warmup, sampler_index=None):
+        dp = DataParallel(t, dist, args.sync_every, device="cuda")
+        for i in range(warmup):
+            dp.step(B)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(sampler_index) if sampler_index is not None else None
+        acc = dict(words=0, positions=0, rows=0, kernel_ms=0.0, launches=0, h2d=0, d2h=0, loss=0.0, sync_ms=0.0)
+        t0 = time.time()
+        for i in range(steps):
+            ts = time.time()
+            n_sync = dp.syncs
+            st = dp.step(B)  # train_step + (every sync_every steps) the NCCL replica average
+            if dp.syncs != n_sync:
+                acc["sync_ms"] += max(0.0, (time.time() - ts) * 1e3 - st["kernel_ms"])
+            acc["words"] += st["words"]; acc["positions"] += st["positions"]
+            acc["rows"] += st["context_rows"] + st["target_rows"]
+            acc["kernel_ms"] += st["kernel_ms"]; acc["launches"] += st["launches"]
+            acc["h2d"] += st["h2d_bytes"]; acc["d2h"] += st["d2h_bytes"]; acc["loss"] += st["loss"]
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        acc["wall_s"] = t1 - t0
+        acc["alpha"] = st["alpha"]
+        acc["clocks"] = clocks.stop(t0, t1) if clocks else None
+        return acc
+
+    def reduce_max(x):
+        if not dist:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def reduce_sum(x):
+        if not dist:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return float(tt.item())
+
+    # ---- device-resident run: `value`, roofline
+    t = make(resident=True)
+    a = run(t, args.steps, args.warmup, sampler_index=local if rank == 0 else None)
+    t.close()
+    # device time of the timed region = kernel events + sync; whole-job rate = all ranks' words / max time
+    dev_s = reduce_max(a["kernel_ms"] / 1e3 + a["sync_ms"] / 1e3)
+    wall_s = reduce_max(a["wall_s"])
+    words = reduce_sum(a["words"])
+    positions = reduce_sum(a["positions"])
+    value = words / dev_s
+    alg_bytes = 2.0 * 4.0 * D * a["rows"]
+    kern_s = a["kernel_ms"] / 1e3
+    achieved = alg_bytes / kern_s / 1e9
+    peak, peak_src = measured_peak()
+    tpp = ncu_traffic_per_position()
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (tpp * a["positions"] / max(a["launches"], 1)) if tpp else None,
+            "peak_source": peak_src, "kernel": "train_ring_kernel<1,7> (one launch per step)",
+            "algorithmic_bytes_per_launch": alg_bytes / max(a["launches"], 1),
+            "kernel_ms_per_launch": a["kernel_ms"] / max(a["launches"], 1),
+            "bytes_per_position": alg_bytes / max(a["positions"], 1)}
+
+    # ---- end-to-end run: host token buffers, H2D slices + D2H shard state inside every step
+    t = make(resident=False)
+    e = run(t, args.steps, args.warmup)
+    t.close()
+    e_wall = reduce_max(e["wall_s"])
+    e_words = reduce_sum(e["words"])
+    e2e = {"value": e_words / e_wall, "unit": "words/s", "h2d_bytes_per_step": int(e["h2d"] / args.steps),
+           "d2h_bytes_per_step": int(e["d2h"] / args.steps), "kernel_ms_per_step": e["kernel_ms"] / args.steps,
+           "wall_ms_per_step": e_wall / args.steps * 1e3}
+
+    out = {"metric": METRIC, "value": value, "unit": "words/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "synthetic Zipf corpus vocab=400k, bitlevel=1, size=800, window=10, negative=24, 1xB200"
+                      if world == 1 else "synthetic Zipf corpus vocab=400k per-GPU shard, bitlevel=1, size=800, window=10, negative=24, %dxB200 data-parallel" % world,
+                      "vocab": V, "size": D, "window": WINDOW, "negative": NEG, "bitlevel": BITS, "sample": SAMPLE,
+                      "shards_per_gpu": S_local, "words_per_shard_per_step": B,
+                      "l2": "inputs larger than L2: 2 x 1.28 GB embedding tables + 400 MB unigram table per GPU, rows drawn at random",
+                      "parallelism": "dp%d, replica all-reduce-average of u and v every %d steps (NCCL)" % (world, args.sync_every) if world > 1 else "single GPU, %d concurrent shards (one CTA each)" % S_local},
+           "positions_per_s": positions / dev_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
+           "sync_ms_per_step": a["sync_ms"] / args.steps,
+           "roofline": roof, "e2e": e2e, "clocks": a["clocks"], "gpu_launches": int(a["launches"]),
+           "mean_loss_per_position": a["loss"] / max(a["positions"], 1)}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline_leg()
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                out["cpu_baseline"] = {"value": None, "unit": "words/s", "cores": os.cpu_count(), "kind": "reference",
+                                       "sample": "failed: %r" % (ex,)}
+        print(json.dumps(out), flush=True)
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

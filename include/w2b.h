@@ -91,6 +91,8 @@ typedef struct {
   int64_t word_count_actual;
   float kernel_ms;        /* CUDA-event time of the training kernel(s) in this call */
   int32_t launches;       /* kernels launched by this call */
+  int64_t h2d_bytes;      /* host->device bytes copied by this call (token slices, shard states) */
+  int64_t d2h_bytes;      /* device->host bytes copied by this call (shard states, alpha, counter) */
 } w2b_step_stats;
 
 /* One record per loop iteration that reaches the window draw (:428). */

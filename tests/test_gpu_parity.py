@@ -315,3 +315,35 @@ def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
         cu = np.corrcoef(u.ravel(), m.u.ravel())[0, 1]
         cv = np.corrcoef(v.ravel(), m.v.ravel())[0, 1]
         assert cu > 0.9 and cv > 0.9, (cu, cv)
+
+
+def test_cli_end_to_end(tmp_path):
+    """The drop-in binary: strict mode writes byte-for-byte the file the oracle writes (text and
+    binary formats, :560-576); the production mode writes a well-formed 1-bit file."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "word2bits_b200", "word2bits")
+    o = po.Corpus(GOLDEN_CORPUS, 1)
+    for binary in (0, 1):
+        out = str(tmp_path / ("strict%d" % binary))
+        r = subprocess.run([cli, "-train", GOLDEN_CORPUS, "-output", out, "-size", "16", "-window", "3", "-negative", "4",
+                            "-bitlevel", "2", "-threads", "2", "-iter", "2", "-min-count", "1", "-binary", str(binary),
+                            "-strict", "1", "-save-every-epoch", "1"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Starting epoch: 0" in r.stdout and "Starting epoch: 1" in r.stdout and "Epoch Loss:" in r.stdout
+        m = po.OracleModel(o, 16, 3, 4, 2, shards=2, iters=2)
+        for ep in range(2):
+            for s in range(2):
+                m.train_shard(s)
+            want = str(tmp_path / "want")
+            m.write_vectors(want, binary)
+            assert open(out + "_epoch%d" % ep, "rb").read() == open(want, "rb").read()
+        assert open(out, "rb").read() == open(want, "rb").read()
+    out = str(tmp_path / "fast.bin")
+    r = subprocess.run([cli, "-train", GOLDEN_CORPUS, "-output", out, "-size", "32", "-window", "3", "-negative", "4",
+                        "-min-count", "1", "-binary", "1", "-iter", "1", "-debug", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(out, "rb").read()
+    assert raw.startswith(b"31 32\n</s> ")
+    body = raw[len(b"31 32\n</s> "):][: 32 * 4]
+    assert set(np.frombuffer(body, np.uint32).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}  # README.md:124-131

@@ -1,0 +1,135 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads without a GPU and exports
+every symbol include/w2b.h declares; the corpus/vocabulary glue equals the oracle (and through
+it the reference); the CLI reproduces the reference's messages and exit codes; compute entry
+points fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import zipf_corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "word2bits_b200", "libw2b.so")
+CLI = os.path.join(ROOT, "word2bits_b200", "word2bits")
+
+
+def _has_gpu():
+    import word2bits_b200 as w2b
+    return w2b.device_count() > 0
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "w2b.h")).read()
+    names = set(re.findall(r"\b(w2b_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 35
+    lib = ctypes.CDLL(LIB)
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback():
+    import word2bits_b200 as w2b
+    if _has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(w2b.W2BError) as e:
+        w2b.Trainer(None, vocab_size=100, size=8, threads=2)
+    assert e.value.code == 2  # W2B_ECUDA
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "word2bits_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pyoracle" not in src and "liboracle" not in src and "w2b_oracle" not in src, f
+
+
+@pytest.mark.parametrize("newline_every,min_count,vocab", [(0, 5, 3000), (15, 1, 30), (7, 2, 200)])
+def test_corpus_matches_oracle(tmp_path, newline_every, min_count, vocab):
+    import word2bits_b200 as w2b
+    path = zipf_corpus(str(tmp_path / "c.txt"), 50000, vocab, seed=11, newline_every=newline_every)
+    c = w2b.Corpus(path, min_count)
+    o = po.Corpus(path, min_count)
+    assert (c.vocab_size, c.train_words, c.file_size, c.num_tokens) == (o.vocab_size, o.train_words, o.file_size, o.num_tokens)
+    assert c.words() == o.words()
+    assert np.array_equal(c.counts, o.counts) and np.array_equal(c.tokens, o.tokens)
+    for n in (1, 2, 3, 7, 16, 61, 148):
+        s, f = c.shards(n)
+        want = [o.shard_start(i, n) for i in range(n)]
+        assert [w[0] for w in want] == list(s) and [w[1] for w in want] == list(f), n
+
+
+def test_corpus_edge_cases(tmp_path):
+    import word2bits_b200 as w2b
+    cases = {
+        "empty.txt": b"",
+        "one.txt": b"hello",                      # last token without trailing whitespace is never seen
+        "nl.txt": b"\n\n\n",
+        "crlf.txt": b"a b\r\nc\td  e\r\n\r\nf" + b" g" * 10,
+        "long.txt": b"x" * 5000 + b" y y y\n",    # token longer than MAX_STRING is truncated
+        "tie.txt": b"b a c a b c d d e\n" * 3,    # equal counts keep first-appearance order
+    }
+    for name, data in cases.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        c = w2b.Corpus(str(p), 1)
+        o = po.Corpus(str(p), 1)
+        assert c.words() == o.words(), name
+        assert np.array_equal(c.counts, o.counts) and np.array_equal(c.tokens, o.tokens), name
+        assert (c.train_words, c.file_size) == (o.train_words, o.file_size), name
+        for n in (1, 2, 5):
+            s, f = c.shards(n)
+            assert [o.shard_start(i, n) for i in range(n)] == list(zip(s.tolist(), f.tolist())), (name, n)
+
+
+@pytest.mark.skipif(not po.ref_available("strict"), reason="oracle/_ref not built")
+def test_corpus_matches_reference(tmp_path):
+    import word2bits_b200 as w2b
+    path = zipf_corpus(str(tmp_path / "c.txt"), 80000, 5000, seed=5)
+    ref = po.Ref("strict")
+    for mc in (1, 5):
+        ref.configure(path, 8, 3, 4, 1, min_count=mc)
+        ref.learn_vocab()
+        c = w2b.Corpus(path, mc)
+        assert c.words() == ref.words() and np.array_equal(c.counts, ref.counts())
+        assert (c.train_words, c.file_size) == (ref.train_words, ref.file_size)
+
+
+def test_vector_writer_matches_oracle(tmp_path):
+    import word2bits_b200 as w2b
+    path = os.path.join(ROOT, "tests", "golden", "golden_corpus.txt")
+    c = w2b.Corpus(path, 1)
+    o = po.Corpus(path, 1)
+    m = po.OracleModel(o, 8, 3, 4, 2)
+    vec = m.export()
+    for binary in (0, 1):
+        a, b = str(tmp_path / ("a%d" % binary)), str(tmp_path / ("b%d" % binary))
+        c.write_vectors(a, vec, binary)
+        m.write_vectors(b, binary)
+        assert open(a, "rb").read() == open(b, "rb").read()
+    # README.md:124-131 framing: header, "</s> " first, rows end with "\n"
+    raw = open(a, "rb").read()
+    assert raw.startswith(b"31 8\n</s> ") and raw.endswith(b"\n")
+
+
+def test_cli_messages_and_exit_codes(tmp_path):
+    def run(exe, *args):
+        r = subprocess.run([exe, *args], capture_output=True, text=True)
+        return r.returncode, r.stdout
+    golden = os.path.join(ROOT, "tests", "golden", "golden_corpus.txt")
+    ours = [run(CLI, "-train", "/nonexistent", "-output", "x"), run(CLI, "-train"),
+            run(CLI, "-train", golden, "-min-count", "1"), run(CLI, "-train", golden, "-min-count", "5", "-debug", "0")]
+    assert ours[0] == (1, "Starting training using file /nonexistent\nERROR: training data file not found!\n")
+    assert ours[1] == (1, "Argument missing for -train\n")
+    assert ours[2] == (0, "Starting training using file %s\nVocab size: 31\nWords in train file: 13533\n" % golden)
+    refbin = os.path.join(ROOT, "oracle", "_ref", "word2bits")
+    if os.path.exists(refbin):
+        theirs = [run(refbin, "-train", "/nonexistent", "-output", "x"), run(refbin, "-train"),
+                  run(refbin, "-train", golden, "-min-count", "1"),
+                  run(refbin, "-train", golden, "-min-count", "5", "-debug", "0")]
+        assert ours == theirs

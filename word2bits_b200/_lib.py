@@ -34,7 +34,7 @@ class StepStats(C.Structure):
     _fields_ = [("loss", C.c_double), ("words", C.c_int64), ("positions", C.c_int64),
                 ("context_rows", C.c_int64), ("target_rows", C.c_int64), ("shards_done", C.c_int64),
                 ("alpha", C.c_float), ("word_count_actual", C.c_int64), ("kernel_ms", C.c_float),
-                ("launches", C.c_int32)]
+                ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -489,7 +489,7 @@ static void sum_shards(const std::vector<ShardState> &s, w2b_step_stats *o) {
 
 // Streaming mode: copy every unfinished shard's next slice into the pinned staging
 // buffer, upload, and point the shard states at it.
-static int stage_slices(w2b_ctx *c, long long want) {
+static int stage_slices(w2b_ctx *c, long long want, w2b_step_stats *acc) {
   const long long L = want + c->stage_margin;
   const long long need = L * c->nlocal;
   if (need > c->stage_cap) {
@@ -515,6 +515,7 @@ static int stage_slices(w2b_ctx *c, long long want) {
   CK(cudaMemcpyAsync(c->d_tokens, c->h_stage, need * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice,
                      c->stream));
+  acc->h2d_bytes += need * (long long)sizeof(int) + (long long)sizeof(ShardState) * c->nlocal;
   return W2B_OK;
 }
 
@@ -534,6 +535,7 @@ static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     acc->kernel_ms += ms;
     acc->launches += 1;
+    acc->d2h_bytes += (long long)sizeof(ShardState) * c->nlocal;
     return W2B_OK;
   }
   train_fn fn = pick_train(c);
@@ -562,6 +564,7 @@ static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   acc->kernel_ms += ms;
   acc->launches += launches;
+  acc->d2h_bytes += (long long)sizeof(ShardState) * c->nlocal;
   return W2B_OK;
 }
 
@@ -583,7 +586,7 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
     // streaming: slices of (budget + margin) tokens; run-to-end loops over slices
     const long long chunk = words_per_shard > 0 ? words_per_shard : 65536;
     for (;;) {
-      int rc = stage_slices(c, chunk);
+      int rc = stage_slices(c, chunk, &acc);
       if (rc) return rc;
       p.tokens = c->d_tokens;
       p.word_budget = chunk;
@@ -612,6 +615,8 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
     stats->shards_done = after.shards_done;
     stats->kernel_ms = acc.kernel_ms;
     stats->launches = acc.launches;
+    stats->h2d_bytes = acc.h2d_bytes;
+    stats->d2h_bytes = acc.d2h_bytes + (long long)(sizeof(float) + sizeof(unsigned long long));
     unsigned long long wca = 0;
     CK(cudaMemcpy(&stats->alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&wca, c->d_wca, sizeof wca, cudaMemcpyDeviceToHost));
