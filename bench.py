@@ -110,40 +110,64 @@ def ncu_traffic_per_position():
 
 
 # ------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank):
+def _write_text(ids, path_prefix):
+    words = np.array([("w%d" % i).encode() for i in range(V + 1)], dtype=object)
+    tmp = tempfile.NamedTemporaryFile(prefix=path_prefix, suffix=".txt", delete=False)
+    step = 1 << 20
+    for a in range(0, len(ids), step):
+        tmp.write(b" ".join(words[ids[a:a + step]]) + b" ")
+    tmp.close()
+    return tmp.name
+
+
+def _ref_runner(po, path, threads, iters):
+    """(run_one_pass, words_per_pass, kind) for the reference on `path` with `threads` threads."""
+    if po.ref_available("o3"):
+        ref = po.Ref("o3")
+        ref.configure(path, D, WINDOW, NEG, BITS, threads=threads, iters=iters, min_count=1, alpha=ALPHA, sample=SAMPLE)
+        ref.learn_vocab(); ref.init_net(); ref.init_unigram()
+        return ref.train_epoch, ref.train_words, "reference"
+    corpus = po.Corpus(path, 1)
+    model = po.OracleModel(corpus, D, WINDOW, NEG, BITS, shards=threads, iters=iters, alpha=ALPHA, sample=SAMPLE)
+    return model.train_epoch_threads, corpus.train_words, "port"
+
+
+def run_reference(args, rank, budget_s=100.0):
     """The reference's own CPU implementation of the path (oracle/_ref = the unmodified source
-    compiled as a library, else the C port), all host threads, on a bounded sample of the same
-    workload.  One step = one pass over the sample (the reference's per-epoch thread launch)."""
+    compiled as a library, else the C port) on a bounded sample of the same workload; one step =
+    one pass over the sample (the reference's per-epoch thread launch).  The thread count is the
+    best of {all, 1/2, 1/4, 1/8 of the host threads} on a calibration sample — Hogwild on two
+    sockets can get slower with more threads — and the sample is sized so that W+K passes fit the
+    time budget."""
     if rank != 0:
         return None
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    threads = int(os.environ.get("W2B_REF_THREADS", cores))
-    n = int(os.environ.get("W2B_REF_TOKENS", min(12_000_000, 90_000 * threads)))
     cdf, _ = zipf_cdf(V)
-    ids = synth_ids(n, 4242, cdf)
-    words = np.array([("w%d" % i).encode() for i in range(V + 1)], dtype=object)
-    tmp = tempfile.NamedTemporaryFile(prefix="w2b_ref_", suffix=".txt", delete=False)
-    step = 1 << 20
-    for a in range(0, n, step):
-        tmp.write(b" ".join(words[ids[a:a + step]]) + b" ")
-    tmp.close()
-    iters = args.steps + args.warmup
-    kind = "reference"
+    ids = synth_ids(12_000_000, 4242, cdf)
+    cands = [int(os.environ["W2B_REF_THREADS"])] if "W2B_REF_THREADS" in os.environ else \
+        sorted({max(1, cores // k) for k in (1, 2, 4, 8)}, reverse=True)
+    cal_n = 400_000
+    cal = _write_text(ids[:cal_n], "w2b_cal_")
+    best = (0.0, cands[-1])
+    tried = []
     try:
-        if po.ref_available("o3"):
-            ref = po.Ref("o3")
-            ref.configure(tmp.name, D, WINDOW, NEG, BITS, threads=threads, iters=iters, min_count=1, alpha=ALPHA,
-                          sample=SAMPLE)
-            ref.learn_vocab(); ref.init_net(); ref.init_unigram()
-            words_per_pass = ref.train_words
-            run = ref.train_epoch
-        else:
-            kind = "port"
-            corpus = po.Corpus(tmp.name, 1)
-            model = po.OracleModel(corpus, D, WINDOW, NEG, BITS, shards=threads, iters=iters, alpha=ALPHA, sample=SAMPLE)
-            words_per_pass = corpus.train_words
-            run = model.train_epoch_threads
+        for th in cands:
+            run, wpp, kind = _ref_runner(po, cal, th, 1)
+            t0 = time.time()
+            run()
+            rate = wpp / (time.time() - t0)
+            tried.append((th, round(rate)))
+            if rate > best[0]:
+                best = (rate, th)
+    finally:
+        os.unlink(cal)
+    rate, threads = best
+    passes = args.steps + args.warmup
+    n = int(min(len(ids), max(300_000, rate * min(15.0, budget_s / passes))))
+    path = _write_text(ids[:n], "w2b_ref_")
+    try:
+        run, words_per_pass, kind = _ref_runner(po, path, threads, passes)
         for _ in range(args.warmup):
             run()
         t0 = time.time()
@@ -151,14 +175,16 @@ def run_reference(args, rank):
             run()
         dt = time.time() - t0
     finally:
-        os.unlink(tmp.name)
+        os.unlink(path)
     value = words_per_pass * args.steps / dt
-    sample = "%d-token Zipf(1.0) V=%d text sample, %d passes, %s" % (n, V, args.steps, "oracle/_ref (unmodified reference, -O3 x86-64-v3)" if kind == "reference" else "oracle C port")
+    sample = "%d-token Zipf(1.0) V=%d text sample, %d timed passes, %s; threads chosen from %s (words/s on a %d-token calibration sample)" % (
+        n, V, args.steps, "oracle/_ref (unmodified reference, -O3 x86-64-v3)" if kind == "reference" else "oracle C port",
+        tried, cal_n)
     return {"metric": METRIC, "value": value, "unit": "words/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "synthetic Zipf corpus vocab=400k, bitlevel=1, size=800, window=10, negative=24 (CPU, bounded sample)",
-                       "threads": threads},
+                       "threads": threads, "host_threads": cores},
             "cpu_baseline": {"value": value, "unit": "words/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "words/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
@@ -169,7 +195,7 @@ def cpu_baseline_leg():
         pass
     a = A()
     a.steps, a.warmup, a.gpus = 1, 0, 1
-    out = run_reference(a, 0)
+    out = run_reference(a, 0, budget_s=15.0)
     return out["cpu_baseline"]
 
 
