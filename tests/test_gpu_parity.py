@@ -347,3 +347,39 @@ def test_cli_end_to_end(tmp_path):
     assert raw.startswith(b"31 32\n</s> ")
     body = raw[len(b"31 32\n</s> "):][: 32 * 4]
     assert set(np.frombuffer(body, np.uint32).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}  # README.md:124-131
+
+
+def test_planted_topic_quality(tmp_path):
+    """L3 statistical end-to-end: on a corpus with planted topics the trained
+    1-bit vectors must recover the topics as well as the reference's own (kNN purity within 0.02,
+    final epoch loss within 1 %), for the production ring kernel with its prefetch on."""
+    from tests.util import planted_topic_corpus, topic_purity
+    topics = 25
+    path = planted_topic_corpus(str(tmp_path / "topics.txt"), vocab=5000, topics=topics, sentences=60000, length=20)
+    D, W, neg, iters, shards = 100, 5, 12, 2, 16
+    c = w2b.Corpus(path, 5)
+    o = po.Corpus(path, 5)
+    words = c.words()
+    res = {}
+    if po.ref_available("o3"):   # the unmodified reference, 16 concurrent threads
+        ref = po.Ref("o3")
+        ref.configure(path, D, W, neg, 1, threads=shards, iters=iters, min_count=5)
+        ref.learn_vocab(); ref.init_net(); ref.init_unigram()
+        losses = [ref.train_epoch() for _ in range(iters)]
+        out = po.quantize(ref.u() + ref.v(), 1) if False else None
+        uv = (ref.u() + ref.v()).astype(np.float32)
+        res["reference"] = (losses[-1], topic_purity(words, np.where(uv < 0, -1.0, 1.0), topics))
+    m = po.OracleModel(o, D, W, neg, 1, shards=shards, iters=iters)
+    losses = [m.train_epoch_threads() for _ in range(iters)]
+    res["oracle"] = (losses[-1], topic_purity(words, m.export(), topics))
+    for name, kw in (("ring", dict(kernel=0)), ("ring_serial", dict(kernel=0, ring_serial=1)), ("register", dict(kernel=1))):
+        t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=1, threads=shards, iter=iters, **kw)
+        losses = [t.train_epoch()[0] for _ in range(iters)]
+        res[name] = (losses[-1], topic_purity(words, t.export(), topics))
+        t.close()
+    print("planted-topic quality (final-epoch loss, kNN purity):", {k: (round(v[0], 1), round(v[1], 4)) for k, v in res.items()})
+    base = res.get("reference", res["oracle"])
+    assert base[1] > 0.5, "corpus too weak to measure anything"
+    for name in ("ring", "ring_serial", "register"):
+        assert abs(res[name][1] - base[1]) <= 0.02, (name, res)
+        assert abs(res[name][0] - base[0]) <= 0.01 * abs(base[0]), (name, res)
