@@ -677,10 +677,16 @@ extern "C" int w2b_trace(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trac
   p.train = 0;
   p.max_iters = max_iterations;
   p.wca_scale = 1;
-  train_fn fn = pick_train(c);
-  const size_t smem = dyn_smem(c);
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<1, c->threads, smem, c->stream>>>(p);
+  if (c->ring) {  // the production kernel's own sampler warp (prefetching draw path)
+    ring_fn rf = pick_ring(c);
+    CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
+    rf<<<1, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv, c->ring_g);
+  } else {
+    train_fn fn = pick_train(c);
+    const size_t smem = dyn_smem(c);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<1, c->threads, smem, c->stream>>>(p);
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   unsigned long long cnt[2];

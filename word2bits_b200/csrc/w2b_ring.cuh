@@ -303,8 +303,22 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       }
       ++sp;
       if (sp >= len) len = 0;  // :505-509
+      if (p.trace) {  // parity hook: one record per window draw, exactly what the oracle's trace holds
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned long long k = (*p.trace_n)++;
+          if ((long long)k < p.trace_cap) {
+            w2b_trace_rec *tr = p.trace + k;
+            tr->center = center; tr->b = b; tr->cw = cw; tr->ntargets = nt; tr->alpha = alpha_c;
+            for (int i = 0; i < nt; ++i) tr->targets[i] = d->tg[i];
+          }
+        }
+        __syncwarp();
+      }
+      if (p.max_iters >= 0 && iters >= p.max_iters) { if (cw) { n_pos += 1; n_ctx += cw; n_tgt += nt; } break; }
       if (cw == 0) continue;   // single-word or empty sentence: one window draw, nothing trained
       n_pos += 1; n_ctx += cw; n_tgt += nt;
+      if (!p.train) continue;  // draws only: nothing is handed to the loader / consumers
       if (lane == 0) {
         d->center = center; d->b = b; d->cw = cw; d->nt = nt;
         d->alpha = alpha_c;
