@@ -67,12 +67,15 @@ def test_tables_bit_exact(medium):
     ("small", 1, 3, 4, 1e-3, 3), ("small", 1, 5, 6, 1e-2, 2), ("small", 1, 3, 4, 0.0, 1),
     ("medium", 5, 5, 6, 1e-3, 4), ("medium", 1, 8, 24, 1e-4, 7), ("medium", 5, 10, 40, 1e-3, 2),
 ])
-def test_draw_trace_bit_exact(cfg, small, medium):
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_draw_trace_bit_exact(cfg, kernel, small, medium):
+    """kernel=0: the ring kernel's sampler warp (jump-ahead + prefetched table lookups);
+    kernel=1: the register kernel's inline sampler.  Both must replay the oracle's draws exactly."""
     name, mc, W, neg, sample, shards = cfg
     path = {"small": small, "medium": medium}[name]
     c = w2b.Corpus(path, mc)
     o = po.Corpus(path, mc)
-    t = w2b.Trainer(c, size=8, window=W, negative=neg, bitlevel=1, sample=sample, threads=shards)
+    t = w2b.Trainer(c, size=8, window=W, negative=neg, bitlevel=1, sample=sample, threads=shards, kernel=kernel)
     table = po.unigram_table(o.counts)
     for sid in range(shards):
         m = po.OracleModel(o, 8, W, neg, 1, shards=shards, sample=sample, table=table)
@@ -383,3 +386,30 @@ def test_planted_topic_quality(tmp_path):
     for name in ("ring", "ring_serial", "register"):
         assert abs(res[name][1] - base[1]) <= 0.02, (name, res)
         assert abs(res[name][0] - base[0]) <= 0.01 * abs(base[0]), (name, res)
+
+
+@pytest.mark.parametrize("D,W,neg,b", [(4, 1, 0, 1), (8, 2, 1, 2), (100, 5, 5, 1), (256, 20, 40, 0), (1024, 3, 7, 1),
+                                         (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (12, 5, 3, 4)])
+def test_ring_kernel_odd_shapes(D, W, neg, b, medium):
+    """Production kernel on edge geometries (negative=0, window 1..30, D 4..1024, > 32 negatives):
+    terminates, trains every position the oracle's trace holds, loss within 2 % of the oracle."""
+    shards = 6
+    c = w2b.Corpus(medium, 5)
+    o = po.Corpus(medium, 5)
+    t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=b, threads=shards, iter=1)
+    lg, st = t.train_epoch()
+    assert st["shards_done"] == shards
+    table = po.unigram_table(o.counts)
+    pos = ctx = tgt = 0
+    for s in range(shards):
+        m0 = po.OracleModel(o, 4, W, neg, b, shards=shards, table=table)
+        _, tr = m0.train_shard(s, trace_cap=200000)
+        for r in tr:
+            if r[2] > 0:
+                pos += 1; ctx += r[2]; tgt += len(r[3])
+    assert (st["positions"], st["context_rows"], st["target_rows"]) == (pos, ctx, tgt)
+    m = po.OracleModel(o, D, W, neg, b, shards=shards, table=table)
+    lo = m.train_epoch_threads()
+    assert abs(lg - lo) <= 0.02 * abs(lo) + 1.0, (lg, lo)
+    u, v = t.download_raw()
+    assert np.isfinite(u).all() and np.isfinite(v).all()
