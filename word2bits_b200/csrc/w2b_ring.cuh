@@ -29,12 +29,15 @@
 // (bumped after cp.async.bulk.wait_group.read) for "slot free again"; monotonic counters
 // for descriptors.
 //
-// Ordering semantics: rows of position p+1.. are fetched before position p's updates
-// land, so a context row shared by neighbouring positions is read one or two updates
-// stale; no update is ever lost (all scatters are atomic adds in L2).  This is the same
-// class of staleness the reference's Hogwild threads have (SURVEY section 7 "hard parts");
-// ring_serial=1 turns the prefetch off for parity work.  DESIGN.md quantifies the effect
-// and tests/test_gpu_parity.py holds it to the L3 bars.
+// Context rows live in a sliding-window cache: the u-"ring" holds the rows of the current
+// sentence around the centre word (each row is fetched ONCE, when it enters the window, and
+// stays for up to 2*window+1 positions).  After every position the consumers add the
+// accumulated error to the cached copies (:501) as well as scattering it to global memory, so a
+// shard always sees its own context updates immediately — exactly like one reference thread —
+// and only the updates of OTHER shards arrive with the delay of one window residency (the
+// reference's Hogwild threads have the same kind of delay).  Target rows are fetched one or two
+// positions ahead of their use; no update is ever lost (all scatters are atomic adds in L2).
+// ring_serial=1 additionally turns the cross-position prefetch off (parity aid).
 #pragma once
 #include "w2b_kernels.cuh"
 
@@ -44,10 +47,13 @@ constexpr int kND = 8;      // descriptor ring depth (positions in flight)
 constexpr int kMaxGrp = 8;  // max target groups per position
 
 struct RingDesc {
-  int cw, nt, exit_flag, us0, vs0;
+  int cw, nt, exit_flag, vs0;
+  int cs_lo, n_left, n_right;  // context = cache slots cs_lo.. (n_left rows), [centre], n_right rows
+  int nload, ld_slot0;         // rows entering the window with this position -> cache slots ld_slot0..
   float alpha;
   int center, b;
-  int ctx[2 * W2B_MAX_WINDOW];
+  int ctx[2 * W2B_MAX_WINDOW];      // word ids of the context rows, in window order (u scatter)
+  int ld[W2B_MAX_WINDOW + 1];       // word ids of the rows to fetch
   int tg[W2B_MAX_NEGATIVE + 1];
 };
 
@@ -56,7 +62,6 @@ struct RingCtl {
   unsigned long long vbar[kND][kMaxGrp];
   volatile int desc_ready;  // descriptors published by the sampler
   volatile int prog;        // positions whose descriptor is no longer needed by the consumers
-  volatile int urel;        // u slots released
   float sf[2][W2B_MAX_NEGATIVE + 1];  // +-f of every target of a position (reported loss, :480-483)
   double loss_out;
 };
@@ -174,7 +179,6 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       for (int g = 0; g < kMaxGrp; ++g) mbar_init(&ctl->vbar[i][g], 1);
     }
     ctl->desc_ready = 0;
-    ctl->urel = 0;
     ctl->prog = 0;
     ctl->loss_out = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,6 +201,9 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
     const int negl = neg < 32 ? neg : 32;
     const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
     const unsigned long long JAn = c_JA[neg], JCn = c_JC[neg];
+    // sliding-window cache bookkeeping: cache row ids are handed out consecutively; row id of
+    // sentence index i is row_base + i and lives in slot (row_base + i) % nu
+    int row_base = 0, loaded_hi = -1;
     bool have_pre = false;
     unsigned long long r1_pre = 0, rd_pre = 0;
     int t_pre = 0;
@@ -222,6 +229,8 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         __syncwarp();
         if (status == 2) break;  // slice exhausted mid-sentence: nothing committed
         r = r2; cursor = c2; wc = w2; len = l2; sp = 0;
+        row_base = (row_base + loaded_hi + 1) % nu;  // the new sentence's rows follow the old one's in the ring
+        loaded_hi = -1;
         have_pre = false;
         // the shared learning rate (:53) is re-read once per sentence: other shards move it
         // every 10k words each, by ~1e-4 relative per update
@@ -301,6 +310,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       } else {
         r = r1;
       }
+      const int pos = sp, slen = len;  // this position, before the cursor moves on
       ++sp;
       if (sp >= len) len = 0;  // :505-509
       if (p.trace) {  // parity hook: one record per window draw, exactly what the oracle's trace holds
@@ -319,10 +329,24 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       if (cw == 0) continue;   // single-word or empty sentence: one window draw, nothing trained
       n_pos += 1; n_ctx += cw; n_tgt += nt;
       if (!p.train) continue;  // draws only: nothing is handed to the loader / consumers
-      if (lane == 0) {
-        d->center = center; d->b = b; d->cw = cw; d->nt = nt;
-        d->alpha = alpha_c;
-        d->exit_flag = 0;
+      {
+        // window cache: context = sentence indices [lo, hi] minus the centre; rows up to index
+        // `want` (the right edge of the FULL window) enter the cache with this position
+        const int lo = max(0, pos - W + b), hi = min(slen - 1, pos + W - b);
+        const int want = min(slen - 1, pos + W);
+        const int nload = max(0, want - loaded_hi);
+        for (int k = lane; k < nload; k += 32) d->ld[k] = s_sen[loaded_hi + 1 + k];
+        if (lane == 0) {
+          d->center = center; d->b = b; d->cw = cw; d->nt = nt;
+          d->alpha = alpha_c;
+          d->exit_flag = 0;
+          d->cs_lo = (row_base + lo) % nu;
+          d->n_left = pos - lo;
+          d->n_right = hi - pos;
+          d->nload = nload;
+          d->ld_slot0 = (row_base + loaded_hi + 1) % nu;
+        }
+        loaded_hi = max(loaded_hi, want);
       }
       __syncwarp();
       ++q;
@@ -353,7 +377,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
   } else if (warp == ncw) {
     // ================================================================= loader warp
     const int ngmax = (p.negative + 1 + G - 1) / G;
-    int u_alloc = 0;
+    const int delta = nu - (2 * p.window + 1);  // cache slots beyond one full window = loader lead
     int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
     for (int q = 0;; ++q) {
       while (ctl->desc_ready <= q) __nanosleep(32);
@@ -365,18 +389,20 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         if (lane == 0) mbar_expect_tx(ubar, 0);
         break;
       }
-      const int cw = d->cw, nt = d->nt;
-      // ---- context rows -> u-ring
-      while (u_alloc + cw - ctl->urel > nu) __nanosleep(32);
+      const int nt = d->nt;
+      // ---- rows entering the sentence window -> cache slots.  A slot's previous occupant was
+      // last used (read and locally updated) `delta`+1 positions ago at the latest.
+      while (ctl->prog < q - delta) __nanosleep(32);
+      const int nload = d->nload;
       if (lane == 0) {
-        d->us0 = u_alloc % nu;
         d->vs0 = v_alloc % nv;
-        mbar_expect_tx(ubar, (unsigned)cw * rowb);
+        mbar_expect_tx(ubar, (unsigned)nload * rowb);
       }
       __syncwarp();
-      for (int k = lane; k < cw; k += 32)
-        bulk_load(uring + (unsigned)((u_alloc + k) % nu) * rowb, p.u + (long long)d->ctx[k] * p.D, rowb, ubar);
-      u_alloc += cw;
+      for (int k = lane; k < nload; k += 32) {
+        int sl = d->ld_slot0 + k; if (sl >= nu) sl -= nu;
+        bulk_load(uring + (unsigned)sl * rowb, p.u + (long long)d->ld[k] * p.D, rowb, ubar);
+      }
       // ---- target rows -> v-ring, group by group.  Every group barrier of the slot is armed
       // for every position (0 bytes when the position has fewer groups) so that all barriers
       // of a descriptor slot stay on the same phase.
@@ -423,13 +449,15 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       mbar_wait(ubar0 + slot * 8, par);
       const RingDesc *d = &desc[slot];
       const bool fin = d->exit_flag != 0;
-      const int cw = d->cw, nt = d->nt, us0 = d->us0, vs0 = d->vs0;
+      const int cw = d->cw, nt = d->nt, vs0 = d->vs0;
+      const int cs_lo = d->cs_lo, n_left = d->n_left;
       const float alpha = d->alpha;
-      // ---- context phase: gather + quantize + average (:431-449), thread per float4 column
+      // ---- context phase: cached rows -> quantize -> average (:431-449), thread per float4 column
       if (!fin && col_on) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int s = us0;
+        int s = cs_lo;
         for (int k = 0; k < cw; ++k) {
+          if (k == n_left) { if (++s == nu) s = 0; }  // skip the centre word's own row
           const float4 x = lds128(uring + (unsigned)s * rowb + colb);
           a0 = __fadd_rn(a0, quant<BM>(x.x, qp));
           a1 = __fadd_rn(a1, quant<BM>(x.y, qp));
@@ -442,7 +470,6 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       }
       consumer_bar(nct);  // A: context_avg visible; u rows consumed; previous staging row complete
       if (issuer) {
-        if (!fin) ctl->urel = ctl->urel + cw;
         if (pend_u) {  // scatter of the previous position's error to its context rows (:494-503)
           const unsigned eb = errbuf + (unsigned)(pend_q & 1) * rowb;
           for (int k = 0; k < pend_u->cw; ++k) bulk_reduce_add(p.u + (long long)pend_u->ctx[k] * p.D, eb, rowb);
@@ -548,6 +575,16 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
           acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
         sts128(errbuf + (unsigned)(q & 1) * rowb + colb, acc);
+        // the shard's own update (:501) is applied to the cached context rows right away
+        int s = cs_lo;
+        for (int k = 0; k < cw; ++k) {
+          if (k == n_left) { if (++s == nu) s = 0; }
+          const unsigned addr = uring + (unsigned)s * rowb + colb;
+          float4 x = lds128(addr);
+          x.x += acc.x; x.y += acc.y; x.z += acc.z; x.w += acc.w;
+          sts128(addr, x);
+          if (++s == nu) s = 0;
+        }
       }
       fence_async_smem();
       if (warp == 0)  // reported loss (:480-483): one lane per target, off the row loop's critical path
