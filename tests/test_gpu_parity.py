@@ -289,7 +289,7 @@ def test_fast_streaming_and_steps(large):
     assert tot[0] == tot[1]
 
 
-@pytest.mark.parametrize("kernel,serial", [(1, 0), (0, 1)])
+@pytest.mark.parametrize("kernel,serial", [(1, 0), (0, 1), (0, 0)])
 @pytest.mark.parametrize("b,D", [(0, 64), (0, 200), (2, 64)])
 def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
     """One shard, positions in order (register kernel; ring kernel with prefetch off): the
