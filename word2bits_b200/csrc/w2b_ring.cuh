@@ -29,15 +29,12 @@
 // (bumped after cp.async.bulk.wait_group.read) for "slot free again"; monotonic counters
 // for descriptors.
 //
-// Context rows live in a sliding-window cache: the u-"ring" holds the rows of the current
-// sentence around the centre word (each row is fetched ONCE, when it enters the window, and
-// stays for up to 2*window+1 positions).  After every position the consumers add the
-// accumulated error to the cached copies (:501) as well as scattering it to global memory, so a
-// shard always sees its own context updates immediately — exactly like one reference thread —
-// and only the updates of OTHER shards arrive with the delay of one window residency (the
-// reference's Hogwild threads have the same kind of delay).  Target rows are fetched one or two
-// positions ahead of their use; no update is ever lost (all scatters are atomic adds in L2).
-// ring_serial=1 additionally turns the cross-position prefetch off (parity aid).
+// Ordering semantics: rows of position p+1.. are fetched before position p's updates
+// land, so a context row shared by neighbouring positions is read one or two updates
+// stale; no update is ever lost (all scatters are atomic adds in L2).  This is the same
+// class of staleness the reference's Hogwild threads have (SURVEY section 7 "hard parts");
+// ring_serial=1 turns the prefetch off for parity work.  DESIGN.md quantifies the effect
+// and tests/test_gpu_parity.py holds it to the L3 bars.
 #pragma once
 #include "w2b_kernels.cuh"
 
@@ -47,13 +44,10 @@ constexpr int kND = 8;      // descriptor ring depth (positions in flight)
 constexpr int kMaxGrp = 8;  // max target groups per position
 
 struct RingDesc {
-  int cw, nt, exit_flag, vs0;
-  int cs_lo, n_left, n_right;  // context = cache slots cs_lo.. (n_left rows), [centre], n_right rows
-  int nload, ld_slot0;         // rows entering the window with this position -> cache slots ld_slot0..
+  int cw, nt, exit_flag, us0, vs0;
   float alpha;
   int center, b;
-  int ctx[2 * W2B_MAX_WINDOW];      // word ids of the context rows, in window order (u scatter)
-  int ld[W2B_MAX_WINDOW + 1];       // word ids of the rows to fetch
+  int ctx[2 * W2B_MAX_WINDOW];
   int tg[W2B_MAX_NEGATIVE + 1];
 };
 
@@ -62,6 +56,7 @@ struct RingCtl {
   unsigned long long vbar[kND][kMaxGrp];
   volatile int desc_ready;  // descriptors published by the sampler
   volatile int prog;        // positions whose descriptor is no longer needed by the consumers
+  volatile int urel;        // u slots released
   float sf[2][W2B_MAX_NEGATIVE + 1];  // +-f of every target of a position (reported loss, :480-483)
   double loss_out;
 };
@@ -149,8 +144,8 @@ __device__ __forceinline__ int mod_small(unsigned long long r, unsigned w) {
   return (int)(((hi % w) * two32 + lo % w) % w);
 }
 
-template <int BM, int NJ>
-__global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
+template <int BM, int NJ, int R>
+__global__ void __launch_bounds__((NJ + 2) * 32, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncw = (blockDim.x >> 5) - 2;  // consumer warps; then the loader warp, then the sampler warp
@@ -179,6 +174,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       for (int g = 0; g < kMaxGrp; ++g) mbar_init(&ctl->vbar[i][g], 1);
     }
     ctl->desc_ready = 0;
+    ctl->urel = 0;
     ctl->prog = 0;
     ctl->loss_out = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,9 +197,6 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
     const int negl = neg < 32 ? neg : 32;
     const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
     const unsigned long long JAn = c_JA[neg], JCn = c_JC[neg];
-    // sliding-window cache bookkeeping: cache row ids are handed out consecutively; row id of
-    // sentence index i is row_base + i and lives in slot (row_base + i) % nu
-    int row_base = 0, loaded_hi = -1;
     bool have_pre = false;
     unsigned long long r1_pre = 0, rd_pre = 0;
     int t_pre = 0;
@@ -229,8 +222,6 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         __syncwarp();
         if (status == 2) break;  // slice exhausted mid-sentence: nothing committed
         r = r2; cursor = c2; wc = w2; len = l2; sp = 0;
-        row_base = (row_base + loaded_hi + 1) % nu;  // the new sentence's rows follow the old one's in the ring
-        loaded_hi = -1;
         have_pre = false;
         // the shared learning rate (:53) is re-read once per sentence: other shards move it
         // every 10k words each, by ~1e-4 relative per update
@@ -310,7 +301,6 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       } else {
         r = r1;
       }
-      const int pos = sp, slen = len;  // this position, before the cursor moves on
       ++sp;
       if (sp >= len) len = 0;  // :505-509
       if (p.trace) {  // parity hook: one record per window draw, exactly what the oracle's trace holds
@@ -329,24 +319,10 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       if (cw == 0) continue;   // single-word or empty sentence: one window draw, nothing trained
       n_pos += 1; n_ctx += cw; n_tgt += nt;
       if (!p.train) continue;  // draws only: nothing is handed to the loader / consumers
-      {
-        // window cache: context = sentence indices [lo, hi] minus the centre; rows up to index
-        // `want` (the right edge of the FULL window) enter the cache with this position
-        const int lo = max(0, pos - W + b), hi = min(slen - 1, pos + W - b);
-        const int want = min(slen - 1, pos + W);
-        const int nload = max(0, want - loaded_hi);
-        for (int k = lane; k < nload; k += 32) d->ld[k] = s_sen[loaded_hi + 1 + k];
-        if (lane == 0) {
-          d->center = center; d->b = b; d->cw = cw; d->nt = nt;
-          d->alpha = alpha_c;
-          d->exit_flag = 0;
-          d->cs_lo = (row_base + lo) % nu;
-          d->n_left = pos - lo;
-          d->n_right = hi - pos;
-          d->nload = nload;
-          d->ld_slot0 = (row_base + loaded_hi + 1) % nu;
-        }
-        loaded_hi = max(loaded_hi, want);
+      if (lane == 0) {
+        d->center = center; d->b = b; d->cw = cw; d->nt = nt;
+        d->alpha = alpha_c;
+        d->exit_flag = 0;
       }
       __syncwarp();
       ++q;
@@ -377,7 +353,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
   } else if (warp == ncw) {
     // ================================================================= loader warp
     const int ngmax = (p.negative + 1 + G - 1) / G;
-    const int delta = nu - (2 * p.window + 1);  // cache slots beyond one full window = loader lead
+    int u_alloc = 0;
     int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
     for (int q = 0;; ++q) {
       while (ctl->desc_ready <= q) __nanosleep(32);
@@ -389,20 +365,18 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         if (lane == 0) mbar_expect_tx(ubar, 0);
         break;
       }
-      const int nt = d->nt;
-      // ---- rows entering the sentence window -> cache slots.  A slot's previous occupant was
-      // last used (read and locally updated) `delta`+1 positions ago at the latest.
-      while (ctl->prog < q - delta) __nanosleep(32);
-      const int nload = d->nload;
+      const int cw = d->cw, nt = d->nt;
+      // ---- context rows -> u-ring
+      while (u_alloc + cw - ctl->urel > nu) __nanosleep(32);
       if (lane == 0) {
+        d->us0 = u_alloc % nu;
         d->vs0 = v_alloc % nv;
-        mbar_expect_tx(ubar, (unsigned)nload * rowb);
+        mbar_expect_tx(ubar, (unsigned)cw * rowb);
       }
       __syncwarp();
-      for (int k = lane; k < nload; k += 32) {
-        int sl = d->ld_slot0 + k; if (sl >= nu) sl -= nu;
-        bulk_load(uring + (unsigned)sl * rowb, p.u + (long long)d->ld[k] * p.D, rowb, ubar);
-      }
+      for (int k = lane; k < cw; k += 32)
+        bulk_load(uring + (unsigned)((u_alloc + k) % nu) * rowb, p.u + (long long)d->ctx[k] * p.D, rowb, ubar);
+      u_alloc += cw;
       // ---- target rows -> v-ring, group by group.  Every group barrier of the slot is armed
       // for every position (0 bytes when the position has fewer groups) so that all barriers
       // of a descriptor slot stay on the same phase.
@@ -426,7 +400,9 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
     qp.bits = p.bitlevel;
     qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
     double loss = 0.0;                 // warp 0: one lane per target
-    int prev0 = -1, prev1 = -1;        // lane 0: slots whose reduce is committed but not yet confirmed read
+    int prev[R];                       // lane 0: slots whose reduce is committed but not yet confirmed read
+#pragma unroll
+    for (int t = 0; t < R; ++t) prev[t] = -1;
     const bool issuer = (warp == ncw - 1) && lane == 0;  // the last warp has the fewest rows: it scatters u
     const RingDesc *pend_u = nullptr;  // issuer: position whose u scatter is staged but not yet issued
     int pend_q = 0;
@@ -449,15 +425,13 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       mbar_wait(ubar0 + slot * 8, par);
       const RingDesc *d = &desc[slot];
       const bool fin = d->exit_flag != 0;
-      const int cw = d->cw, nt = d->nt, vs0 = d->vs0;
-      const int cs_lo = d->cs_lo, n_left = d->n_left;
+      const int cw = d->cw, nt = d->nt, us0 = d->us0, vs0 = d->vs0;
       const float alpha = d->alpha;
-      // ---- context phase: cached rows -> quantize -> average (:431-449), thread per float4 column
+      // ---- context phase: gather + quantize + average (:431-449), thread per float4 column
       if (!fin && col_on) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int s = cs_lo;
+        int s = us0;
         for (int k = 0; k < cw; ++k) {
-          if (k == n_left) { if (++s == nu) s = 0; }  // skip the centre word's own row
           const float4 x = lds128(uring + (unsigned)s * rowb + colb);
           a0 = __fadd_rn(a0, quant<BM>(x.x, qp));
           a1 = __fadd_rn(a1, quant<BM>(x.y, qp));
@@ -470,6 +444,7 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
       }
       consumer_bar(nct);  // A: context_avg visible; u rows consumed; previous staging row complete
       if (issuer) {
+        if (!fin) ctl->urel = ctl->urel + cw;
         if (pend_u) {  // scatter of the previous position's error to its context rows (:494-503)
           const unsigned eb = errbuf + (unsigned)(pend_q & 1) * rowb;
           for (int k = 0; k < pend_u->cw; ++k) bulk_reduce_add(p.u + (long long)pend_u->ctx[k] * p.D, eb, rowb);
@@ -480,88 +455,104 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
         }
       }
       if (fin) break;
-      // ---- target phase (:450-492): one warp per landed v row, two rows in flight per warp
-      float4 a[NJ], e[NJ];
+      // ---- target phase (:450-492): one warp per landed v row, R rows in flight per warp
+      // context_avg columns of this lane: re-read from shared memory at each use (registers are
+      // capped at 168/thread with 9+ warps per CTA; the R row buffers need them more)
+      float4 e[NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        a[j] = lds128(s_avg + coff[j]);
-        if (!on[j]) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int j = 0; j < NJ; ++j) e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       float *sf = ctl->sf[q & 1];
-      for (int i = warp; i < nt; i += 2 * ncw) {
-        const int i2 = i + ncw;
-        const bool two = i2 < nt;
-        const int ib = two ? i2 : i;  // a lone row is simply read twice; its second copy gets g = 0
-        mbar_wait(vbar0 + (slot * kMaxGrp + i / G) * 8, par);
-        if (two) mbar_wait(vbar0 + (slot * kMaxGrp + i2 / G) * 8, par);
-        int sA = vs0 + i; if (sA >= nv) sA -= nv;
-        int sB = vs0 + ib; if (sB >= nv) sB -= nv;
-        const unsigned rowA = vring + (unsigned)sA * rowb, rowB = vring + (unsigned)sB * rowb;
-        float4 xa[NJ], xb[NJ];
+      for (int i0 = warp; i0 < nt; i0 += R * ncw) {
+        // rows i0, i0+ncw, ... of this warp; a missing row re-reads row i0 and gets g = 0
+        int sl[R];
+        unsigned row[R];
+        bool have[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+          const int i = i0 + t * ncw;
+          have[t] = i < nt;
+          const int ii = have[t] ? i : i0;
+          if (have[t]) mbar_wait(vbar0 + (slot * kMaxGrp + ii / G) * 8, par);
+          int s = vs0 + ii; if (s >= nv) s -= nv;
+          sl[t] = s;
+          row[t] = vring + (unsigned)s * rowb;
+        }
+        float4 x[R][NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int t = 0; t < R; ++t) x[t][j] = lds128(row[t] + coff[j]);
+        float f[R];
+        {
+          float d0[R], d1[R], d2[R], d3[R];
+#pragma unroll
+          for (int t = 0; t < R; ++t) d0[t] = d1[t] = d2[t] = d3[t] = 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            float4 aj = lds128(s_avg + coff[j]);
+            if (!on[j]) aj = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+              x[t][j] = make_float4(quant<BM>(x[t][j].x, qp), quant<BM>(x[t][j].y, qp), quant<BM>(x[t][j].z, qp),
+                                    quant<BM>(x[t][j].w, qp));
+              d0[t] = fmaf(aj.x, x[t][j].x, d0[t]);
+              d1[t] = fmaf(aj.y, x[t][j].y, d1[t]);
+              d2[t] = fmaf(aj.z, x[t][j].z, d2[t]);
+              d3[t] = fmaf(aj.w, x[t][j].w, d3[t]);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < R; ++t) f[t] = (d0[t] + d1[t]) + (d2[t] + d3[t]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)  // R interleaved butterflies: every lane ends with the full sums
+#pragma unroll
+          for (int t = 0; t < R; ++t) f[t] += __shfl_xor_sync(kFull, f[t], o);
+        float g[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+          const int i = i0 + t * ncw;
+          g[t] = have[t] ? grad_scalar(f[t], i == 0 ? 1 : 0, alpha, p.exptab) : 0.f;
+          if (lane == 0 && have[t]) sf[i] = (i == 0) ? f[t] : -f[t];
+        }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          xa[j] = lds128(rowA + coff[j]);
-          xb[j] = lds128(rowB + coff[j]);
-        }
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+          const float4 aj = lds128(s_avg + coff[j]);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          xa[j] = make_float4(quant<BM>(xa[j].x, qp), quant<BM>(xa[j].y, qp), quant<BM>(xa[j].z, qp), quant<BM>(xa[j].w, qp));
-          xb[j] = make_float4(quant<BM>(xb[j].x, qp), quant<BM>(xb[j].y, qp), quant<BM>(xb[j].z, qp), quant<BM>(xb[j].w, qp));
-          p0 = fmaf(a[j].x, xa[j].x, p0); r0 = fmaf(a[j].x, xb[j].x, r0);
-          p1 = fmaf(a[j].y, xa[j].y, p1); r1 = fmaf(a[j].y, xb[j].y, r1);
-          p2 = fmaf(a[j].z, xa[j].z, p2); r2 = fmaf(a[j].z, xb[j].z, r2);
-          p3 = fmaf(a[j].w, xa[j].w, p3); r3 = fmaf(a[j].w, xb[j].w, r3);
-        }
-        float fa = (p0 + p1) + (p2 + p3), fb = (r0 + r1) + (r2 + r3);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {  // all lanes end up with the same sums
-          fa += __shfl_xor_sync(kFull, fa, o);
-          fb += __shfl_xor_sync(kFull, fb, o);
-        }
-        const float ga = grad_scalar(fa, i == 0 ? 1 : 0, alpha, p.exptab);
-        const float gb = two ? grad_scalar(fb, 0, alpha, p.exptab) : 0.f;
-        if (lane == 0) {
-          sf[i] = (i == 0) ? fa : -fa;
-          if (two) sf[i2] = -fb;
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          e[j].x = fmaf(ga, xa[j].x, fmaf(gb, xb[j].x, e[j].x));  // :487, quantized OLD v
-          e[j].y = fmaf(ga, xa[j].y, fmaf(gb, xb[j].y, e[j].y));
-          e[j].z = fmaf(ga, xa[j].z, fmaf(gb, xb[j].z, e[j].z));
-          e[j].w = fmaf(ga, xa[j].w, fmaf(gb, xb[j].w, e[j].w));
-          if (on[j]) {  // :490 — the update g*context_avg replaces the landed row in its slot
-            sts128(rowA + coff[j], make_float4(ga * a[j].x, ga * a[j].y, ga * a[j].z, ga * a[j].w));
-            if (two) sts128(rowB + coff[j], make_float4(gb * a[j].x, gb * a[j].y, gb * a[j].z, gb * a[j].w));
+          for (int t = 0; t < R; ++t) {
+            e[j].x = fmaf(g[t], x[t][j].x, e[j].x);  // :487, quantized OLD v
+            e[j].y = fmaf(g[t], x[t][j].y, e[j].y);
+            e[j].z = fmaf(g[t], x[t][j].z, e[j].z);
+            e[j].w = fmaf(g[t], x[t][j].w, e[j].w);
+            if (on[j] && have[t])  // :490 — the update g*context_avg replaces the landed row in its slot
+              sts128(row[t] + coff[j], make_float4(g[t] * aj.x, g[t] * aj.y, g[t] * aj.z, g[t] * aj.w));
           }
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          bulk_reduce_add(p.v + (long long)d->tg[i] * p.D, rowA, rowb);
-          if (two) bulk_reduce_add(p.v + (long long)d->tg[i2] * p.D, rowB, rowb);
+#pragma unroll
+          for (int t = 0; t < R; ++t)
+            if (have[t]) bulk_reduce_add(p.v + (long long)d->tg[i0 + t * ncw] * p.D, row[t], rowb);
           bulk_commit();
           if (p.serial) bulk_wait_all(); else bulk_wait_read<1>();
           // everything this lane committed before the group above has left shared memory
-          if (prev0 >= 0) s_rc[prev0] = s_rc[prev0] + 1;
-          if (prev1 >= 0) s_rc[prev1] = s_rc[prev1] + 1;
-          prev0 = sA;
-          prev1 = two ? sB : -1;
-          if (p.serial) {
-            s_rc[sA] = s_rc[sA] + 1;
-            if (two) s_rc[sB] = s_rc[sB] + 1;
-            prev0 = prev1 = -1;
+#pragma unroll
+          for (int t = 0; t < R; ++t) {
+            if (prev[t] >= 0) s_rc[prev[t]] = s_rc[prev[t]] + 1;
+            prev[t] = have[t] ? sl[t] : -1;
+            if (p.serial && have[t]) { s_rc[sl[t]] = s_rc[sl[t]] + 1; prev[t] = -1; }
           }
         }
         __syncwarp();
       }
       if (lane == 0) {  // confirm this warp's last rows (and, for the issuer, the u scatter) right away
         bulk_wait_read<0>();
-        if (prev0 >= 0) s_rc[prev0] = s_rc[prev0] + 1;
-        if (prev1 >= 0) s_rc[prev1] = s_rc[prev1] + 1;
-        prev0 = prev1 = -1;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+          if (prev[t] >= 0) s_rc[prev[t]] = s_rc[prev[t]] + 1;
+          prev[t] = -1;
+        }
       }
       // ---- error partials -> staging row (its scatter, :494-503, is issued after the next barrier A)
 #pragma unroll
@@ -575,16 +566,6 @@ __global__ void __launch_bounds__(352, 1) train_ring_kernel(TrainParams p, int n
           acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
         sts128(errbuf + (unsigned)(q & 1) * rowb + colb, acc);
-        // the shard's own update (:501) is applied to the cached context rows right away
-        int s = cs_lo;
-        for (int k = 0; k < cw; ++k) {
-          if (k == n_left) { if (++s == nu) s = 0; }
-          const unsigned addr = uring + (unsigned)s * rowb + colb;
-          float4 x = lds128(addr);
-          x.x += acc.x; x.y += acc.y; x.z += acc.z; x.w += acc.w;
-          sts128(addr, x);
-          if (++s == nu) s = 0;
-        }
       }
       fence_async_smem();
       if (warp == 0)  // reported loss (:480-483): one lane per target, off the row loop's critical path
