@@ -168,30 +168,25 @@ static apply_fn pick_apply(const w2b_ctx *c) {
 }
 
 typedef void (*ring_fn)(TrainParams, int, int, int);
-// Target rows in flight per consumer warp.  Registers cap it: a CTA with 9+ warps gets at most
-// 168 registers per thread (three warps share one SM sub-partition's 16K registers).
-static int ring_rows_in_flight(int nj) {
-  if (nj <= 4) return 4;
-  if (nj <= 6) return 3;
-  const char *e = getenv("W2B_RING_R");  // experiment hook for the D >= 800 kernels
-  const int r = e ? atoi(e) : 3;
-  return (r == 2) ? 2 : 3;
-}
+// Target rows in flight per consumer warp.  Measured on B200 (tools/quick_perf.py): R=2 wins
+// everywhere — R=3 at D=800 spills (a CTA with 9+ warps gets at most 168 registers per thread:
+// three warps share one SM sub-partition's 16K registers) and drops 5782 -> 4440 GB/s; R=4 at
+// D=400 costs the second CTA per SM (204 registers) and halves throughput.
 template <int BM>
 static ring_fn ring_by_nj(int nj) {
-  const int r = ring_rows_in_flight(nj);
   switch (nj) {
-    case 1: return train_ring_kernel<BM, 1, 4>;
-    case 2: return train_ring_kernel<BM, 2, 4>;
-    case 3: return train_ring_kernel<BM, 3, 4>;
-    case 4: return train_ring_kernel<BM, 4, 4>;
-    case 5: return train_ring_kernel<BM, 5, 3>;
-    case 6: return train_ring_kernel<BM, 6, 3>;
-    case 7: return r == 2 ? (ring_fn)train_ring_kernel<BM, 7, 2> : (ring_fn)train_ring_kernel<BM, 7, 3>;
-    case 8: return r == 2 ? (ring_fn)train_ring_kernel<BM, 8, 2> : (ring_fn)train_ring_kernel<BM, 8, 3>;
+    case 1: return train_ring_kernel<BM, 1, 2>;
+    case 2: return train_ring_kernel<BM, 2, 2>;
+    case 3: return train_ring_kernel<BM, 3, 2>;
+    case 4: return train_ring_kernel<BM, 4, 2>;
+    case 5: return train_ring_kernel<BM, 5, 2>;
+    case 6: return train_ring_kernel<BM, 6, 2>;
+    case 7: return train_ring_kernel<BM, 7, 2>;
+    case 8: return train_ring_kernel<BM, 8, 2>;
   }
   return nullptr;
 }
+static int ring_rows_in_flight(int) { return 2; }
 static ring_fn pick_ring(const w2b_ctx *c) {
   const int nj = (c->ncol + 31) / 32;
   switch (bm_of(c->cfg.bitlevel)) {
@@ -212,8 +207,11 @@ static void plan_ring(w2b_ctx *c) {
   const int nt = c->cfg.negative + 1;
   int G = (c->cfg.group > 0 && c->cfg.group <= 16) ? c->cfg.group : 13;
   if ((nt + G - 1) / G > kMaxGrp) G = (nt + kMaxGrp - 1) / kMaxGrp;
-  const int ncw = (c->ncol + 31) / 32;
-  if (ncw > 8) return;  // kernels are instantiated for D <= 1024
+  const int nj = (c->ncol + 31) / 32;
+  if (nj > 8) return;  // kernels are instantiated for D <= 1024
+  // consumer warps: one per 128 columns, but at least 4 — the target phase deals whole rows to
+  // warps, so narrow rows (D < 512) still get enough warps to walk 1+negative rows quickly
+  const int ncw = std::max(nj, 4);
   const long long D = c->cfg.layer1_size;
   // Small rows: aim for several CTAs per SM (more warps hide the per-row dependency chains);
   // k CTAs share the 227 KB (minus 1 KB reserved per CTA).  Take the largest k <= 4 whose

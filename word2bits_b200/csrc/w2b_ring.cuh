@@ -145,7 +145,7 @@ __device__ __forceinline__ int mod_small(unsigned long long r, unsigned w) {
 }
 
 template <int BM, int NJ, int R>
-__global__ void __launch_bounds__((NJ + 2) * 32, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
+__global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncw = (blockDim.x >> 5) - 2;  // consumer warps; then the loader warp, then the sampler warp
