@@ -133,3 +133,22 @@ def test_cli_messages_and_exit_codes(tmp_path):
                   run(refbin, "-train", golden, "-min-count", "1"),
                   run(refbin, "-train", golden, "-min-count", "5", "-debug", "0")]
         assert ours == theirs
+
+
+def test_parallel_tokenizer_equals_sequential(tmp_path, monkeypatch):
+    """The corpus reader cuts the file into chunks for several threads; word order, counts, the
+    token stream and every shard start must not depend on the number of chunks."""
+    import word2bits_b200 as w2b
+    path = zipf_corpus(str(tmp_path / "c.txt"), 300000, 8000, seed=21, newline_every=23)
+    monkeypatch.setenv("W2B_TOKENIZER_MIN_CHUNK", "50000")
+    res = []
+    for threads in ("1", "2", "5", "16"):
+        monkeypatch.setenv("W2B_TOKENIZER_THREADS", threads)
+        c = w2b.Corpus(path, 3)
+        s, f = c.shards(37)
+        res.append((c.words(), c.counts.copy(), c.tokens.copy(), c.train_words, s.copy(), f.copy()))
+    o = po.Corpus(path, 3)
+    assert res[0][0] == o.words() and np.array_equal(res[0][2], o.tokens)
+    for r in res[1:]:
+        assert r[0] == res[0][0] and np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2])
+        assert r[3] == res[0][3] and np.array_equal(r[4], res[0][4]) and np.array_equal(r[5], res[0][5])

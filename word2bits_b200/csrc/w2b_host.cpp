@@ -14,7 +14,9 @@
 
 #include <algorithm>
 #include <numeric>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "w2b.h"
@@ -152,6 +154,29 @@ struct w2b_corpus {
   std::vector<int64_t> ck_begin, ck_comp;
 };
 
+// Pass 1 over one chunk [begin, end) of the mapped file: chunk-local vocabulary in first-appearance
+// order + the chunk's tokens as local ids.  Chunks start right after a whitespace byte, so the
+// sequential reader would be in the same (empty-word) state there.
+struct ChunkResult {
+  WordMap map;
+  std::vector<uint32_t> raw;        // local entry id per token
+  std::vector<int64_t> ck_begin;    // byte offset of every kCkptEvery-th token of the chunk
+};
+
+static void tokenize_chunk(const uint8_t *buf, int64_t begin, int64_t end, ChunkResult *out) {
+  out->raw.reserve((size_t)((end - begin) / 5 + 16));
+  char word[kMaxWord];
+  int len = 0;
+  int64_t pos = begin, tb = 0;
+  while (next_token(buf, end, pos, word, len, tb)) {
+    int64_t e = out->map.find(word, len);
+    if (e < 0) e = out->map.insert(word, len);
+    out->map.count[e]++;
+    if ((int64_t)out->raw.size() % kCkptEvery == 0) out->ck_begin.push_back(tb);
+    out->raw.push_back((uint32_t)e);
+  }
+}
+
 extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out) {
   *out = nullptr;
   int fd = open(path, O_RDONLY);
@@ -172,25 +197,58 @@ extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out
       w2b_set_error("mmap failed for %s", path);
       return W2B_EIO;
     }
-    madvise(m, st.st_size, MADV_SEQUENTIAL);
     c->buf = (const uint8_t *)m;
   }
-  // pass 1: provisional ids in first-appearance order, </s> first (:276)
+  const bool dbg = getenv("W2B_TOKENIZER_DEBUG") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!dbg) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tokenizer] %-10s %.3f s\n", what, std::chrono::duration<double>(now - t_start).count());
+    t_start = now;
+  };
+  // ---- pass 1, parallel over chunks of the file (the reference's single fgetc loop, :277-293,
+  // runs at ~7 M words/s; the GPU consumes 30 M words/s)
+  const int64_t n = c->file_size;
+  int nthreads = (int)std::thread::hardware_concurrency();
+  if (const char *e = getenv("W2B_TOKENIZER_THREADS")) nthreads = atoi(e);
+  int64_t min_chunk = 4 << 20;
+  if (const char *e = getenv("W2B_TOKENIZER_MIN_CHUNK")) min_chunk = atoll(e);
+  nthreads = std::max(1, std::min(nthreads, 64));
+  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, n / std::max<int64_t>(min_chunk, 1)));
+  std::vector<int64_t> cut(nthreads + 1, n);
+  cut[0] = 0;
+  for (int t = 1; t < nthreads; ++t) {
+    int64_t p = n / nthreads * t;
+    if (p < cut[t - 1]) p = cut[t - 1];
+    // advance to just after the next whitespace byte: a clean token boundary
+    while (p < n && !(c->buf[p] == ' ' || c->buf[p] == '\t' || c->buf[p] == '\n')) ++p;
+    cut[t] = p < n ? p + 1 : n;
+  }
+  std::vector<ChunkResult> chunks(nthreads);
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t)
+      th.emplace_back(tokenize_chunk, c->buf, cut[t], cut[t + 1], &chunks[t]);
+    tokenize_chunk(c->buf, cut[0], cut[1], &chunks[0]);
+    for (auto &x : th) x.join();
+  }
+  lap("pass1");
+  // ---- merge in file order: global first-appearance order = chunk order, then local order; </s> first (:276)
   WordMap &map = c->map;
   map.insert("</s>", 4);
-  std::vector<uint32_t> raw;
-  raw.reserve((size_t)(c->file_size / 5 + 16));
-  std::vector<int64_t> ck_begin_raw;
-  char word[kMaxWord];
-  int len = 0;
-  int64_t pos = 0, begin = 0;
-  while (next_token(c->buf, c->file_size, pos, word, len, begin)) {
-    int64_t e = map.find(word, len);
-    if (e < 0) e = map.insert(word, len);
-    map.count[e]++;
-    if ((int64_t)raw.size() % kCkptEvery == 0) ck_begin_raw.push_back(begin);
-    raw.push_back((uint32_t)e);
+  std::vector<std::vector<uint32_t>> l2g(nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    const WordMap &lm = chunks[t].map;
+    l2g[t].resize(lm.off.size());
+    for (uint32_t e = 0; e < lm.off.size(); ++e) {
+      int64_t g = map.find(lm.str(e), (int)lm.wlen[e]);
+      if (g < 0) g = map.insert(lm.str(e), (int)lm.wlen[e]);
+      map.count[g] += lm.count[e];
+      l2g[t][e] = (uint32_t)g;
+    }
   }
+  lap("merge");
   // SortVocab (:215-242): </s> pinned at 0, the rest by count descending, ties in
   // first-appearance order (what glibc's qsort yields here; asserted against the
   // reference in tests), then the min_count cut.
@@ -204,22 +262,50 @@ extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out
     const uint32_t e = order[k];
     if (map.count[e] < min_count && k != 0) continue;
     c->final_id[e] = (int32_t)c->words.size();
-    c->words.push_back(nullptr);  // arena may still move: fixed up below
+    c->words.push_back(nullptr);
     c->cn.push_back(map.count[e]);
     c->train_words += map.count[e];
   }
   for (size_t e = 0; e < m; ++e)
     if (c->final_id[e] >= 0) c->words[c->final_id[e]] = map.str((uint32_t)e);
-  // compact to the in-vocab stream, remembering where every checkpoint lands in it
-  c->ids.reserve(raw.size());
-  for (size_t t = 0; t < raw.size(); ++t) {
-    if ((int64_t)t % kCkptEvery == 0) {
-      c->ck_begin.push_back(ck_begin_raw[t / kCkptEvery]);
-      c->ck_comp.push_back((int64_t)c->ids.size());
-    }
-    const int32_t id = c->final_id[raw[t]];
-    if (id >= 0) c->ids.push_back(id);
+  lap("sort");
+  // ---- compact to the in-vocab stream (parallel per chunk), remembering where every checkpoint lands
+  std::vector<int64_t> kept(nthreads, 0), base(nthreads + 1, 0);
+  {
+    auto count_kept = [&](int t) {
+      int64_t k = 0;
+      for (uint32_t le : chunks[t].raw) k += c->final_id[l2g[t][le]] >= 0;
+      kept[t] = k;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(count_kept, t);
+    count_kept(0);
+    for (auto &x : th) x.join();
   }
+  for (int t = 0; t < nthreads; ++t) base[t + 1] = base[t] + kept[t];
+  c->ids.resize((size_t)base[nthreads]);
+  std::vector<std::vector<int64_t>> ck_comp(nthreads);
+  {
+    auto fill = [&](int t) {
+      int64_t w = base[t];
+      const auto &raw = chunks[t].raw;
+      ck_comp[t].reserve(chunks[t].ck_begin.size());
+      for (size_t k = 0; k < raw.size(); ++k) {
+        if ((int64_t)k % kCkptEvery == 0) ck_comp[t].push_back(w);
+        const int32_t id = c->final_id[l2g[t][raw[k]]];
+        if (id >= 0) c->ids[(size_t)w++] = id;
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(fill, t);
+    fill(0);
+    for (auto &x : th) x.join();
+  }
+  for (int t = 0; t < nthreads; ++t) {
+    c->ck_begin.insert(c->ck_begin.end(), chunks[t].ck_begin.begin(), chunks[t].ck_begin.end());
+    c->ck_comp.insert(c->ck_comp.end(), ck_comp[t].begin(), ck_comp[t].end());
+  }
+  lap("compact");
   *out = c;
   return W2B_OK;
 }
