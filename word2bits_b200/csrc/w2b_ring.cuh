@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
           have[t] = i < nt;
           const int ii = have[t] ? i : i0;
           if (have[t]) mbar_wait(vbar0 + (slot * kMaxGrp + ii / G) * 8, par);
-          int s = vs0 + ii; if (s >= nv) s -= nv;
+          const int s = (vs0 + ii) % nv;  // a position may be longer than the ring (1+negative > nv)
           sl[t] = s;
           row[t] = vring + (unsigned)s * rowb;
         }
