@@ -55,6 +55,16 @@ int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int32_t *first
 int w2b_write_vectors(const char *path, const w2b_corpus *c, const float *vectors, int64_t V,
                       int64_t D, int binary);
 
+/* Packed vector file (the README's storage claim is realised only by gzip in the
+ * reference).  Header "<V> <D> <bitlevel>\n", then per word "<word> " + ceil(D*bitlevel/8) bytes
+ * (value j occupies bits [j*bitlevel, (j+1)*bitlevel) little-endian: bit 0 = sign (1 = negative),
+ * bit 1 (bitlevel 2) = magnitude (1 = .75)) + "\n".  bitlevel 1 and 2 only.  unpack restores the exact
+ * float32 levels, so `unpack -> w2b_write_vectors(binary=1)` feeds compute_accuracy unchanged. */
+int w2b_write_packed(const char *path, const w2b_corpus *c, const float *vectors, int64_t V, int64_t D,
+                     int bitlevel);
+int w2b_read_packed_header(const char *path, int64_t *V, int64_t *D, int *bitlevel);
+int w2b_read_packed(const char *path, float *vectors /* V*D */, char *words /* V*max_word */, int max_word);
+
 /* ------------------------------------------------------------------------ device path */
 typedef struct w2b_ctx w2b_ctx;
 
@@ -144,6 +154,11 @@ int w2b_download_raw(w2b_ctx *ctx, float *u, float *v);   /* fp32 master tables 
 int w2b_upload_raw(w2b_ctx *ctx, const float *u, const float *v);
 int w2b_download_table(w2b_ctx *ctx, int32_t *table);    /* 1e8 entries */
 int w2b_download_exptable(w2b_ctx *ctx, float *t);       /* 1000 entries */
+
+/* Resumable checkpoint (-save-every-epoch only keeps the non-resumable quantized
+ * sum, :540-557): fp32 master tables + learning rate + global word counter + epochs done. */
+int w2b_checkpoint_save(w2b_ctx *ctx, const char *path, int64_t epochs_done);
+int w2b_checkpoint_load(w2b_ctx *ctx, const char *path, int64_t *epochs_done);
 
 /* quantize(u+v) (:568-569), V*D floats into host memory. */
 int w2b_export(w2b_ctx *ctx, float *out);

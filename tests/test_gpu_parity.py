@@ -415,3 +415,25 @@ def test_ring_kernel_odd_shapes(D, W, neg, b, medium):
     assert abs(lg - lo) <= 0.02 * abs(lo) + 1.0, (lg, lo)
     u, v = t.download_raw()
     assert np.isfinite(u).all() and np.isfinite(v).all()
+
+
+def test_checkpoint_resume_is_exact(tmp_path, medium):
+    """fp32 master tables + alpha + word counter on disk; a run resumed from the
+    checkpoint after epoch 1 ends bit-identical to an uninterrupted run (strict mode)."""
+    c = w2b.Corpus(medium, 5)
+    kw = dict(size=20, window=5, negative=6, bitlevel=1, threads=2, iter=2, mode=w2b.MODE_STRICT)
+    a = w2b.Trainer(c, **kw)
+    a.train_epoch(); a.train_epoch()
+    b = w2b.Trainer(c, **kw)
+    b.train_epoch()
+    ck = str(tmp_path / "ck.bin")
+    b.checkpoint_save(ck, 1)
+    b.close()
+    r = w2b.Trainer(c, **kw)
+    assert r.checkpoint_load(ck) == 1
+    r.train_epoch()
+    for x, y in zip(a.download_raw(), r.download_raw()):
+        assert np.array_equal(bits(x), bits(y))
+    assert a.get_state() == r.get_state()
+    with pytest.raises(w2b.W2BError):
+        w2b.Trainer(c, size=24, window=5, negative=6, threads=2).checkpoint_load(ck)  # wrong shape

@@ -152,3 +152,25 @@ def test_parallel_tokenizer_equals_sequential(tmp_path, monkeypatch):
     for r in res[1:]:
         assert r[0] == res[0][0] and np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2])
         assert r[3] == res[0][3] and np.array_equal(r[4], res[0][4]) and np.array_equal(r[5], res[0][5])
+
+
+@pytest.mark.parametrize("bits", [1, 2])
+def test_packed_vector_file_round_trip(tmp_path, bits):
+    """bitlevel bits per value on disk; unpack restores the exact float levels."""
+    import word2bits_b200 as w2b
+    path = os.path.join(ROOT, "tests", "golden", "golden_corpus.txt")
+    c = w2b.Corpus(path, 1)
+    o = po.Corpus(path, 1)
+    m = po.OracleModel(o, 20, 3, 4, bits)
+    vec = m.export()                       # quantize(u+v): on the level set
+    out = str(tmp_path / "packed.bin")
+    c.write_packed(out, vec, bits)
+    words, back, b = w2b.read_packed(out)
+    assert b == bits and words == c.words()
+    assert np.array_equal(back.view(np.uint32), vec.view(np.uint32))
+    full = str(tmp_path / "full.bin")
+    c.write_vectors(full, vec, 1)
+    ratio = os.path.getsize(full) / os.path.getsize(out)
+    assert ratio > 5                       # 20 dims only: the word names dominate, still >> 1
+    with pytest.raises(w2b.W2BError):
+        c.write_packed(out, vec, 4)

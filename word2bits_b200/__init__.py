@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import MODE_FAST, MODE_STRICT, TABLE_SIZE, W2BError, check, lib, ptr
 
-__all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count"]
+__all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id"]
 
 
 def device_count():
@@ -55,6 +55,11 @@ class Corpus:
         vectors = np.ascontiguousarray(vectors, np.float32)
         V, D = vectors.shape
         check(lib.w2b_write_vectors(path.encode(), self.h, ptr(vectors), V, D, int(binary)))
+
+    def write_packed(self, path, vectors, bitlevel):
+        vectors = np.ascontiguousarray(vectors, np.float32)
+        V, D = vectors.shape
+        check(lib.w2b_write_packed(path.encode(), self.h, ptr(vectors), V, D, int(bitlevel)))
 
     def close(self):
         if self.h:
@@ -190,6 +195,14 @@ class Trainer:
         check(lib.w2b_quantize(self.h, ptr(x), ptr(out), x.size, bitlevel))
         return out
 
+    def checkpoint_save(self, path, epochs_done=0):
+        check(lib.w2b_checkpoint_save(self.h, path.encode(), int(epochs_done)))
+
+    def checkpoint_load(self, path):
+        n = C.c_int64()
+        check(lib.w2b_checkpoint_load(self.h, path.encode(), C.byref(n)))
+        return n.value
+
     # -- multi-GPU
     def device_ptrs(self):
         u, v, n = C.c_void_p(), C.c_void_p(), C.c_int64()
@@ -219,3 +232,14 @@ def nccl_unique_id():
     buf = (C.c_char * 128)()
     check(lib.w2b_nccl_unique_id(C.cast(buf, C.c_void_p)))
     return bytes(buf)
+
+
+def read_packed(path, max_word=64):
+    """(words, vectors, bitlevel) of a packed vector file written by Corpus.write_packed / -binary 2."""
+    V, D, b = C.c_int64(), C.c_int64(), C.c_int()
+    check(lib.w2b_read_packed_header(path.encode(), C.byref(V), C.byref(D), C.byref(b)))
+    vec = np.empty((V.value, D.value), np.float32)
+    names = np.zeros((V.value, max_word), np.uint8)
+    check(lib.w2b_read_packed(path.encode(), ptr(vec), ptr(names), max_word))
+    words = [bytes(r[: list(r).index(0)] if 0 in r else r).decode("latin1") for r in names]
+    return words, vec, b.value

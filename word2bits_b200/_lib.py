@@ -54,6 +54,7 @@ EXPORTS = [
     "w2b_strict_prefix", "w2b_apply_position", "w2b_get_state", "w2b_set_state", "w2b_download_raw",
     "w2b_upload_raw", "w2b_download_table", "w2b_download_exptable", "w2b_export", "w2b_quantize",
     "w2b_device_ptrs", "w2b_nccl_unique_id", "w2b_nccl_init", "w2b_sync", "w2b_scale_tables",
+    "w2b_write_packed", "w2b_read_packed_header", "w2b_read_packed", "w2b_checkpoint_save", "w2b_checkpoint_load",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -80,6 +81,11 @@ lib.w2b_corpus_tokens.restype = _P(_i32)
 lib.w2b_corpus_tokens.argtypes = [_vp]
 lib.w2b_corpus_shards.argtypes = [_vp, C.c_int, _vp, _vp]
 lib.w2b_write_vectors.argtypes = [C.c_char_p, _vp, _vp, _i64, _i64, C.c_int]
+lib.w2b_write_packed.argtypes = [C.c_char_p, _vp, _vp, _i64, _i64, C.c_int]
+lib.w2b_read_packed_header.argtypes = [C.c_char_p, _P(_i64), _P(_i64), _P(C.c_int)]
+lib.w2b_read_packed.argtypes = [C.c_char_p, _vp, _vp, C.c_int]
+lib.w2b_checkpoint_save.argtypes = [_vp, C.c_char_p, _i64]
+lib.w2b_checkpoint_load.argtypes = [_vp, C.c_char_p, _P(_i64)]
 lib.w2b_device_count.argtypes = [_P(C.c_int)]
 lib.w2b_suggest_shards.argtypes = [_P(Config), _P(C.c_int)]
 lib.w2b_create.argtypes = [_P(Config), _P(_vp)]

@@ -6,6 +6,9 @@
 //                shard count that fills the GPU is used instead of the reference's 12.
 //   -gpu N       CUDA device ordinal (default 0).
 //   -strict 1    parity mode: shards one after another, sequential IEEE arithmetic.
+//   -binary 2    packed output: bitlevel bits per value (bitlevel 1 and 2), see w2b_write_packed.
+//   -checkpoint F  write a resumable checkpoint (fp32 u, v, alpha, word counter) to F after every epoch.
+//   -resume F      continue from checkpoint F at the epoch it was written after.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,9 +37,11 @@ static void die(const char *what) {
   exit(1);
 }
 
+static int g_bitlevel = 1;
 static int write_vectors(const std::string &path, w2b_ctx *ctx, w2b_corpus *corpus, long long V, long long D,
                          int binary, std::vector<float> &buf) {
   if (w2b_export(ctx, buf.data())) return 1;
+  if (binary == 2) return w2b_write_packed(path.c_str(), corpus, buf.data(), V, D, g_bitlevel);
   return w2b_write_vectors(path.c_str(), corpus, buf.data(), V, D, binary);
 }
 
@@ -66,6 +71,10 @@ int main(int argc, char **argv) {
   if ((i = arg_pos("-classes", argc, argv)) > 0) classes = atoi(argv[i + 1]);
   if ((i = arg_pos("-gpu", argc, argv)) > 0) device = atoi(argv[i + 1]);
   if ((i = arg_pos("-strict", argc, argv)) > 0) strict = atoi(argv[i + 1]);
+  std::string ckpt_file, resume_file;
+  if ((i = arg_pos("-checkpoint", argc, argv)) > 0) ckpt_file = argv[i + 1];
+  if ((i = arg_pos("-resume", argc, argv)) > 0) resume_file = argv[i + 1];
+  g_bitlevel = bitlevel;
 
   printf("Starting training using file %s\n", train_file.c_str());  // :523
   w2b_corpus *corpus = nullptr;
@@ -119,7 +128,13 @@ int main(int argc, char **argv) {
   struct timespec t0;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   long long words_done = 0;
-  for (int iteration = 0; iteration < iter; iteration++) {
+  long long first_epoch = 0;
+  if (!resume_file.empty()) {
+    int64_t done = 0;
+    if (w2b_checkpoint_load(ctx, resume_file.c_str(), &done)) die("w2b_checkpoint_load");
+    first_epoch = done;
+  }
+  for (int iteration = (int)first_epoch; iteration < iter; iteration++) {
     printf("Starting epoch: %d\n", iteration);  // :533
     if (w2b_epoch_begin(ctx)) die("w2b_epoch_begin");
     double epoch_loss = 0;
@@ -141,6 +156,7 @@ int main(int argc, char **argv) {
       if (st.shards_done >= cfg.num_shards) break;
     }
     printf("Epoch Loss: %lf\n", epoch_loss);  // :539
+    if (!ckpt_file.empty() && w2b_checkpoint_save(ctx, ckpt_file.c_str(), iteration + 1)) die("w2b_checkpoint_save");
     if (classes == 0 && save_every_epoch) {     // :540-557
       char name[4200];
       snprintf(name, sizeof name, "%s_epoch%d", output_file.c_str(), iteration);

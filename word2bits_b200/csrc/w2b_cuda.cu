@@ -811,6 +811,72 @@ extern "C" int w2b_download_exptable(w2b_ctx *c, float *t) {
   return W2B_OK;
 }
 
+// Resumable checkpoint: header + raw fp32 u, v (device -> host in 64 MB pieces).
+struct CkptHeader {
+  char magic[8];
+  int64_t V, D, epochs_done, wca;
+  float alpha;
+  int32_t pad;
+};
+extern "C" int w2b_checkpoint_save(w2b_ctx *c, const char *path, int64_t epochs_done) {
+  CK(cudaSetDevice(c->cfg.device));
+  FILE *f = fopen(path, "wb");
+  if (!f) { w2b_set_error("cannot open %s for writing", path); return W2B_EIO; }
+  CkptHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, "W2BCKPT1", 8);
+  h.V = c->cfg.vocab_size; h.D = c->cfg.layer1_size; h.epochs_done = epochs_done;
+  unsigned long long w = 0;
+  CK(cudaMemcpy(&h.alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost));
+  h.wca = (int64_t)w;
+  fwrite(&h, sizeof h, 1, f);
+  const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
+  std::vector<float> buf(std::min(n, piece));
+  for (const float *src : {c->d_u, c->d_v})
+    for (size_t o = 0; o < n; o += piece) {
+      const size_t k = std::min(piece, n - o);
+      if (cudaMemcpy(buf.data(), src + o, k * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fclose(f);
+        w2b_set_error("checkpoint download failed");
+        return W2B_ECUDA;
+      }
+      fwrite(buf.data(), sizeof(float), k, f);
+    }
+  fclose(f);
+  return W2B_OK;
+}
+
+extern "C" int w2b_checkpoint_load(w2b_ctx *c, const char *path, int64_t *epochs_done) {
+  CK(cudaSetDevice(c->cfg.device));
+  FILE *f = fopen(path, "rb");
+  if (!f) { w2b_set_error("cannot open %s", path); return W2B_EIO; }
+  CkptHeader h;
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "W2BCKPT1", 8) != 0 || h.V != c->cfg.vocab_size ||
+      h.D != c->cfg.layer1_size) {
+    fclose(f);
+    w2b_set_error("%s is not a checkpoint of a %lld x %lld model", path, (long long)c->cfg.vocab_size,
+                  (long long)c->cfg.layer1_size);
+    return W2B_EIO;
+  }
+  const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
+  std::vector<float> buf(std::min(n, piece));
+  for (float *dst : {c->d_u, c->d_v})
+    for (size_t o = 0; o < n; o += piece) {
+      const size_t k = std::min(piece, n - o);
+      if (fread(buf.data(), sizeof(float), k, f) != k ||
+          cudaMemcpy(dst + o, buf.data(), k * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fclose(f);
+        w2b_set_error("checkpoint %s is truncated or the upload failed", path);
+        return W2B_EIO;
+      }
+    }
+  fclose(f);
+  if (epochs_done) *epochs_done = h.epochs_done;
+  c->have_tables = c->have_tables || false;
+  return w2b_set_state(c, h.alpha, h.wca);
+}
+
 extern "C" int w2b_export(w2b_ctx *c, float *out) {
   CK(cudaSetDevice(c->cfg.device));
   const long long n = c->cfg.vocab_size * c->cfg.layer1_size;

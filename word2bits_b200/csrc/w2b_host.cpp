@@ -384,3 +384,91 @@ extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const fl
   fclose(fo);
   return W2B_OK;
 }
+
+// ------------------------------------------------------------------------- packed vector files
+static inline int level_code(float x, int bits) {  // inverse of quantize() for bitlevel 1 / 2
+  const int neg = x < 0.f;
+  if (bits == 1) return neg;
+  return neg | ((fabsf(x) > 0.5f) ? 2 : 0);
+}
+static inline float level_value(int code, int bits) {
+  const float m = (bits == 1) ? (1.0f / 3) : ((code & 2) ? 0.75f : 0.25f);
+  return (code & 1) ? -m : m;
+}
+
+extern "C" int w2b_write_packed(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
+                                int bitlevel) {
+  if (bitlevel != 1 && bitlevel != 2) {
+    w2b_set_error("packed format supports bitlevel 1 and 2");
+    return W2B_EINVAL;
+  }
+  FILE *fo = fopen(path, "wb");
+  if (!fo) {
+    w2b_set_error("cannot open %s for writing", path);
+    return W2B_EIO;
+  }
+  fprintf(fo, "%lld %lld %d\n", (long long)V, (long long)D, bitlevel);
+  const int64_t nbytes = (D * bitlevel + 7) / 8;
+  std::vector<uint8_t> row(nbytes);
+  for (int64_t a = 0; a < V; ++a) {
+    fprintf(fo, "%s ", c->words[a]);
+    std::fill(row.begin(), row.end(), 0);
+    for (int64_t j = 0; j < D; ++j) {
+      const int code = level_code(vec[a * D + j], bitlevel);
+      const int64_t bit = j * bitlevel;
+      row[bit >> 3] |= (uint8_t)(code << (bit & 7));  // bitlevel divides 8: a value never straddles bytes
+    }
+    fwrite(row.data(), 1, nbytes, fo);
+    fputc('\n', fo);
+  }
+  fclose(fo);
+  return W2B_OK;
+}
+
+extern "C" int w2b_read_packed_header(const char *path, int64_t *V, int64_t *D, int *bitlevel) {
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    w2b_set_error("cannot open %s", path);
+    return W2B_EIO;
+  }
+  long long v = 0, d = 0;
+  int b = 0;
+  const int n = fscanf(f, "%lld %lld %d", &v, &d, &b);
+  fclose(f);
+  if (n != 3 || (b != 1 && b != 2)) {
+    w2b_set_error("%s is not a packed vector file", path);
+    return W2B_EIO;
+  }
+  *V = v; *D = d; *bitlevel = b;
+  return W2B_OK;
+}
+
+extern "C" int w2b_read_packed(const char *path, float *vec, char *words, int max_word) {
+  int64_t V, D;
+  int bits;
+  int rc = w2b_read_packed_header(path, &V, &D, &bits);
+  if (rc) return rc;
+  FILE *f = fopen(path, "rb");
+  int ch;
+  while ((ch = fgetc(f)) != EOF && ch != '\n') {}
+  const int64_t nbytes = (D * bits + 7) / 8;
+  std::vector<uint8_t> row(nbytes);
+  for (int64_t a = 0; a < V; ++a) {
+    int k = 0;
+    while ((ch = fgetc(f)) != EOF && ch != ' ')
+      if (words && k < max_word - 1) words[a * max_word + k++] = (char)ch;
+    if (words) words[a * max_word + k] = 0;
+    if (fread(row.data(), 1, nbytes, f) != (size_t)nbytes) {
+      fclose(f);
+      w2b_set_error("%s is truncated", path);
+      return W2B_EIO;
+    }
+    for (int64_t j = 0; j < D; ++j) {
+      const int64_t bit = j * bits;
+      vec[a * D + j] = level_value((row[bit >> 3] >> (bit & 7)) & ((1 << bits) - 1), bits);
+    }
+    fgetc(f);  // '\n'
+  }
+  fclose(f);
+  return W2B_OK;
+}
