@@ -165,6 +165,19 @@ int w2b_export(w2b_ctx *ctx, float *out);
 /* quantize() itself on the device, for known-answer tests (:73-108). */
 int w2b_quantize(w2b_ctx *ctx, const float *in, float *out, int64_t n, int bitlevel);
 
+/* Analogy evaluator, replaces src/compute-accuracy.c:63-189: same inputs
+ * (word2vec-binary vector file, optional re-quantisation, vocabulary threshold, question stream),
+ * same report text; all questions are scored on the GPU as one Q x V x D contraction with a fused
+ * arg-max.  questions_file NULL = stdin.  report may be NULL. */
+typedef struct {
+  int64_t questions_total, questions_seen, correct;
+  int64_t semantic_correct, semantic_seen, syntactic_correct, syntactic_seen;
+  int64_t vocab, size;
+  float gpu_ms; /* normalise + query build + scoring kernels, CUDA events */
+} w2b_accuracy;
+int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int64_t threshold, const char *questions_file,
+                         int device, w2b_accuracy *acc, char *report, int64_t report_cap);
+
 /* Multi-GPU replica averaging; G=1 contexts never touch NCCL. */
 int w2b_device_ptrs(w2b_ctx *ctx, void **u, void **v, int64_t *elems);
 int w2b_nccl_unique_id(void *id128);                                    /* ncclGetUniqueId */

@@ -437,3 +437,64 @@ def test_checkpoint_resume_is_exact(tmp_path, medium):
     assert a.get_state() == r.get_state()
     with pytest.raises(w2b.W2BError):
         w2b.Trainer(c, size=24, window=5, negative=6, threads=2).checkpoint_load(ck)  # wrong shape
+
+
+def _analogy_fixture(tmp_path, D=48, pairs=300, sections=8, per_section=120, bits=0, seed=5):
+    """Vector file (word2vec binary) with planted a:b offsets + a question file with `sections`
+    sections, OOV words, mixed case and a trailing EXIT-less EOF, like questions-words.txt."""
+    rng = np.random.default_rng(seed)
+    off = rng.normal(size=D).astype(np.float32) * 1.5
+    a = rng.normal(size=(pairs, D)).astype(np.float32)
+    b = a + off + 1.1 * rng.normal(size=(pairs, D)).astype(np.float32)
+    words = ["</s>"] + ["Alpha%d" % i for i in range(pairs)] + ["beta%d" % i for i in range(pairs)] + ["noise%d" % i for i in range(400)]
+    vec = np.concatenate([np.zeros((1, D), np.float32) + 0.01, a, b, rng.normal(size=(400, D)).astype(np.float32)])
+    if bits:
+        vec = po.quantize(vec * 0.3, bits)
+    vf = str(tmp_path / "vec.bin")
+    with open(vf, "wb") as f:
+        f.write(b"%d %d\n" % (len(words), D))
+        for w, row in zip(words, vec):
+            f.write(w.encode() + b" " + row.astype(np.float32).tobytes() + b"\n")
+    qf = str(tmp_path / "questions.txt")
+    with open(qf, "w") as f:
+        for s in range(sections):
+            f.write(": section-%d\n" % s)
+            for _ in range(per_section):
+                i, j = rng.integers(0, pairs, 2)
+                q = ["alpha%d" % i, "BETA%d" % i, "Alpha%d" % j, "beta%d" % j]
+                if rng.random() < 0.05:
+                    q[rng.integers(0, 4)] = "missingword"
+                f.write(" ".join(q) + "\n")
+    return vf, qf
+
+
+@pytest.mark.parametrize("bits,threshold", [(0, 0), (0, 700), (2, 0), (1, 0)])
+def test_gpu_analogy_evaluator_matches_reference(tmp_path, bits, threshold):
+    """the GPU evaluator prints what src/compute-accuracy.c prints.  fp32 vectors:
+    the report is identical text; 1-/2-bit vectors produce exact score ties whose winner depends on
+    the summation order even inside the reference, so the counters are held to +-2 %."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    refbin = os.path.join(root, "oracle", "_ref", "compute_accuracy")
+    if not os.path.exists(refbin):
+        pytest.skip("oracle/_ref/compute_accuracy not built")
+    vf, qf = _analogy_fixture(tmp_path, bits=bits)
+    want = subprocess.run([refbin, vf, str(bits), str(threshold)], stdin=open(qf), capture_output=True, text=True).stdout
+    got, acc = w2b.compute_accuracy(vf, qf, bitlevel=bits, threshold=threshold)
+    cli = subprocess.run([os.path.join(root, "word2bits_b200", "compute_accuracy"), vf, str(bits), str(threshold)],
+                         stdin=open(qf), capture_output=True, text=True).stdout
+    assert cli == got
+    assert acc["questions_total"] == 8 * 120 and acc["questions_seen"] > 0
+    if bits == 0:
+        assert got == want
+        assert acc["correct"] > 0.3 * acc["questions_seen"]   # the planted offsets are recoverable
+    else:
+        import re
+        def nums(txt):
+            return [float(x) for x in re.findall(r"[-+]?\d+\.\d+|\d+", txt)]
+        gw, gg = nums(want), nums(got)
+        assert len(gw) == len(gg) and want.splitlines()[1] == got.splitlines()[1]
+        assert want.splitlines()[-1] == got.splitlines()[-1]          # questions seen / total: exact
+        total_w = [l for l in want.splitlines() if l.startswith("Total accuracy")][-1]
+        total_g = [l for l in got.splitlines() if l.startswith("Total accuracy")][-1]
+        assert abs(nums(total_w)[0] - nums(total_g)[0]) <= 2.0, (total_w, total_g)

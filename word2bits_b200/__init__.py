@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import MODE_FAST, MODE_STRICT, TABLE_SIZE, W2BError, check, lib, ptr
 
-__all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id"]
+__all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id", "compute_accuracy"]
 
 
 def device_count():
@@ -243,3 +243,12 @@ def read_packed(path, max_word=64):
     check(lib.w2b_read_packed(path.encode(), ptr(vec), ptr(names), max_word))
     words = [bytes(r[: list(r).index(0)] if 0 in r else r).decode("latin1") for r in names]
     return words, vec, b.value
+
+
+def compute_accuracy(vectors_file, questions_file, bitlevel=0, threshold=0, device=0):
+    """GPU port of the reference's compute_accuracy: returns (report text, dict of counters)."""
+    acc = _lib.Accuracy()
+    buf = C.create_string_buffer(1 << 20)
+    check(lib.w2b_compute_accuracy(vectors_file.encode(), int(bitlevel), int(threshold), questions_file.encode(),
+                                   int(device), C.byref(acc), buf, len(buf)))
+    return buf.value.decode("latin1"), {k: getattr(acc, k) for k, _ in acc._fields_}

@@ -40,6 +40,12 @@ class StepStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Accuracy(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("questions_total", "questions_seen", "correct", "semantic_correct",
+                                         "semantic_seen", "syntactic_correct", "syntactic_seen", "vocab", "size")] + \
+               [("gpu_ms", C.c_float)]
+
+
 class TraceRec(C.Structure):
     _fields_ = [("center", C.c_int32), ("b", C.c_int32), ("cw", C.c_int32), ("ntargets", C.c_int32),
                 ("targets", C.c_int32 * 64), ("alpha", C.c_float)]
@@ -54,7 +60,7 @@ EXPORTS = [
     "w2b_strict_prefix", "w2b_apply_position", "w2b_get_state", "w2b_set_state", "w2b_download_raw",
     "w2b_upload_raw", "w2b_download_table", "w2b_download_exptable", "w2b_export", "w2b_quantize",
     "w2b_device_ptrs", "w2b_nccl_unique_id", "w2b_nccl_init", "w2b_sync", "w2b_scale_tables",
-    "w2b_write_packed", "w2b_read_packed_header", "w2b_read_packed", "w2b_checkpoint_save", "w2b_checkpoint_load",
+    "w2b_write_packed", "w2b_read_packed_header", "w2b_read_packed", "w2b_checkpoint_save", "w2b_checkpoint_load", "w2b_compute_accuracy",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -86,6 +92,7 @@ lib.w2b_read_packed_header.argtypes = [C.c_char_p, _P(_i64), _P(_i64), _P(C.c_in
 lib.w2b_read_packed.argtypes = [C.c_char_p, _vp, _vp, C.c_int]
 lib.w2b_checkpoint_save.argtypes = [_vp, C.c_char_p, _i64]
 lib.w2b_checkpoint_load.argtypes = [_vp, C.c_char_p, _P(_i64)]
+lib.w2b_compute_accuracy.argtypes = [C.c_char_p, C.c_int, _i64, C.c_char_p, C.c_int, _P(Accuracy), C.c_char_p, _i64]
 lib.w2b_device_count.argtypes = [_P(C.c_int)]
 lib.w2b_suggest_shards.argtypes = [_P(Config), _P(C.c_int)]
 lib.w2b_create.argtypes = [_P(Config), _P(_vp)]

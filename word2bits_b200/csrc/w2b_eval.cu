@@ -1,0 +1,309 @@
+// Analogy evaluator on the GPU — the "next" row after the training path.
+// Replaces src/compute-accuracy.c:63-189: load word2vec-binary vectors, optional re-quantize,
+// L2-normalise (:96-111), and for every question a:b :: c:? take vec = (M[b] - M[a]) + M[c]
+// (:155) and the arg-max cosine over the whole vocabulary except the three query words
+// (:158-177), first index winning ties and only strictly positive scores counting (bestd
+// starts at 0, :150).  Here all questions are scored together as one Q x V x D contraction
+// (fp32 SIMT tiles — arg-max parity needs fp32, so no tensor-core path yet) with a fused
+// arg-max epilogue; the report text is the reference's, line for line.
+#include <cuda_runtime.h>
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "w2b.h"
+#include "w2b_internal.h"
+#include "w2b_quant.cuh"
+
+using namespace w2b;
+
+#define CKE(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      w2b_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return W2B_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+namespace {
+
+// quantize (:102) + L2 normalise (:103-106): one warp per row.
+__global__ void eval_normalize_kernel(float *M, long long words, long long D, int bits) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= words) return;
+  QParams qp;
+  qp.bits = bits;
+  qp.seg = (bits >= 4) ? exp2f((float)(bits - 1)) : 1.f;
+  float *r = M + row * D;
+  float s = 0.f;
+  for (long long a = lane; a < D; a += 32) {
+    const float q = quant<9>(r[a], qp);
+    r[a] = q;
+    s = fmaf(q, q, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  const float len = sqrtf(s);
+  for (long long a = lane; a < D; a += 32) r[a] = __fdiv_rn(r[a], len);
+}
+
+// vec = (M[b2] - M[b1]) + M[b3] (:155), rows padded to a multiple of 64 with zeros.
+__global__ void eval_query_kernel(const float *M, const int *q3, float *Q, long long nq, long long D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * D) return;
+  const long long q = i / D, a = i % D;
+  const int b1 = q3[q * 3], b2 = q3[q * 3 + 1], b3 = q3[q * 3 + 2];
+  Q[i] = __fadd_rn(__fsub_rn(M[b2 * D + a], M[b1 * D + a]), M[b3 * D + a]);
+}
+
+// scores = Q (nq x D) . M^T (D x words), 64 x 64 tile per CTA, 4 x 4 per thread, fused arg-max:
+// best[q] = max over c not in {b1,b2,b3} with score > 0 of (score, smallest c).
+constexpr int TM = 64, TN = 64, TK = 16;
+__global__ void __launch_bounds__(256) eval_score_kernel(const float *Q, const float *M, const int *q3,
+                                                         unsigned long long *best, long long nq, long long words,
+                                                         long long D) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4 x 4 outputs
+  const long long q0 = (long long)blockIdx.y * TM, c0 = (long long)blockIdx.x * TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long k0 = 0; k0 < D; k0 += TK) {
+    // 64 rows x 16 k per operand = 1024 floats, 4 per thread
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int e = tid + l * 256;
+      const int r = e >> 4, k = e & 15;
+      const long long qa = q0 + r, ca = c0 + r, ka = k0 + k;
+      As[k][r] = (qa < nq && ka < D) ? Q[qa * D + ka] : 0.f;
+      Bs[k][r] = (ca < words && ka < D) ? M[ca * D + ka] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long q = q0 + ty * 4 + i;
+    const bool qok = q < nq;  // no early exit: the shuffles below need the whole warp
+    const int b1 = qok ? q3[q * 3] : -1, b2 = qok ? q3[q * 3 + 1] : -1, b3 = qok ? q3[q * 3 + 2] : -1;
+    unsigned long long key = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long c = c0 + tx * 4 + j;
+      const float s = acc[i][j];
+      if (qok && c < words && c != b1 && c != b2 && c != b3 && s > 0.f) {
+        const unsigned long long k2 =
+            ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)c);
+        key = k2 > key ? k2 : key;
+      }
+    }
+    // combine the 16 threads of this row (same ty): lanes tx = 0..15 are contiguous in a half warp
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, key, o);
+      key = other > key ? other : key;
+    }
+    if (tx == 0 && key && qok) atomicMax(best + q, key);
+  }
+}
+
+std::string upper(std::string s) {
+  for (auto &ch : s) ch = (char)toupper((unsigned char)ch);
+  return s;
+}
+
+}  // namespace
+
+// Reads the word2vec-binary file exactly like :85-111 (names up to the first ' ', '\n' skipped,
+// upper-cased; D raw float32 per word).
+static int read_vectors(const char *path, long long threshold, std::vector<std::string> &names,
+                        std::vector<float> &M, long long &words, long long &size) {
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    w2b_set_error("Input file not found");
+    return W2B_EIO;
+  }
+  if (fscanf(f, "%lld", &words) != 1) { fclose(f); w2b_set_error("bad header"); return W2B_EIO; }
+  if (threshold && words > threshold) words = threshold;
+  if (fscanf(f, "%lld", &size) != 1) { fclose(f); w2b_set_error("bad header"); return W2B_EIO; }
+  names.resize(words);
+  M.resize((size_t)words * size);
+  for (long long b = 0; b < words; ++b) {
+    std::string w;
+    for (;;) {
+      const int ch = fgetc(f);
+      if (ch == EOF || ch == ' ') break;
+      if (ch != '\n' && w.size() < 50) w.push_back((char)ch);
+    }
+    names[b] = upper(w);
+    if (fread(&M[(size_t)b * size], sizeof(float), size, f) != (size_t)size) {
+      fclose(f);
+      w2b_set_error("vector file truncated at word %lld", b);
+      return W2B_EIO;
+    }
+  }
+  fclose(f);
+  return W2B_OK;
+}
+
+extern "C" int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int64_t threshold,
+                                    const char *questions_file, int device, w2b_accuracy *acc, char *report,
+                                    int64_t report_cap) {
+  std::vector<std::string> names;
+  std::vector<float> M;
+  long long words = 0, size = 0;
+  int rc = read_vectors(vectors_file, threshold, names, M, words, size);
+  if (rc) return rc;
+  std::unordered_map<std::string, int> first;  // the reference's linear strcmp scan = first match (:140-145)
+  for (long long b = words - 1; b >= 0; --b) first[names[b]] = (int)b;
+  auto find = [&](const std::string &s) -> long long {
+    auto it = first.find(s);
+    return it == first.end() ? words : it->second;
+  };
+
+  // ---- parse the question stream the way the scanf loop does (:113-147), resolving ids
+  FILE *qf = questions_file ? fopen(questions_file, "rb") : stdin;
+  if (!qf) { w2b_set_error("questions file not found"); return W2B_EIO; }
+  std::vector<std::string> tok;
+  {
+    char buf[2048];
+    while (fscanf(qf, "%2000s", buf) == 1) tok.push_back(buf);
+    if (questions_file) fclose(qf);
+  }
+  struct Ev { int kind; std::string name; long long b1, b2, b3; std::string st4; int qidx; };  // 0 = section, 1 = question
+  std::vector<Ev> events;
+  std::vector<int> q3;
+  size_t t = 0;
+  std::string st1;
+  for (;;) {
+    const bool eof = t >= tok.size();
+    if (!eof) st1 = upper(tok[t++]);
+    if (st1 == ":" || st1 == "EXIT" || eof) {
+      Ev e{0, "", 0, 0, 0, "", -1};
+      const bool eof2 = t >= tok.size();
+      if (!eof2) e.name = tok[t++];
+      e.b1 = eof2 ? 1 : 0;  // b1 = "stream ended here"
+      events.push_back(e);
+      if (eof2) break;
+      continue;
+    }
+    std::string st2 = t < tok.size() ? upper(tok[t++]) : st1;
+    std::string st3 = t < tok.size() ? upper(tok[t++]) : st2;
+    std::string st4 = t < tok.size() ? upper(tok[t++]) : st3;
+    Ev e{1, "", find(st1), find(st2), find(st3), st4, -1};
+    if (e.b1 != words && e.b2 != words && e.b3 != words && find(st4) != words) {
+      e.qidx = (int)(q3.size() / 3);
+      q3.push_back((int)e.b1); q3.push_back((int)e.b2); q3.push_back((int)e.b3);
+    }
+    events.push_back(e);
+  }
+  const long long nq = (long long)q3.size() / 3;
+
+  // ---- GPU: normalise, build queries, score + arg-max
+  std::vector<unsigned long long> best(nq > 0 ? nq : 1, 0);
+  float ms = 0.f;
+  if (nq > 0) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
+      w2b_set_error("no CUDA device %d: the evaluator has no CPU fallback", device);
+      return W2B_ECUDA;
+    }
+    CKE(cudaSetDevice(device));
+    float *dM = nullptr, *dQ = nullptr;
+    int *dq3 = nullptr;
+    unsigned long long *dbest = nullptr;
+    CKE(cudaMalloc(&dM, M.size() * sizeof(float)));
+    CKE(cudaMalloc(&dQ, (size_t)nq * size * sizeof(float)));
+    CKE(cudaMalloc(&dq3, q3.size() * sizeof(int)));
+    CKE(cudaMalloc(&dbest, nq * sizeof(unsigned long long)));
+    CKE(cudaMemcpy(dM, M.data(), M.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CKE(cudaMemcpy(dq3, q3.data(), q3.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CKE(cudaMemset(dbest, 0, nq * sizeof(unsigned long long)));
+    cudaEvent_t e0, e1;
+    CKE(cudaEventCreate(&e0));
+    CKE(cudaEventCreate(&e1));
+    CKE(cudaEventRecord(e0));
+    eval_normalize_kernel<<<(unsigned)((words + 7) / 8), 256>>>(dM, words, size, bitlevel);
+    eval_query_kernel<<<(unsigned)((nq * size + 255) / 256), 256>>>(dM, dq3, dQ, nq, size);
+    dim3 grid((unsigned)((words + TN - 1) / TN), (unsigned)((nq + TM - 1) / TM));
+    eval_score_kernel<<<grid, 256>>>(dQ, dM, dq3, dbest, nq, words, size);
+    CKE(cudaGetLastError());
+    CKE(cudaEventRecord(e1));
+    CKE(cudaMemcpy(best.data(), dbest, nq * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CKE(cudaEventElapsedTime(&ms, e0, e1));
+    cudaFree(dM); cudaFree(dQ); cudaFree(dq3); cudaFree(dbest);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+
+  // ---- replay the control flow of :113-187 to produce the same report
+  std::string out = "Starting eval...\n";
+  char line[512];
+  int TCN = 0, CCN = 0, TACN = 0, CACN = 0, SECN = 0, SYCN = 0, SEAC = 0, SYAC = 0, QID = 0, TQ = 0, TQS = 0;
+  for (const Ev &e : events) {
+    if (e.kind == 0) {
+      if (TCN == 0) TCN = 1;
+      if (QID != 0) {
+        snprintf(line, sizeof line, "ACCURACY TOP1: %.2f %%  (%d / %d)\n", CCN / (float)TCN * 100, CCN, TCN);
+        out += line;
+        snprintf(line, sizeof line,
+                 "Total accuracy: %.2f %%   Semantic accuracy: %.2f %%   Syntactic accuracy: %.2f %% \n",
+                 CACN / (float)TACN * 100, SEAC / (float)SECN * 100, SYAC / (float)SYCN * 100);
+        out += line;
+      }
+      QID++;
+      if (e.b1) break;  // stream ended
+      out += e.name + ":\n";
+      TCN = 0;
+      CCN = 0;
+      continue;
+    }
+    TQ++;
+    if (e.qidx < 0) continue;
+    TQS++;
+    const unsigned long long key = best[e.qidx];
+    std::string bestw;
+    if (key) bestw = names[0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)];
+    if (e.st4 == bestw) {
+      CCN++; CACN++;
+      if (QID <= 5) SEAC++; else SYAC++;
+    }
+    if (QID <= 5) SECN++; else SYCN++;
+    TCN++;
+    TACN++;
+  }
+  snprintf(line, sizeof line, "Questions seen / total: %d %d   %.2f %% \n", TQS, TQ, TQS / (float)TQ * 100);
+  out += line;
+  if (acc) {
+    acc->questions_total = TQ; acc->questions_seen = TQS; acc->correct = CACN;
+    acc->semantic_correct = SEAC; acc->semantic_seen = SECN; acc->syntactic_correct = SYAC; acc->syntactic_seen = SYCN;
+    acc->gpu_ms = ms; acc->vocab = words; acc->size = size;
+  }
+  if (report && report_cap > 0) {
+    strncpy(report, out.c_str(), (size_t)report_cap - 1);
+    report[report_cap - 1] = 0;
+  }
+  return W2B_OK;
+}
