@@ -391,7 +391,8 @@ def test_planted_topic_quality(tmp_path):
 
 
 @pytest.mark.parametrize("D,W,neg,b", [(4, 1, 0, 1), (8, 2, 1, 2), (100, 5, 5, 1), (256, 20, 40, 0), (1024, 3, 7, 1),
-                                         (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (12, 5, 3, 4)])
+                                         (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (12, 5, 3, 4), (800, 10, 63, 1),
+                                         (100, 5, 63, 1)])
 def test_ring_kernel_odd_shapes(D, W, neg, b, medium):
     """Production kernel on edge geometries (negative=0, window 1..30, D 4..1024, > 32 negatives):
     terminates, trains every position the oracle's trace holds, loss within 2 % of the oracle."""

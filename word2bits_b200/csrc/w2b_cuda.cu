@@ -204,11 +204,6 @@ static ring_fn pick_ring(const w2b_ctx *c) {
 static void plan_ring(w2b_ctx *c) {
   c->ring = false;
   if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
-  // validated envelope of the ring kernel (tests/test_gpu_parity.py): up to 40 negatives and a
-  // v-ring that holds a whole position; anything else takes the register kernel (a wrap of one
-  // position around the ring, 1+negative > nv, hangs on hardware — open item for round 2)
-  const bool any_shape = getenv("W2B_RING_ANY") != nullptr;  // experiment hook: lift the envelope
-  if (c->cfg.negative > 40 && !any_shape) return;
   const int nt = c->cfg.negative + 1;
   int G = (c->cfg.group > 0 && c->cfg.group <= 16) ? c->cfg.group : 13;
   if ((nt + G - 1) / G > kMaxGrp) G = (nt + kMaxGrp - 1) / kMaxGrp;
@@ -244,7 +239,6 @@ static void plan_ring(w2b_ctx *c) {
     if (cand < nv_min) return;
     nv = cand;
   }
-  if (nv < nt && !any_shape) return;
   c->ring = true;
   c->ring_g = G;
   c->ring_nu = nu;
