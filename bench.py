@@ -36,14 +36,21 @@ def zipf_cdf(v):
 
 
 def synth_ids(n, seed, cdf):
-    """n token ids in [1, V] (id = Zipf rank, so the vocabulary is already count-sorted)."""
-    rng = np.random.default_rng(seed)
+    """n token ids in [1, V] (id = Zipf rank, so the vocabulary is already count-sorted).
+    Deterministic: chunk c of 4 Mi tokens is drawn from default_rng([seed, c]); chunks are filled by a
+    thread pool (numpy releases the GIL inside random() and searchsorted())."""
+    from concurrent.futures import ThreadPoolExecutor
     out = np.empty(n, np.int32)
-    step = 1 << 24
-    for a in range(0, n, step):
-        b = min(n, a + step)
-        out[a:b] = np.searchsorted(cdf, rng.random(b - a)).astype(np.int32) + 1
-    np.minimum(out, len(cdf), out=out)
+    step = 1 << 22
+    vmax = len(cdf)
+
+    def fill(c):
+        a, b = c * step, min(n, (c + 1) * step)
+        rng = np.random.default_rng([seed, c])
+        out[a:b] = np.minimum(np.searchsorted(cdf, rng.random(b - a)) + 1, vmax)
+
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(fill, range((n + step - 1) // step)))
     return out
 
 
@@ -206,7 +213,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--words-per-shard", type=int, default=16384)
+    ap.add_argument("--words-per-shard", type=int, default=65536)
     ap.add_argument("--sync-every", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

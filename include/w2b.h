@@ -84,7 +84,7 @@ typedef struct {
   int32_t device;      /* CUDA device ordinal */
   int32_t mode;        /* W2B_MODE_FAST | W2B_MODE_STRICT */
   int32_t group;       /* fast mode: target rows in flight per CTA step (0 = default) */
-  int32_t plain_store; /* fast mode: 1 = racy load/add/store like the reference, 0 = red.add */
+  int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
   int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
   int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed */

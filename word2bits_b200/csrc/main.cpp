@@ -140,8 +140,9 @@ int main(int argc, char **argv) {
     double epoch_loss = 0;
     for (;;) {
       w2b_step_stats st;
-      // ~10k words per shard per step = the cadence of the reference's progress line (:379)
-      if (w2b_train_step(ctx, debug_mode > 1 ? 10000 : 0, &st)) die("w2b_train_step");
+      // 50k words per shard per step: progress lines 5x less often than the reference (:379), steps long
+      // enough that the whole-sentence overshoot at a step boundary (<= ~1.2k words) stays ~1 %
+      if (w2b_train_step(ctx, debug_mode > 1 ? 50000 : 0, &st)) die("w2b_train_step");
       epoch_loss += st.loss;
       words_done += st.words;
       if (debug_mode > 1) {  // :384-387 (Words/sec here is wall-clock and whole-job, not per CPU thread)

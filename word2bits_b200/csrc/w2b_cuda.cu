@@ -106,6 +106,7 @@ struct w2b_ctx {
   long long stage_cap = 0, stage_len = 0, stage_margin = 4096;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned long long *d_scratch = nullptr;  // 64 B: word-count all-reduce
   nccl_comm comm = nullptr;
   int rank = 0, nranks = 1;
   long long wca_at_sync = 0;
@@ -338,7 +339,22 @@ extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
   return W2B_OK;
 }
 
+static int create_impl(const w2b_config *cfg, w2b_ctx **out);
 extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
+  *out = nullptr;
+  w2b_ctx *c = nullptr;
+  const int rc = create_impl(cfg, &c);
+  if (rc) {
+    const std::string keep = w2b_last_error();  // destroy must not clobber the message
+    if (c) w2b_destroy(c);
+    w2b_set_error("%s", keep.c_str());
+    return rc;
+  }
+  *out = c;
+  return W2B_OK;
+}
+
+static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   *out = nullptr;
   int rc = validate(cfg);
   if (rc) return rc;
@@ -350,13 +366,13 @@ extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
     return W2B_ECUDA;
   }
   w2b_ctx *c = new w2b_ctx();
+  *out = c;  // owned by the caller from here on (destroyed there if anything below fails)
   c->cfg = *cfg;
   if (c->cfg.shard_end <= c->cfg.shard_begin) {
     c->cfg.shard_begin = 0;
     c->cfg.shard_end = cfg->num_shards;
   }
   if (c->cfg.shard_end > cfg->num_shards) {
-    delete c;
     w2b_set_error("shard range exceeds num_shards");
     return W2B_EINVAL;
   }
@@ -392,7 +408,12 @@ extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
   CK(cudaMemset(c->d_wca, 0, sizeof(unsigned long long)));
   CK(cudaMemcpy(c->d_alpha, &cfg->alpha, sizeof(float), cudaMemcpyHostToDevice));
   c->h_shards.assign(c->nlocal, ShardState());
-  *out = c;
+  {  // expTable (:614-618) does not depend on the corpus: ready as soon as the context exists
+    float t[kExpN];
+    w2b_exptable(t);
+    CK(cudaMemcpy(c->d_exptab, t, sizeof t, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&c->d_scratch, 64));
   return W2B_OK;
 }
 
@@ -403,6 +424,7 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   cudaFree(c->d_u); cudaFree(c->d_v); cudaFree(c->d_keep); cudaFree(c->d_exptab);
   cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
   cudaFree(c->d_shards);
+  cudaFree(c->d_scratch);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -868,7 +890,7 @@ extern "C" int w2b_checkpoint_load(w2b_ctx *c, const char *path, int64_t *epochs
     }
   fclose(f);
   if (epochs_done) *epochs_done = h.epochs_done;
-  c->have_tables = c->have_tables || false;
+  c->have_tables = true;  // u and v now hold trained values
   return w2b_set_state(c, h.alpha, h.wca);
 }
 
@@ -955,15 +977,13 @@ extern "C" int w2b_sync(w2b_ctx *c) {
   CK(cudaMemcpyAsync(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   unsigned long long own = ((long long)w - c->wca_at_sync) / c->nranks;
-  unsigned long long *d_tmp = nullptr;
-  CK(cudaMalloc(&d_tmp, sizeof(unsigned long long)));
+  unsigned long long *d_tmp = c->d_scratch;
   CK(cudaMemcpyAsync(d_tmp, &own, sizeof own, cudaMemcpyHostToDevice, c->stream));
   e = g_nccl.AllReduce(d_tmp, d_tmp, 1, kNcclUint64, kNcclSum, c->comm, c->stream);
   if (e) { w2b_set_error("ncclAllReduce(wca): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
   unsigned long long total = 0;
   CK(cudaMemcpyAsync(&total, d_tmp, sizeof total, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_tmp));
   c->wca_at_sync += (long long)total;
   unsigned long long nw = (unsigned long long)c->wca_at_sync;
   CK(cudaMemcpy(c->d_wca, &nw, sizeof nw, cudaMemcpyHostToDevice));
