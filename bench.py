@@ -246,6 +246,10 @@ def main():
     S = S_local * world
     B = args.words_per_shard
     total_steps = args.steps + args.warmup
+    # keep the synthetic corpus of one rank under ~300 M tokens (1.2 GB of host ids): very long runs
+    # get proportionally shorter steps instead of a bigger corpus
+    while B > 8192 and (total_steps + 2) * (B + 1500) * 1.05 * S_local > 300e6:
+        B //= 2
     per_shard = int((total_steps + 2) * (B + 1500) * 1.05) + 4096
     n_local = per_shard * S_local
     cdf, pmf = zipf_cdf(V)
