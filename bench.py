@@ -151,10 +151,10 @@ def run_reference(args, rank, budget_s=100.0):
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
     cdf, _ = zipf_cdf(V)
-    ids = synth_ids(12_000_000, 4242, cdf)
+    ids = synth_ids(int(os.environ.get("W2B_REF_MAX_TOKENS", 12_000_000)), 4242, cdf)
     cands = [int(os.environ["W2B_REF_THREADS"])] if "W2B_REF_THREADS" in os.environ else \
         sorted({max(1, cores // k) for k in (1, 2, 4, 8)}, reverse=True)
-    cal_n = 400_000
+    cal_n = int(os.environ.get("W2B_REF_CAL_TOKENS", 400_000))  # (tests shrink it)
     cal = _write_text(ids[:cal_n], "w2b_cal_")
     best = (0.0, cands[-1])
     tried = []
@@ -171,7 +171,7 @@ def run_reference(args, rank, budget_s=100.0):
         os.unlink(cal)
     rate, threads = best
     passes = args.steps + args.warmup
-    n = int(min(len(ids), max(300_000, rate * min(15.0, budget_s / passes))))
+    n = int(min(len(ids), max(int(os.environ.get("W2B_REF_MIN_TOKENS", 300_000)), rate * min(15.0, budget_s / passes))))
     path = _write_text(ids[:n], "w2b_ref_")
     try:
         run, words_per_pass, kind = _ref_runner(po, path, threads, passes)
