@@ -234,6 +234,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
