@@ -614,9 +614,22 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
   sum_shards(c->h_shards, &before);
   TrainParams p = base_params(c);
   if (c->resident) {
-    p.word_budget = words_per_shard;
-    int rc = launch_train(c, p, &acc);
-    if (rc) return rc;
+    if (words_per_shard > 0 || c->cfg.mode == W2B_MODE_STRICT) {
+      p.word_budget = words_per_shard;
+      int rc = launch_train(c, p, &acc);
+      if (rc) return rc;
+    } else {
+      // "to the end of the shard": a sequence of bounded launches (the ring kernel keeps 32-bit
+      // row counters per launch; 4 M words per shard per launch stays far below their range)
+      for (;;) {
+        p.word_budget = 4 << 20;
+        int rc = launch_train(c, p, &acc);
+        if (rc) return rc;
+        w2b_step_stats now;
+        sum_shards(c->h_shards, &now);
+        if (now.shards_done == c->nlocal) break;
+      }
+    }
   } else {
     // streaming: slices of (budget + margin) tokens; run-to-end loops over slices
     const long long chunk = words_per_shard > 0 ? words_per_shard : 65536;
