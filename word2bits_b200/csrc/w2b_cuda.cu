@@ -281,6 +281,10 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.train = 1;
   p.plain_store = c->cfg.plain_store;
   p.serial = c->cfg.ring_serial;
+  {
+    const char *e = getenv("W2B_SLEEP_NS");  // tuning hook
+    p.sleep_ns = e ? (unsigned)atoi(e) : 32u;
+  }
   p.wca_scale = c->nranks;
   return p;
 }

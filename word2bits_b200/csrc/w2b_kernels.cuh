@@ -75,6 +75,7 @@ struct TrainParams {
   int train;                    // 0: draws only (trace)
   int plain_store;
   int serial;                   // ring kernel debug: no prefetch across positions
+  unsigned sleep_ns;            // ring kernel: back-off of the sampler/loader polling loops
   int wca_scale;                // multi-GPU: local words stand for wca_scale x as many globally
   w2b_trace_rec *trace;
   long long trace_cap;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
       const int b = mod_small(r1, (unsigned)W);
       // descriptor slot: free once every consumer is done with position q - kND
       const int slot = q % kND;
-      while (q - ctl->prog >= (p.serial ? 1 : kND)) __nanosleep(32);
+      while (q - ctl->prog >= (p.serial ? 1 : kND)) __nanosleep(p.sleep_ns);
       RingDesc *d = &desc[slot];
       const int center = len ? s_sen[sp] : -1;
       int cw = 0;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
       }
     }
     // tell the loader (and through it the consumers) to stop
-    while (q - ctl->prog >= kND) __nanosleep(32);
+    while (q - ctl->prog >= kND) __nanosleep(p.sleep_ns);
     if (lane == 0) {
       RingDesc *d = &desc[q % kND];
       d->exit_flag = 1;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
     int u_alloc = 0;
     int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
     for (int q = 0;; ++q) {
-      while (ctl->desc_ready <= q) __nanosleep(32);
+      while (ctl->desc_ready <= q) __nanosleep(p.sleep_ns);
       __threadfence_block();
       const int slot = q % kND;
       RingDesc *d = &desc[slot];
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
       }
       const int cw = d->cw, nt = d->nt;
       // ---- context rows -> u-ring
-      while (u_alloc + cw - ctl->urel > nu) __nanosleep(32);
+      while (u_alloc + cw - ctl->urel > nu) __nanosleep(p.sleep_ns);
       if (lane == 0) {
         d->us0 = u_alloc % nu;
         d->vs0 = v_alloc % nv;
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
         __syncwarp();
         if (lane < ng) {  // each lane waits for its own slot to have been released by its last user
           const int vi = v_alloc + lane, sl = vi % nv, uses = vi / nv;
-          while (s_rc[sl] < uses) __nanosleep(32);
+          while (s_rc[sl] < uses) __nanosleep(p.sleep_ns);
           bulk_load(vring + (unsigned)sl * rowb, p.v + (long long)d->tg[g0 + lane] * p.D, rowb, vbar);
         }
         __syncwarp();
