@@ -502,3 +502,45 @@ def test_gpu_analogy_evaluator_matches_reference(tmp_path, bits, threshold):
         total_w = [l for l in want.splitlines() if l.startswith("Total accuracy")][-1]
         total_g = [l for l in got.splitlines() if l.startswith("Total accuracy")][-1]
         assert abs(nums(total_w)[0] - nums(total_g)[0]) <= 2.0, (total_w, total_g)
+
+
+def test_full_size_shape_properties(tmp_path):
+    """BASELINE configs[1] shape (400k-word Zipf vocabulary, D=800, window 10, negative 24, 148 shards),
+    checked through size-independent properties: vocabulary/table/InitNet equal the oracle's on the
+    full arrays, the production sampler replays the oracle's draws on a 1e8-slot table over ~300k words,
+    every shard ends, the word accounting adds up, and quantize is idempotent on the exported matrix."""
+    import bench
+    cdf, _ = bench.zipf_cdf(400000)
+    ids = bench.synth_ids(3_000_000, 99, cdf)
+    path = bench._write_text(ids, str(tmp_path / "big_"))
+    try:
+        c = w2b.Corpus(path, 1)
+        o = po.Corpus(path, 1)
+        V, D, S = c.vocab_size, 800, 148
+        assert V > 250000 and c.words() == o.words() and np.array_equal(c.counts, o.counts)
+        assert np.array_equal(c.tokens, o.tokens)
+        t = w2b.Trainer(c, size=D, window=10, negative=24, bitlevel=1, threads=S, iter=1)
+        table = po.unigram_table(o.counts)
+        assert np.array_equal(t.download_table(), table)
+        u, v = t.download_raw()
+        ou, ov = po.init_net(V, D)
+        assert np.array_equal(bits(u), bits(ou)) and np.array_equal(bits(v), bits(ov))
+        del ou, ov
+        for sid in (0, 3, 147):                           # first, middle (mid-word seek), last shard
+            got = t.trace(sid, max_iterations=1500, cap=2000)
+            m = po.OracleModel(o, 4, 10, 24, 1, shards=S, table=table)
+            _, want = m.train_shard(sid, max_positions=1500, trace_cap=2000)
+            assert len(got) == len(want) == 1500
+            assert all(a[:4] == b[:4] for a, b in zip(got, want)), sid
+        loss, st = t.train_epoch()
+        assert st["shards_done"] == S and np.isfinite(loss)
+        # every shard stops after the first sentence that takes it past train_words/S (:414)
+        assert st["words"] > c.train_words - S and st["words"] < c.train_words + S * 1300
+        assert st["positions"] > 0.7 * st["words"] and st["target_rows"] > 24.9 * st["positions"]
+        out = t.export()
+        assert set(np.unique(bits(out)).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}
+        assert np.array_equal(bits(t.quantize(out, 1)), bits(out))       # idempotent
+        u2, v2 = t.download_raw()
+        assert np.isfinite(u2).all() and np.isfinite(v2).all() and not np.array_equal(bits(v2), bits(v))
+    finally:
+        os.unlink(path)
