@@ -228,13 +228,17 @@ def test_fast_statistical(b, D, neg, group, kernel, serial, large):
     t = w2b.Trainer(c, size=D, window=8, negative=neg, bitlevel=b, threads=shards, iter=2, group=group,
                     kernel=kernel, ring_serial=serial)
     m = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=2)
+    words_total = 0
     for ep in range(2):
         lo = m.train_epoch_threads()
         lg, st = t.train_epoch()
+        words_total += st["words"]
         assert st["shards_done"] == shards
         assert abs(lg - lo) <= (0.02 if D >= 800 else 0.01) * abs(lo), (ep, lg, lo)
     a, wca = t.get_state()
-    assert wca == m.word_count_actual
+    # the device counter is an atomic: exact.  The oracle's 16 threads race on word_count_actual
+    # like the reference's do (:380,:415) and may lose increments, never gain any.
+    assert wca == words_total and m.word_count_actual <= wca
     out = t.export()
     if b == 1:
         assert set(np.unique(bits(out)).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}
