@@ -15,10 +15,11 @@
 //   * consumer warps, two phases per position:
 //       context phase  (:431-449) thread t owns float4 column t of the cw landed u rows:
 //                      quantize, sum in row order, divide by cw, publish context_avg.
-//       target phase   (:450-492) one WARP per landed v row (rows dealt round-robin):
-//                      lane l holds float4 columns l, l+32, ... of context_avg in
-//                      registers, reads the row, quantizes, dots (4 independent FMA chains
-//                      + one 5-step shuffle all-reduce per row), takes g from the expTable,
+//       target phase   (:450-492) one WARP per landed v row (rows dealt round-robin, R = 2 rows
+//                      in flight per warp): lane l covers float4 columns l, l+32, ... ; it
+//                      reads the rows, quantizes, dots against context_avg (4 independent FMA
+//                      chains per row + interleaved 5-step shuffle all-reduces), takes g from
+//                      the expTable,
 //                      accumulates g*quantize(v) into private error registers (:487),
 //                      overwrites the row in place with g*context_avg (:490) and hands the
 //                      slot back to the TMA: cp.reduce.async.bulk.global.add.f32, one
