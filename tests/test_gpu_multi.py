@@ -23,3 +23,39 @@ def test_replica_average_over_nccl(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(root, "tests", "mgpu_worker.py"), path], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_cli_on_two_gpus(tmp_path):
+    """`word2bits -gpus 2`: one host thread per GPU, NCCL replica averaging inside libw2b; the result
+    must be as good as the single-GPU run (planted-topic purity, final loss)."""
+    w2b = pytest.importorskip("word2bits_b200")
+    if w2b.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import re
+    import numpy as np
+    from tests.util import planted_topic_corpus, topic_purity
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "word2bits_b200", "word2bits")
+    path = planted_topic_corpus(str(tmp_path / "topics.txt"), vocab=5000, topics=25, sentences=60000, length=20)
+    res = {}
+    for g in (1, 2):
+        out = str(tmp_path / ("v%d.bin" % g))
+        r = subprocess.run([cli, "-train", path, "-output", out, "-size", "100", "-window", "5", "-negative", "12",
+                            "-iter", "2", "-min-count", "5", "-binary", "1", "-threads", "32", "-gpus", str(g),
+                            "-sync-every", "2", "-debug", "0"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        losses = [float(x) for x in re.findall(r"Epoch Loss: (-?[0-9.]+)", r.stdout)]
+        assert len(losses) == 2
+        raw = open(out, "rb").read()
+        head, body = raw.split(b"\n", 1)
+        V, D = [int(x) for x in head.split()]
+        words, vec, pos = [], np.empty((V, D), np.float32), 0
+        for i in range(V):
+            sp = body.index(b" ", pos)
+            words.append(body[pos:sp].decode())
+            vec[i] = np.frombuffer(body[sp + 1: sp + 1 + 4 * D], np.float32)
+            pos = sp + 1 + 4 * D + 1
+        res[g] = (losses[-1], topic_purity(words, vec, 25))
+    print("cli 1 vs 2 GPUs (final loss, purity):", res)
+    assert abs(res[2][0] - res[1][0]) <= 0.02 * abs(res[1][0])
+    assert abs(res[2][1] - res[1][1]) <= 0.05 and res[2][1] > 0.5

@@ -4,7 +4,9 @@
 // / TrainModel() (src/word2bits.cpp:518-621).  Differences, all additive:
 //   -threads N   number of corpus shards (one CUDA CTA each).  When the flag is absent the
 //                shard count that fills the GPU is used instead of the reference's 12.
-//   -gpu N       CUDA device ordinal (default 0).
+//   -gpu N       first CUDA device ordinal (default 0).
+//   -gpus G      train on G GPUs (devices gpu..gpu+G-1): shards split in G blocks, full replicas,
+//                NCCL all-reduce-average every -sync-every steps (default 4) and at every epoch end.
 //   -strict 1    parity mode: shards one after another, sequential IEEE arithmetic.
 //   -binary 2    packed output: bitlevel bits per value (bitlevel 1 and 2), see w2b_write_packed.
 //   -checkpoint F  write a resumable checkpoint (fp32 u, v, alpha, word counter) to F after every epoch.
@@ -15,10 +17,36 @@
 #include <string.h>
 #include <time.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "w2b.h"
+
+// reusable barrier for the per-GPU host threads
+class Barrier {
+ public:
+  explicit Barrier(int n) : n_(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const long gen = gen_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++gen_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lk, [&] { return gen_ != gen; });
+    }
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_, count_ = 0;
+  long gen_ = 0;
+};
 
 static int arg_pos(const char *str, int argc, char **argv) {  // ArgPos, :579-589
   for (int a = 1; a < argc; a++)
@@ -75,6 +103,11 @@ int main(int argc, char **argv) {
   if ((i = arg_pos("-checkpoint", argc, argv)) > 0) ckpt_file = argv[i + 1];
   if ((i = arg_pos("-resume", argc, argv)) > 0) resume_file = argv[i + 1];
   g_bitlevel = bitlevel;
+  int ngpus = 1, sync_every = 4;
+  if ((i = arg_pos("-gpus", argc, argv)) > 0) ngpus = atoi(argv[i + 1]);
+  if ((i = arg_pos("-sync-every", argc, argv)) > 0) sync_every = atoi(argv[i + 1]);
+  if (ngpus < 1) ngpus = 1;
+  if (sync_every < 1) sync_every = 1;
 
   printf("Starting training using file %s\n", train_file.c_str());  // :523
   w2b_corpus *corpus = nullptr;
@@ -108,69 +141,119 @@ int main(int argc, char **argv) {
     int s = 0;
     if (w2b_suggest_shards(&cfg, &s)) die("w2b_suggest_shards");
     // never cut the corpus into shards shorter than a few sentences
-    while (s > 1 && train_words / s < 4000) s /= 2;
+    s *= ngpus;
+    while (s > ngpus && train_words / s < 4000) s /= 2;
     cfg.num_shards = s;
   }
-  w2b_ctx *ctx = nullptr;
-  if (w2b_create(&cfg, &ctx)) {
-    if (strstr(w2b_last_error(), "cudaMalloc")) printf("Memory allocation failed\n");  // :347
-    die("w2b_create");
+  if (strict && ngpus > 1) {
+    printf("-strict 1 runs on one GPU\n");
+    exit(1);
   }
-  if (w2b_set_vocab_counts(ctx, w2b_corpus_counts(corpus), V, train_words)) die("w2b_set_vocab_counts");
+  if (cfg.num_shards < ngpus) {
+    printf("-threads must be at least -gpus\n");
+    exit(1);
+  }
+  // ---- one host thread per GPU (rank); each owns a contiguous block of shards on a full replica of
+  // u/v; replicas are all-reduce-averaged every `sync_every` steps and at every epoch end (w2b_sync)
+  const int G = ngpus;
   std::vector<int64_t> start(cfg.num_shards);
   std::vector<int32_t> first(cfg.num_shards);
   if (w2b_corpus_shards(corpus, cfg.num_shards, start.data(), first.data())) die("w2b_corpus_shards");
-  if (w2b_set_corpus(ctx, w2b_corpus_tokens(corpus), w2b_corpus_num_tokens(corpus), start.data(), first.data(), 1))
-    die("w2b_set_corpus");
-  if (w2b_init_tables(ctx)) die("w2b_init_tables");
-
-  std::vector<float> buf((size_t)V * layer1_size);
+  unsigned char uid[128] = {0};
+  if (G > 1 && w2b_nccl_unique_id(uid)) die("w2b_nccl_unique_id");
+  Barrier bar(G);
+  std::mutex mu;
+  double epoch_loss = 0;
+  long long words_done = 0, step_words = 0;
+  int ranks_busy = 0;
   struct timespec t0;
   clock_gettime(CLOCK_MONOTONIC, &t0);
-  long long words_done = 0;
-  long long first_epoch = 0;
-  if (!resume_file.empty()) {
-    int64_t done = 0;
-    if (w2b_checkpoint_load(ctx, resume_file.c_str(), &done)) die("w2b_checkpoint_load");
-    first_epoch = done;
-  }
-  for (int iteration = (int)first_epoch; iteration < iter; iteration++) {
-    printf("Starting epoch: %d\n", iteration);  // :533
-    if (w2b_epoch_begin(ctx)) die("w2b_epoch_begin");
-    double epoch_loss = 0;
-    for (;;) {
-      w2b_step_stats st;
-      // 50k words per shard per step: progress lines 5x less often than the reference (:379), steps long
-      // enough that the whole-sentence overshoot at a step boundary (<= ~1.2k words) stays ~1 %
-      if (w2b_train_step(ctx, debug_mode > 1 ? 50000 : 0, &st)) die("w2b_train_step");
-      epoch_loss += st.loss;
-      words_done += st.words;
-      if (debug_mode > 1) {  // :384-387 (Words/sec here is wall-clock and whole-job, not per CPU thread)
-        struct timespec now;
-        clock_gettime(CLOCK_MONOTONIC, &now);
-        double secs = (now.tv_sec - t0.tv_sec) + (now.tv_nsec - t0.tv_nsec) * 1e-9;
-        printf("%cAlpha: %f  Progress: %.2f%%  Cost: %f Words/sec: %.2fk  ", 13, st.alpha,
-               st.word_count_actual / (float)(iter * train_words + 1) * 100, st.loss,
-               words_done / (secs + 1e-9) / 1000);
-        fflush(stdout);
+
+  auto worker = [&](int rank) {
+    w2b_config c = cfg;
+    c.device = device + rank;
+    c.shard_begin = (int)((long long)cfg.num_shards * rank / G);
+    c.shard_end = (int)((long long)cfg.num_shards * (rank + 1) / G);
+    const int nlocal = c.shard_end - c.shard_begin;
+    w2b_ctx *ctx = nullptr;
+    if (w2b_create(&c, &ctx)) {
+      if (strstr(w2b_last_error(), "cudaMalloc")) printf("Memory allocation failed\n");  // :347
+      die("w2b_create");
+    }
+    if (w2b_set_vocab_counts(ctx, w2b_corpus_counts(corpus), V, train_words)) die("w2b_set_vocab_counts");
+    if (w2b_set_corpus(ctx, w2b_corpus_tokens(corpus), w2b_corpus_num_tokens(corpus), start.data(), first.data(), 1))
+      die("w2b_set_corpus");
+    if (w2b_init_tables(ctx)) die("w2b_init_tables");
+    if (G > 1 && w2b_nccl_init(ctx, uid, rank, G)) die("w2b_nccl_init");
+    long long first_epoch = 0;
+    if (!resume_file.empty()) {
+      int64_t done = 0;
+      if (w2b_checkpoint_load(ctx, resume_file.c_str(), &done)) die("w2b_checkpoint_load");
+      first_epoch = done;
+    }
+    std::vector<float> buf;
+    if (rank == 0) buf.resize((size_t)V * layer1_size);
+    for (int iteration = (int)first_epoch; iteration < iter; iteration++) {
+      if (rank == 0) {
+        printf("Starting epoch: %d\n", iteration);  // :533
+        epoch_loss = 0;
       }
-      if (st.shards_done >= cfg.num_shards) break;
+      if (w2b_epoch_begin(ctx)) die("w2b_epoch_begin");
+      bar.wait();
+      for (long long step = 1;; ++step) {
+        w2b_step_stats st;
+        // 50k words per shard per step: progress lines 5x less often than the reference (:379), steps
+        // long enough that the whole-sentence overshoot at a step boundary (<= ~1.2k words) stays ~1 %
+        if (w2b_train_step(ctx, (debug_mode > 1 || G > 1) ? 50000 : 0, &st)) die("w2b_train_step");
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          epoch_loss += st.loss;
+          words_done += st.words;
+          step_words += st.words;
+          if (st.shards_done < nlocal) ++ranks_busy;
+        }
+        bar.wait();  // every rank sees the same ranks_busy: collectives stay aligned
+        const bool more = ranks_busy > 0;
+        if (G > 1 && (step % sync_every == 0 || !more) && w2b_sync(ctx)) die("w2b_sync");
+        if (rank == 0 && debug_mode > 1) {  // :384-387 (Words/sec is wall-clock and whole-job, not per CPU thread)
+          struct timespec now;
+          clock_gettime(CLOCK_MONOTONIC, &now);
+          double secs = (now.tv_sec - t0.tv_sec) + (now.tv_nsec - t0.tv_nsec) * 1e-9;
+          printf("%cAlpha: %f  Progress: %.2f%%  Cost: %f Words/sec: %.2fk  ", 13, st.alpha,
+                 words_done / (float)(iter * train_words + 1) * 100, st.loss, words_done / (secs + 1e-9) / 1000);
+          fflush(stdout);
+        }
+        bar.wait();
+        if (rank == 0) ranks_busy = 0;
+        bar.wait();
+        if (!more) break;
+      }
+      if (rank == 0) {
+        printf("Epoch Loss: %lf\n", epoch_loss);  // :539
+        if (!ckpt_file.empty() && w2b_checkpoint_save(ctx, ckpt_file.c_str(), iteration + 1)) die("w2b_checkpoint_save");
+        if (classes == 0 && save_every_epoch) {  // :540-557
+          char name[4200];
+          snprintf(name, sizeof name, "%s_epoch%d", output_file.c_str(), iteration);
+          if (write_vectors(name, ctx, corpus, V, layer1_size, binary, buf)) die("write");
+        }
+      }
+      bar.wait();
     }
-    printf("Epoch Loss: %lf\n", epoch_loss);  // :539
-    if (!ckpt_file.empty() && w2b_checkpoint_save(ctx, ckpt_file.c_str(), iteration + 1)) die("w2b_checkpoint_save");
-    if (classes == 0 && save_every_epoch) {     // :540-557
-      char name[4200];
-      snprintf(name, sizeof name, "%s_epoch%d", output_file.c_str(), iteration);
-      if (write_vectors(name, ctx, corpus, V, layer1_size, binary, buf)) die("write");
+    if (rank == 0) {
+      if (classes == 0) {  // :560-576
+        if (write_vectors(output_file, ctx, corpus, V, layer1_size, binary, buf)) die("write");
+      } else {
+        FILE *fo = fopen(output_file.c_str(), "wb");  // the reference creates an empty file (:561-562)
+        if (fo) fclose(fo);
+      }
     }
-  }
-  if (classes == 0) {  // :560-576
-    if (write_vectors(output_file, ctx, corpus, V, layer1_size, binary, buf)) die("write");
-  } else {
-    FILE *fo = fopen(output_file.c_str(), "wb");  // the reference creates an empty file (:561-562)
-    if (fo) fclose(fo);
-  }
-  w2b_destroy(ctx);
+    bar.wait();
+    w2b_destroy(ctx);
+  };
+  std::vector<std::thread> threads;
+  for (int r = 1; r < G; ++r) threads.emplace_back(worker, r);
+  worker(0);
+  for (auto &t : threads) t.join();
   w2b_corpus_free(corpus);
   return 0;
 }
