@@ -65,6 +65,17 @@ int w2b_write_packed(const char *path, const w2b_corpus *c, const float *vectors
 int w2b_read_packed_header(const char *path, int64_t *V, int64_t *D, int *bitlevel);
 int w2b_read_packed(const char *path, float *vectors /* V*D */, char *words /* V*max_word */, int max_word);
 
+/* Host-side arithmetic of the path, callable (and tested) without a GPU.  The device path uses exactly
+ * these functions for what it uploads: unigram boundaries (InitUnigramTable :112-128 in boundary form:
+ * start[i] = first of the 1e8 table slots owned by word i, start[V] = 1e8), expTable (:614-618, same libm
+ * expf), the sub-sampling thresholds `ran` (:403-404, float32), and the k-step / 2^j-step jump constants
+ * of the LCG r*25214903917+11 (:352,:405,:428,:455) that let 32 lanes take 32 draws at once
+ * (ja/jc: 65 entries, r_k = r*ja[k]+jc[k]; pa/pc: 64 entries for 2^j steps). */
+int w2b_host_unigram_bounds(const int64_t *cn, int64_t V, int32_t *start /* V+1 */);
+int w2b_host_exptable(float *out /* 1000 */);
+int w2b_host_keep_thresholds(const int64_t *cn, int64_t V, int64_t train_words, float sample, float *out /* V */);
+int w2b_host_lcg_tables(uint64_t *ja /*65*/, uint64_t *jc /*65*/, uint64_t *pa /*64*/, uint64_t *pc /*64*/);
+
 /* ------------------------------------------------------------------------ device path */
 typedef struct w2b_ctx w2b_ctx;
 
@@ -114,6 +125,22 @@ typedef struct {
 
 const char *w2b_last_error(void);
 int w2b_device_count(int *n);
+
+/* Geometry the production (TMA ring) kernel would run with for a configuration: pure host arithmetic
+ * (no CUDA call).  ring = 0 means the configuration runs the register kernel instead (D % 4 != 0,
+ * D > 1024, reg != 0, strict mode, kernel = 1, or no ring fits 227 KB of shared memory). */
+typedef struct {
+  int32_t ring;            /* 1 = ring kernel applies */
+  int32_t group;           /* target rows per landing barrier (G) */
+  int32_t consumer_warps;  /* warps doing the arithmetic; + 1 loader warp + 1 sampler warp */
+  int32_t rows_in_flight;  /* target rows a consumer warp holds at once (R) */
+  int32_t u_rows, v_rows;  /* ring depths in rows of 4*D bytes */
+  int32_t threads;         /* CTA size */
+  int32_t desc_depth;      /* positions in flight (descriptor ring) */
+  int32_t max_groups;      /* landing barriers per descriptor slot */
+  int64_t smem_bytes;      /* dynamic shared memory per CTA */
+} w2b_ring_plan;
+int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out);
 
 /* Number of shards that keeps every SM busy for this configuration (SMs x resident CTAs);
  * the CLI's default for -threads (the reference's default of 12 is a CPU core count). */

@@ -1,0 +1,90 @@
+"""CPU check of the production kernel's flow control: the geometry the host planner picks
+(w2b_ring_plan_query — pure host arithmetic inside libw2b) is run through an executable model of the
+kernel's sampler / loader / consumer protocol (tests/ring_model.py) under randomised schedules.
+A geometry that can hang the GPU or recycle a shared-memory row too early fails here, without a GPU."""
+import random
+
+import pytest
+
+import word2bits_b200 as w2b
+from tests.ring_model import Deadlock, RingModel, random_positions
+
+SMEM_LIMIT = 227 * 1024
+
+
+def _check(plan, window, negative, seeds=(0, 1), n=40):
+    for style in ("typical", "extreme", "tiny", "any"):
+        for seed in seeds:
+            rng = random.Random(1000 * seed + len(style))
+            pos = random_positions(rng, n, window, negative, style)
+            RingModel(plan, window, negative, pos, seed=seed).run()
+
+
+def test_planner_invariants_over_the_supported_envelope():
+    """Every (D, window, negative) the ABI accepts: either the planner declines (register kernel) or the
+    geometry fits shared memory, holds a whole window of context rows, has enough landing barriers, and
+    respects the lower bound on the v-ring that rules out a wait cycle inside one position."""
+    n_ring = 0
+    for D in (4, 8, 52, 100, 128, 200, 256, 300, 400, 512, 640, 800, 1000, 1024, 1028, 2048):
+        for window in (1, 2, 5, 8, 10, 16, 32, 64):
+            for negative in (0, 1, 5, 12, 24, 25, 31, 32, 40, 63):
+                p = w2b.ring_plan(size=D, window=window, negative=negative)
+                if not p["ring"]:
+                    continue
+                n_ring += 1
+                nt, G, R, ncw = negative + 1, p["group"], p["rows_in_flight"], p["consumer_warps"]
+                assert p["smem_bytes"] <= SMEM_LIMIT, (D, window, negative, p)
+                assert p["u_rows"] >= 2 * window, (D, window, negative, p)
+                assert (nt + G - 1) // G <= p["max_groups"] and 1 <= G <= 32, (D, window, negative, p)
+                assert p["threads"] == 32 * (ncw + 2) <= 1024
+                assert p["v_rows"] >= 2 * G or p["v_rows"] >= nt, (D, window, negative, p)
+                assert p["v_rows"] >= nt or p["v_rows"] >= (2 * R - 1) * ncw + G, (D, window, negative, p)
+    assert n_ring > 500
+    # outside the envelope the planner declines instead of guessing
+    assert not w2b.ring_plan(size=402, window=5, negative=5)["ring"]          # D % 4 != 0
+    assert not w2b.ring_plan(size=2048, window=5, negative=5)["ring"]         # D > 1024
+    assert not w2b.ring_plan(size=200, window=5, negative=5, reg=0.1)["ring"]  # regularisation
+    assert not w2b.ring_plan(size=200, window=5, negative=5, mode=w2b.MODE_STRICT)["ring"]
+    assert not w2b.ring_plan(size=200, window=5, negative=5, kernel=1)["ring"]
+
+
+# BASELINE.json configurations + the shapes tests/test_gpu_parity.py runs on the GPU
+NAMED = [(800, 10, 24), (400, 10, 12), (400, 10, 24), (200, 8, 24), (800, 10, 63), (1024, 3, 7), (256, 20, 40),
+         (100, 5, 5), (8, 2, 1), (4, 1, 0), (64, 5, 6), (640, 64, 63), (1000, 2, 31)]
+
+
+@pytest.mark.parametrize("D,window,negative", NAMED)
+def test_named_geometries_are_live_and_safe(D, window, negative):
+    p = w2b.ring_plan(size=D, window=window, negative=negative)
+    if not p["ring"]:
+        pytest.skip("register kernel for this shape")
+    _check(p, window, negative, seeds=(0, 1, 2), n=60)
+
+
+def test_sweep_is_live_and_safe():
+    """Coarser positions, wider grid, plus the caller-controlled knobs (group, ring_rows)."""
+    n = 0
+    for D in (8, 200, 400, 800, 1024):
+        for window in (1, 5, 10, 32):
+            for negative in (0, 5, 24, 40, 63):
+                for group, ring_rows in ((0, 0), (1, 0), (5, 0), (16, 0), (0, 1), (0, 27), (7, 30)):
+                    p = w2b.ring_plan(size=D, window=window, negative=negative, group=group, ring_rows=ring_rows)
+                    if not p["ring"]:
+                        continue
+                    n += 1
+                    _check(p, window, negative, seeds=(n,), n=12)
+    assert n > 300
+
+
+def test_model_catches_a_ring_that_is_too_small():
+    """The model must be able to fail: a v-ring below the planner's bound (with positions longer than the
+    ring) dead-locks — this is the hang the bound exists to prevent."""
+    p = w2b.ring_plan(size=800, window=10, negative=63)
+    assert p["ring"] and p["v_rows"] < 64
+    bad = dict(p, v_rows=p["group"] + 2)
+    pos = [(20, 64)] * 6
+    with pytest.raises((Deadlock, AssertionError)):
+        for seed in range(20):
+            RingModel(bad, 10, 63, pos, seed=seed).run()
+    # and a descriptor ring deeper than the barrier phases allow is caught as a safety violation
+    RingModel(p, 10, 63, pos, seed=0).run()

@@ -11,13 +11,56 @@ import numpy as np
 from . import _lib
 from ._lib import MODE_FAST, MODE_STRICT, TABLE_SIZE, W2BError, check, lib, ptr
 
-__all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id", "compute_accuracy"]
+__all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id",
+           "compute_accuracy", "host_unigram_bounds", "host_exptable", "host_keep_thresholds", "host_lcg_tables", "ring_plan"]
 
 
 def device_count():
     n = C.c_int(0)
     rc = lib.w2b_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+# -- host-side arithmetic of the path (no GPU needed): exactly what the device path uploads
+def host_unigram_bounds(counts):
+    """InitUnigramTable (:112-128) in boundary form: start[i] = first table slot of word i, start[V] = 1e8."""
+    cn = np.ascontiguousarray(counts, np.int64)
+    start = np.empty(len(cn) + 1, np.int32)
+    check(lib.w2b_host_unigram_bounds(ptr(cn), len(cn), ptr(start)))
+    return start
+
+
+def host_exptable():
+    t = np.empty(1000, np.float32)
+    check(lib.w2b_host_exptable(ptr(t)))
+    return t
+
+
+def host_keep_thresholds(counts, train_words, sample):
+    """Sub-sampling thresholds `ran` (:403-404), float32."""
+    cn = np.ascontiguousarray(counts, np.int64)
+    out = np.empty(len(cn), np.float32)
+    check(lib.w2b_host_keep_thresholds(ptr(cn), len(cn), int(train_words), float(sample), ptr(out)))
+    return out
+
+
+def host_lcg_tables():
+    """(ja, jc, pa, pc): k-step (k = 0..64) and 2^j-step (j = 0..63) jump constants of the LCG."""
+    ja, jc = np.empty(65, np.uint64), np.empty(65, np.uint64)
+    pa, pc = np.empty(64, np.uint64), np.empty(64, np.uint64)
+    check(lib.w2b_host_lcg_tables(ptr(ja), ptr(jc), ptr(pa), ptr(pc)))
+    return ja, jc, pa, pc
+
+
+def ring_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, mode=MODE_FAST, group=0, kernel=0,
+              ring_rows=0):
+    """Geometry of the production (TMA ring) kernel for a configuration (pure host arithmetic)."""
+    cfg = _lib.Config(vocab_size=vocab_size, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
+                      alpha=0.05, sample=1e-3, reg=reg, iter=1, num_shards=1, shard_begin=0, shard_end=0, device=0,
+                      mode=mode, group=group, plain_store=0, kernel=kernel, ring_rows=ring_rows, ring_serial=0)
+    out = _lib.RingPlan()
+    check(lib.w2b_ring_plan_query(C.byref(cfg), C.byref(out)))
+    return out.as_dict()
 
 
 class Corpus:

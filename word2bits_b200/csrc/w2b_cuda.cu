@@ -41,6 +41,22 @@ extern "C" const char *w2b_last_error(void) { return g_err.c_str(); }
     }                                                                                     \
   } while (0)
 
+#define NEED(ptr)                                                   \
+  do {                                                              \
+    if (!(ptr)) {                                                   \
+      w2b_set_error("%s: null %s", __func__, #ptr);                 \
+      return W2B_EINVAL;                                            \
+    }                                                               \
+  } while (0)
+
+// Temporary device allocation that is released on every return path.
+struct DevTmp {
+  void *p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
 // --------------------------------------------------------------------------- NCCL (dlopen)
 // Loaded lazily so that single-GPU use never touches NCCL and the library has no link-time
 // dependency on it (inside a torch process the already-loaded libnccl.so.2 is reused).
@@ -291,6 +307,7 @@ static TrainParams base_params(const w2b_ctx *c) {
 
 // ---------------------------------------------------------------------------- lifecycle
 extern "C" int w2b_device_count(int *n) {
+  NEED(n);
   int k = 0;
   cudaError_t e = cudaGetDeviceCount(&k);
   if (e != cudaSuccess) {
@@ -319,6 +336,8 @@ static int validate(const w2b_config *c) {
 }
 
 extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
+  NEED(cfg);
+  NEED(out);
   int rc = validate(cfg);
   if (rc) return rc;
   w2b_ctx tmp;
@@ -343,9 +362,45 @@ extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
   return W2B_OK;
 }
 
+// ---- host-only views of the path's host logic (no CUDA call: usable, and tested, without a GPU)
+extern "C" int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out) {
+  if (!cfg || !out) { w2b_set_error("null argument"); return W2B_EINVAL; }
+  int rc = validate(cfg);
+  if (rc) return rc;
+  w2b_ctx tmp;
+  tmp.cfg = *cfg;
+  tmp.vec = (cfg->layer1_size % 4 == 0) ? 4 : 1;
+  tmp.ncol = (int)((cfg->layer1_size + tmp.vec - 1) / tmp.vec);
+  plan_ring(&tmp);
+  memset(out, 0, sizeof *out);
+  out->ring = tmp.ring ? 1 : 0;
+  if (!tmp.ring) return W2B_OK;
+  out->group = tmp.ring_g;
+  out->u_rows = tmp.ring_nu;
+  out->v_rows = tmp.ring_nv;
+  out->threads = tmp.ring_threads;
+  out->consumer_warps = tmp.ring_threads / 32 - 2;
+  out->rows_in_flight = ring_rows_in_flight(out->consumer_warps);
+  out->desc_depth = kND;
+  out->max_groups = kMaxGrp;
+  out->smem_bytes = (int64_t)tmp.ring_smem;
+  return W2B_OK;
+}
+
+extern "C" int w2b_host_lcg_tables(uint64_t *ja, uint64_t *jc, uint64_t *pa, uint64_t *pc) {
+  if (!ja || !jc || !pa || !pc) { w2b_set_error("null argument"); return W2B_EINVAL; }
+  unsigned long long JA[65], JC[65], PA[64], PC[64];
+  lcg_tables(JA, JC, PA, PC);
+  for (int i = 0; i < 65; ++i) { ja[i] = JA[i]; jc[i] = JC[i]; }
+  for (int i = 0; i < 64; ++i) { pa[i] = PA[i]; pc[i] = PC[i]; }
+  return W2B_OK;
+}
+
 static int create_impl(const w2b_config *cfg, w2b_ctx **out);
 extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
+  NEED(out);
   *out = nullptr;
+  NEED(cfg);
   w2b_ctx *c = nullptr;
   const int rc = create_impl(cfg, &c);
   if (rc) {
@@ -439,29 +494,31 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
 
 // ------------------------------------------------------------------------------- tables
 extern "C" int w2b_set_vocab_counts(w2b_ctx *c, const int64_t *cn, int64_t V, int64_t train_words) {
+  NEED(c);
+  NEED(cn);
   if (V != c->cfg.vocab_size) { w2b_set_error("V mismatch"); return W2B_EINVAL; }
+  if (train_words < 1) { w2b_set_error("train_words must be >= 1"); return W2B_EINVAL; }
   CK(cudaSetDevice(c->cfg.device));
   c->train_words = train_words;
   // sub-sampling threshold `ran` (:403-404), float32 throughout
   std::vector<float> keep(V);
-  const float S = c->cfg.sample * (float)train_words;
-  for (int64_t w = 0; w < V; ++w) keep[w] = (sqrtf((float)cn[w] / S) + 1.f) * S / (float)cn[w];
+  w2b_keep_thresholds(cn, V, train_words, c->cfg.sample, keep.data());
   CK(cudaMemcpy(c->d_keep, keep.data(), V * sizeof(float), cudaMemcpyHostToDevice));
   // unigram boundaries (:112-128) with the host libm pow(); the device expands them
   std::vector<int> start(V + 1);
   w2b_unigram_bounds(cn, V, start.data());
-  int *d_start = nullptr;
-  CK(cudaMalloc(&d_start, (V + 1) * sizeof(int)));
-  CK(cudaMemcpy(d_start, start.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  fill_table_kernel<<<(W2B_TABLE_SIZE + 255) / 256, 256, 0, c->stream>>>(c->d_table, d_start, (int)V);
+  DevTmp d_start;
+  CK(d_start.alloc((V + 1) * sizeof(int)));
+  CK(cudaMemcpy(d_start.p, start.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  fill_table_kernel<<<(W2B_TABLE_SIZE + 255) / 256, 256, 0, c->stream>>>(c->d_table, d_start.as<int>(), (int)V);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_start));
   c->have_counts = true;
   return W2B_OK;
 }
 
 extern "C" int w2b_init_tables(w2b_ctx *c) {
+  NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
   const long long threads = (2 * n + 3) / 4;
@@ -477,6 +534,10 @@ extern "C" int w2b_init_tables(w2b_ctx *c) {
 
 extern "C" int w2b_set_corpus(w2b_ctx *c, const int32_t *ids, int64_t n, const int64_t *shard_start,
                               const int32_t *shard_first, int resident) {
+  NEED(c);
+  NEED(shard_start);
+  NEED(shard_first);
+  if (n < 0 || (n > 0 && !ids)) { w2b_set_error("w2b_set_corpus: bad token stream"); return W2B_EINVAL; }
   CK(cudaSetDevice(c->cfg.device));
   c->n_tokens = n;
   c->resident = resident != 0;
@@ -495,6 +556,7 @@ extern "C" int w2b_set_corpus(w2b_ctx *c, const int32_t *ids, int64_t n, const i
 }
 
 extern "C" int w2b_epoch_begin(w2b_ctx *c) {
+  NEED(c);
   if (!c->have_corpus) { w2b_set_error("set_corpus first"); return W2B_ESTATE; }
   CK(cudaSetDevice(c->cfg.device));
   for (int i = 0; i < c->nlocal; ++i) {
@@ -608,6 +670,7 @@ static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
 }
 
 extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stats *stats) {
+  NEED(c);
   if (!c->have_corpus || !c->have_tables || !c->have_counts) {
     w2b_set_error("train_step before set_vocab_counts/set_corpus/init_tables");
     return W2B_ESTATE;
@@ -617,18 +680,22 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
   memset(&acc, 0, sizeof acc);
   sum_shards(c->h_shards, &before);
   TrainParams p = base_params(c);
+  // The ring kernel keeps 32-bit row counters per launch and the streaming path stages one slice per
+  // shard in pinned memory, so a step is cut into bounded launches: 4 M words per shard per launch
+  // (resident) / 1 M words per slice (streaming).  Steps up to those sizes are exactly one launch.
+  const long long kLaunchWords = 4 << 20, kSliceWords = 1 << 20;
   if (c->resident) {
-    if (words_per_shard > 0 || c->cfg.mode == W2B_MODE_STRICT) {
-      p.word_budget = words_per_shard;
+    if (c->cfg.mode == W2B_MODE_STRICT) {
+      p.word_budget = words_per_shard;  // <= 0: every shard to its end, one after another
       int rc = launch_train(c, p, &acc);
       if (rc) return rc;
     } else {
-      // "to the end of the shard": a sequence of bounded launches (the ring kernel keeps 32-bit
-      // row counters per launch; 4 M words per shard per launch stays far below their range)
+      long long left = words_per_shard;  // <= 0: to the end of every shard
       for (;;) {
-        p.word_budget = 4 << 20;
+        p.word_budget = words_per_shard > 0 ? std::min(left, kLaunchWords) : kLaunchWords;
         int rc = launch_train(c, p, &acc);
         if (rc) return rc;
+        if (words_per_shard > 0 && (left -= p.word_budget) <= 0) break;
         w2b_step_stats now;
         sum_shards(c->h_shards, &now);
         if (now.shards_done == c->nlocal) break;
@@ -636,8 +703,9 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
     }
   } else {
     // streaming: slices of (budget + margin) tokens; run-to-end loops over slices
-    const long long chunk = words_per_shard > 0 ? words_per_shard : 65536;
+    long long left = words_per_shard;
     for (;;) {
+      const long long chunk = words_per_shard > 0 ? std::min(left, kSliceWords) : 65536;
       int rc = stage_slices(c, chunk, &acc);
       if (rc) return rc;
       p.tokens = c->d_tokens;
@@ -653,7 +721,7 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
         if (!c->h_shards[i].done && !c->h_shards[i].limit_is_eof && c->h_shards[i].word_count == wc_before[i])
           stuck = true;
       if (stuck) c->stage_margin *= 2;
-      if (words_per_shard > 0 && !stuck) break;
+      else if (words_per_shard > 0 && (left -= chunk) <= 0) break;
       if (a2.shards_done == c->nlocal) break;
     }
   }
@@ -678,6 +746,7 @@ extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stat
 }
 
 extern "C" int w2b_train_epoch(w2b_ctx *c, double *loss, w2b_step_stats *stats) {
+  NEED(c);
   int rc = w2b_epoch_begin(c);
   if (rc) return rc;
   w2b_step_stats st;
@@ -691,6 +760,9 @@ extern "C" int w2b_train_epoch(w2b_ctx *c, double *loss, w2b_step_stats *stats) 
 // --------------------------------------------------------------------------- parity hooks
 extern "C" int w2b_trace(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trace_rec *out, int64_t cap,
                          int64_t *n_out) {
+  NEED(c);
+  NEED(n_out);
+  if (cap > 0) NEED(out);
   if (!c->have_corpus || !c->have_counts || !c->resident) {
     w2b_set_error("trace needs set_vocab_counts + a resident corpus");
     return W2B_ESTATE;
@@ -708,14 +780,15 @@ extern "C" int w2b_trace(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trac
   s.ovr_tok = ovr ? c->shard_first[i] : -1;
   s.limit = c->n_tokens;
   s.limit_is_eof = 1;
-  ShardState *d_s = nullptr;
-  float *d_alpha = nullptr;
-  unsigned long long *d_cnt = nullptr;
-  w2b_trace_rec *d_tr = nullptr;
-  CK(cudaMalloc(&d_s, sizeof s));
-  CK(cudaMalloc(&d_alpha, sizeof(float)));
-  CK(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
-  CK(cudaMalloc(&d_tr, std::max<int64_t>(cap, 1) * sizeof(w2b_trace_rec)));
+  DevTmp t_s, t_alpha, t_cnt, t_tr;
+  CK(t_s.alloc(sizeof s));
+  CK(t_alpha.alloc(sizeof(float)));
+  CK(t_cnt.alloc(2 * sizeof(unsigned long long)));
+  CK(t_tr.alloc(std::max<int64_t>(cap, 1) * sizeof(w2b_trace_rec)));
+  ShardState *d_s = t_s.as<ShardState>();
+  float *d_alpha = t_alpha.as<float>();
+  unsigned long long *d_cnt = t_cnt.as<unsigned long long>();
+  w2b_trace_rec *d_tr = t_tr.as<w2b_trace_rec>();
   CK(cudaMemcpy(d_s, &s, sizeof s, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_alpha, &c->cfg.alpha, sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
@@ -743,14 +816,14 @@ extern "C" int w2b_trace(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trac
   CK(cudaStreamSynchronize(c->stream));
   unsigned long long cnt[2];
   CK(cudaMemcpy(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost));
-  int64_t n = std::min<int64_t>((int64_t)cnt[1], cap);
-  CK(cudaMemcpy(out, d_tr, n * sizeof(w2b_trace_rec), cudaMemcpyDeviceToHost));
+  int64_t n = std::max<int64_t>(0, std::min<int64_t>((int64_t)cnt[1], cap));
+  if (n) CK(cudaMemcpy(out, d_tr, n * sizeof(w2b_trace_rec), cudaMemcpyDeviceToHost));
   *n_out = n;
-  cudaFree(d_s); cudaFree(d_alpha); cudaFree(d_cnt); cudaFree(d_tr);
   return W2B_OK;
 }
 
 extern "C" int w2b_strict_prefix(w2b_ctx *c, int shard, int64_t max_iterations, double *loss) {
+  NEED(c);
   if (c->cfg.mode != W2B_MODE_STRICT) { w2b_set_error("strict_prefix needs W2B_MODE_STRICT"); return W2B_ESTATE; }
   if (!c->have_corpus || !c->have_tables || !c->have_counts || !c->resident) {
     w2b_set_error("strict_prefix before setup");
@@ -777,15 +850,22 @@ extern "C" int w2b_strict_prefix(w2b_ctx *c, int shard, int64_t max_iterations, 
 
 extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, const int32_t *targets, int nt,
                                   float *f_out) {
+  NEED(c);
   if (!c->have_tables) { w2b_set_error("init_tables first"); return W2B_ESTATE; }
   if (cw < 0 || cw > 2 * W2B_MAX_WINDOW || nt < 0 || nt > W2B_MAX_NEGATIVE + 1) { w2b_set_error("cw/nt out of range"); return W2B_EINVAL; }
+  if ((cw > 0 && !ctx_ids) || (nt > 0 && !targets)) { w2b_set_error("w2b_apply_position: null ids"); return W2B_EINVAL; }
+  for (int k = 0; k < cw + nt; ++k) {
+    const int id = k < cw ? ctx_ids[k] : targets[k - cw];
+    if (id < 0 || id >= c->cfg.vocab_size) { w2b_set_error("w2b_apply_position: id %d out of range", id); return W2B_EINVAL; }
+  }
   CK(cudaSetDevice(c->cfg.device));
-  int *d_ids = nullptr;
-  float *d_f = nullptr;
-  CK(cudaMalloc(&d_ids, (cw + nt + 1) * sizeof(int)));
-  CK(cudaMalloc(&d_f, (nt + 1) * sizeof(float)));
-  CK(cudaMemcpy(d_ids, ctx_ids, cw * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_ids + cw, targets, nt * sizeof(int), cudaMemcpyHostToDevice));
+  DevTmp t_ids, t_f;
+  CK(t_ids.alloc((cw + nt + 1) * sizeof(int)));
+  CK(t_f.alloc((nt + 1) * sizeof(float)));
+  int *d_ids = t_ids.as<int>();
+  float *d_f = t_f.as<float>();
+  if (cw) CK(cudaMemcpy(d_ids, ctx_ids, cw * sizeof(int), cudaMemcpyHostToDevice));
+  if (nt) CK(cudaMemcpy(d_ids + cw, targets, nt * sizeof(int), cudaMemcpyHostToDevice));
   TrainParams p = base_params(c);
   apply_fn fn = pick_apply(c);
   const size_t smem = dyn_smem(c);
@@ -793,13 +873,12 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
   fn<<<1, c->threads, smem, c->stream>>>(p, d_ids, cw, d_ids + cw, nt, d_f, nullptr);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
-  if (f_out) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));
-  cudaFree(d_ids);
-  cudaFree(d_f);
+  if (f_out && nt) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));
   return W2B_OK;
 }
 
 extern "C" int w2b_get_state(w2b_ctx *c, float *alpha, int64_t *wca) {
+  NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   unsigned long long w = 0;
   if (alpha) CK(cudaMemcpy(alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
@@ -809,6 +888,7 @@ extern "C" int w2b_get_state(w2b_ctx *c, float *alpha, int64_t *wca) {
 }
 
 extern "C" int w2b_set_state(w2b_ctx *c, float alpha, int64_t wca) {
+  NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   unsigned long long w = (unsigned long long)wca;
   CK(cudaMemcpy(c->d_alpha, &alpha, sizeof(float), cudaMemcpyHostToDevice));
@@ -818,6 +898,7 @@ extern "C" int w2b_set_state(w2b_ctx *c, float alpha, int64_t wca) {
 }
 
 extern "C" int w2b_download_raw(w2b_ctx *c, float *u, float *v) {
+  NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
   if (u) CK(cudaMemcpy(u, c->d_u, n, cudaMemcpyDeviceToHost));
@@ -826,6 +907,7 @@ extern "C" int w2b_download_raw(w2b_ctx *c, float *u, float *v) {
 }
 
 extern "C" int w2b_upload_raw(w2b_ctx *c, const float *u, const float *v) {
+  NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
   if (u) CK(cudaMemcpy(c->d_u, u, n, cudaMemcpyHostToDevice));
@@ -834,12 +916,16 @@ extern "C" int w2b_upload_raw(w2b_ctx *c, const float *u, const float *v) {
 }
 
 extern "C" int w2b_download_table(w2b_ctx *c, int32_t *table) {
+  NEED(c);
+  NEED(table);
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpy(table, c->d_table, (size_t)W2B_TABLE_SIZE * sizeof(int), cudaMemcpyDeviceToHost));
   return W2B_OK;
 }
 
 extern "C" int w2b_download_exptable(w2b_ctx *c, float *t) {
+  NEED(c);
+  NEED(t);
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpy(t, c->d_exptab, kExpN * sizeof(float), cudaMemcpyDeviceToHost));
   return W2B_OK;
@@ -853,9 +939,9 @@ struct CkptHeader {
   int32_t pad;
 };
 extern "C" int w2b_checkpoint_save(w2b_ctx *c, const char *path, int64_t epochs_done) {
+  NEED(c);
+  NEED(path);
   CK(cudaSetDevice(c->cfg.device));
-  FILE *f = fopen(path, "wb");
-  if (!f) { w2b_set_error("cannot open %s for writing", path); return W2B_EIO; }
   CkptHeader h;
   memset(&h, 0, sizeof h);
   memcpy(h.magic, "W2BCKPT1", 8);
@@ -864,24 +950,29 @@ extern "C" int w2b_checkpoint_save(w2b_ctx *c, const char *path, int64_t epochs_
   CK(cudaMemcpy(&h.alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost));
   h.wca = (int64_t)w;
-  fwrite(&h, sizeof h, 1, f);
+  FILE *f = fopen(path, "wb");
+  if (!f) { w2b_set_error("cannot open %s for writing", path); return W2B_EIO; }
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
   const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
   std::vector<float> buf(std::min(n, piece));
   for (const float *src : {c->d_u, c->d_v})
-    for (size_t o = 0; o < n; o += piece) {
+    for (size_t o = 0; o < n && ok; o += piece) {
       const size_t k = std::min(piece, n - o);
       if (cudaMemcpy(buf.data(), src + o, k * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
         fclose(f);
         w2b_set_error("checkpoint download failed");
         return W2B_ECUDA;
       }
-      fwrite(buf.data(), sizeof(float), k, f);
+      ok = fwrite(buf.data(), sizeof(float), k, f) == k;
     }
-  fclose(f);
+  if (fclose(f) != 0) ok = false;
+  if (!ok) { w2b_set_error("short write to %s (disk full?)", path); return W2B_EIO; }
   return W2B_OK;
 }
 
 extern "C" int w2b_checkpoint_load(w2b_ctx *c, const char *path, int64_t *epochs_done) {
+  NEED(c);
+  NEED(path);
   CK(cudaSetDevice(c->cfg.device));
   FILE *f = fopen(path, "rb");
   if (!f) { w2b_set_error("cannot open %s", path); return W2B_EIO; }
@@ -912,33 +1003,40 @@ extern "C" int w2b_checkpoint_load(w2b_ctx *c, const char *path, int64_t *epochs
 }
 
 extern "C" int w2b_export(w2b_ctx *c, float *out) {
+  NEED(c);
+  NEED(out);
   CK(cudaSetDevice(c->cfg.device));
   const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
-  float *d_out = nullptr;
-  CK(cudaMalloc(&d_out, n * sizeof(float)));
+  DevTmp t_out;
+  CK(t_out.alloc(n * sizeof(float)));
+  float *d_out = t_out.as<float>();
   export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, c->d_v, d_out, n, c->cfg.bitlevel);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_out));
   return W2B_OK;
 }
 
 extern "C" int w2b_quantize(w2b_ctx *c, const float *in, float *out, int64_t n, int bitlevel) {
+  NEED(c);
+  if (n <= 0) return W2B_OK;
+  NEED(in);
+  NEED(out);
   CK(cudaSetDevice(c->cfg.device));
-  float *d = nullptr;
-  CK(cudaMalloc(&d, 2 * std::max<int64_t>(n, 1) * sizeof(float)));
+  DevTmp t;
+  CK(t.alloc(2 * n * sizeof(float)));
+  float *d = t.as<float>();
   CK(cudaMemcpy(d, in, n * sizeof(float), cudaMemcpyHostToDevice));
   quantize_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d, d + n, n, bitlevel);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d + n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d));
   return W2B_OK;
 }
 
 // ------------------------------------------------------------------------------ multi-GPU
 extern "C" int w2b_device_ptrs(w2b_ctx *c, void **u, void **v, int64_t *elems) {
+  NEED(c);
   if (u) *u = c->d_u;
   if (v) *v = c->d_v;
   if (elems) *elems = c->cfg.vocab_size * c->cfg.layer1_size;
@@ -946,6 +1044,7 @@ extern "C" int w2b_device_ptrs(w2b_ctx *c, void **u, void **v, int64_t *elems) {
 }
 
 extern "C" int w2b_nccl_unique_id(void *id128) {
+  NEED(id128);
   int rc = nccl_load();
   if (rc) return rc;
   nccl_uid id;
@@ -956,7 +1055,10 @@ extern "C" int w2b_nccl_unique_id(void *id128) {
 }
 
 extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks) {
+  NEED(c);
   if (nranks <= 1) { c->rank = 0; c->nranks = 1; return W2B_OK; }
+  NEED(id128);
+  if (rank < 0 || rank >= nranks) { w2b_set_error("rank %d outside [0,%d)", rank, nranks); return W2B_EINVAL; }
   int rc = nccl_load();
   if (rc) return rc;
   CK(cudaSetDevice(c->cfg.device));
@@ -970,6 +1072,7 @@ extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks
 }
 
 extern "C" int w2b_scale_tables(w2b_ctx *c, float s) {
+  NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
   scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, n, s);
@@ -982,6 +1085,7 @@ extern "C" int w2b_scale_tables(w2b_ctx *c, float s) {
 // Replica averaging: u, v <- mean over ranks (ncclAvg, in place, on this context's
 // stream); word_count_actual <- exact global sum.  G=1: no-op, NCCL never touched.
 extern "C" int w2b_sync(w2b_ctx *c) {
+  NEED(c);
   if (c->nranks <= 1) return W2B_OK;
   if (!c->comm) { w2b_set_error("w2b_nccl_init first"); return W2B_ESTATE; }
   CK(cudaSetDevice(c->cfg.device));

@@ -52,6 +52,29 @@ void w2b_exptable(float *out) {
   }
 }
 
+// Sub-sampling threshold `ran` of every word (:403-404), float32 throughout as in the reference:
+// (sqrt(cn / (sample*train_words)) + 1) * (sample*train_words) / cn.
+void w2b_keep_thresholds(const int64_t *cn, int64_t V, int64_t train_words, float sample, float *out) {
+  const float S = sample * (float)train_words;
+  for (int64_t w = 0; w < V; ++w) out[w] = (sqrtf((float)cn[w] / S) + 1.f) * S / (float)cn[w];
+}
+
+extern "C" int w2b_host_unigram_bounds(const int64_t *cn, int64_t V, int32_t *start) {
+  if (!cn || !start || V < 1) { w2b_set_error("w2b_host_unigram_bounds: bad argument"); return W2B_EINVAL; }
+  w2b_unigram_bounds(cn, V, start);
+  return W2B_OK;
+}
+extern "C" int w2b_host_exptable(float *out) {
+  if (!out) { w2b_set_error("w2b_host_exptable: null argument"); return W2B_EINVAL; }
+  w2b_exptable(out);
+  return W2B_OK;
+}
+extern "C" int w2b_host_keep_thresholds(const int64_t *cn, int64_t V, int64_t train_words, float sample, float *out) {
+  if (!cn || !out || V < 1) { w2b_set_error("w2b_host_keep_thresholds: bad argument"); return W2B_EINVAL; }
+  w2b_keep_thresholds(cn, V, train_words, sample, out);
+  return W2B_OK;
+}
+
 // ----------------------------------------------------------------------------- tokeniser
 namespace {
 
@@ -178,14 +201,22 @@ static void tokenize_chunk(const uint8_t *buf, int64_t begin, int64_t end, Chunk
 }
 
 extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out) {
+  if (!out) {
+    w2b_set_error("w2b_corpus_load: null out");
+    return W2B_EINVAL;
+  }
   *out = nullptr;
-  int fd = open(path, O_RDONLY);
+  int fd = path ? open(path, O_RDONLY) : -1;
   if (fd < 0) {
     w2b_set_error("ERROR: training data file not found!");  // :272
     return W2B_EIO;
   }
   struct stat st;
-  fstat(fd, &st);
+  if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {  // a directory opens fine but cannot be mapped
+    close(fd);
+    w2b_set_error("ERROR: training data file not found!");
+    return W2B_EIO;
+  }
   w2b_corpus *c = new w2b_corpus();
   c->fd = fd;
   c->file_size = st.st_size;  // == ftell at EOF, :299
@@ -326,6 +357,10 @@ extern "C" int64_t w2b_corpus_num_tokens(const w2b_corpus *c) { return (int64_t)
 extern "C" const int32_t *w2b_corpus_tokens(const w2b_corpus *c) { return c->ids.data(); }
 
 extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int32_t *first) {
+  if (!c || !start || !first) {
+    w2b_set_error("w2b_corpus_shards: null argument");
+    return W2B_EINVAL;
+  }
   if (n < 1) {
     w2b_set_error("shard count must be >= 1");
     return W2B_EINVAL;
@@ -365,13 +400,17 @@ extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int
 
 extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
                                  int binary) {
+  if (!path || !c || !vec || V < 0 || V > (int64_t)c->words.size() || D < 1) {
+    w2b_set_error("w2b_write_vectors: bad argument");
+    return W2B_EINVAL;
+  }
   FILE *fo = fopen(path, "wb");
   if (!fo) {
     w2b_set_error("cannot open %s for writing", path);
     return W2B_EIO;
   }
-  static char iobuf[1 << 20];
-  setvbuf(fo, iobuf, _IOFBF, sizeof iobuf);
+  std::vector<char> iobuf(1 << 20);  // per call: two writers may run on two host threads
+  setvbuf(fo, iobuf.data(), _IOFBF, iobuf.size());
   fprintf(fo, "%lld %lld\n", (long long)V, (long long)D);
   for (int64_t a = 0; a < V; ++a) {
     fprintf(fo, "%s ", c->words[a]);
@@ -381,7 +420,11 @@ extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const fl
       for (int64_t b = 0; b < D; ++b) fprintf(fo, "%lf ", row[b]);
     fprintf(fo, "\n");
   }
-  fclose(fo);
+  const bool bad = ferror(fo) != 0;
+  if (fclose(fo) != 0 || bad) {  // the reference ignores write errors; a truncated vector file is worse
+    w2b_set_error("short write to %s (disk full?)", path);
+    return W2B_EIO;
+  }
   return W2B_OK;
 }
 
@@ -400,6 +443,10 @@ extern "C" int w2b_write_packed(const char *path, const w2b_corpus *c, const flo
                                 int bitlevel) {
   if (bitlevel != 1 && bitlevel != 2) {
     w2b_set_error("packed format supports bitlevel 1 and 2");
+    return W2B_EINVAL;
+  }
+  if (!path || !c || !vec || V < 0 || V > (int64_t)c->words.size() || D < 1) {
+    w2b_set_error("w2b_write_packed: bad argument");
     return W2B_EINVAL;
   }
   FILE *fo = fopen(path, "wb");
@@ -421,7 +468,11 @@ extern "C" int w2b_write_packed(const char *path, const w2b_corpus *c, const flo
     fwrite(row.data(), 1, nbytes, fo);
     fputc('\n', fo);
   }
-  fclose(fo);
+  const bool bad = ferror(fo) != 0;
+  if (fclose(fo) != 0 || bad) {
+    w2b_set_error("short write to %s (disk full?)", path);
+    return W2B_EIO;
+  }
   return W2B_OK;
 }
 
@@ -435,7 +486,7 @@ extern "C" int w2b_read_packed_header(const char *path, int64_t *V, int64_t *D, 
   int b = 0;
   const int n = fscanf(f, "%lld %lld %d", &v, &d, &b);
   fclose(f);
-  if (n != 3 || (b != 1 && b != 2)) {
+  if (n != 3 || (b != 1 && b != 2) || v < 0 || d < 1) {
     w2b_set_error("%s is not a packed vector file", path);
     return W2B_EIO;
   }
@@ -449,6 +500,10 @@ extern "C" int w2b_read_packed(const char *path, float *vec, char *words, int ma
   int rc = w2b_read_packed_header(path, &V, &D, &bits);
   if (rc) return rc;
   FILE *f = fopen(path, "rb");
+  if (!f) {
+    w2b_set_error("cannot open %s", path);
+    return W2B_EIO;
+  }
   int ch;
   while ((ch = fgetc(f)) != EOF && ch != '\n') {}
   const int64_t nbytes = (D * bits + 7) / 8;

@@ -9,3 +9,5 @@ void w2b_set_error(const char *fmt, ...);
 void w2b_unigram_bounds(const int64_t *cn, int64_t V, int32_t *start);
 // expTable (:614-618), host expf.
 void w2b_exptable(float *out /*1000*/);
+// Sub-sampling thresholds `ran` (:403-404), float32.
+void w2b_keep_thresholds(const int64_t *cn, int64_t V, int64_t train_words, float sample, float *out /*V*/);
