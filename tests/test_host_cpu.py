@@ -174,3 +174,80 @@ def test_packed_vector_file_round_trip(tmp_path, bits):
     assert ratio > 5                       # 20 dims only: the word names dominate, still >> 1
     with pytest.raises(w2b.W2BError):
         c.write_packed(out, vec, 4)
+
+
+# ---------------------------------------------------------------- host arithmetic the device path uploads
+def test_host_unigram_bounds_match_oracle():
+    """InitUnigramTable (:112-128) in boundary form, same libm pow(): the boundaries libw2b uploads equal the
+    oracle's (which tests/test_oracle_vs_ref.py pins to the reference's full 1e8-entry table)."""
+    import word2bits_b200 as w2b
+    rng = np.random.default_rng(3)
+    cases = [
+        np.array([0, 5, 5, 5], np.int64),                                  # </s> never seen
+        np.array([7, 1], np.int64),
+        np.concatenate([[1000], np.sort(rng.integers(1, 10**6, 5000))[::-1]]).astype(np.int64),
+        np.maximum(1, (3e8 / np.arange(1, 400_001)).astype(np.int64)),    # C2-sized Zipf vocabulary
+        np.concatenate([[0], np.full(3_000_000, 1)]).astype(np.int64),    # more words than some slices are wide
+    ]
+    for cn in cases:
+        got = w2b.host_unigram_bounds(cn)
+        want = po.unigram_bounds(cn)
+        assert got.dtype == np.int32 and np.array_equal(got.astype(np.int64), want), len(cn)
+        assert got[0] == 0 and got[-1] == w2b._lib.TABLE_SIZE and np.all(np.diff(got.astype(np.int64)) >= 0)
+
+
+def test_host_exptable_and_keep_thresholds():
+    import word2bits_b200 as w2b
+    assert np.array_equal(w2b.host_exptable().view(np.uint32), po.exptable().view(np.uint32))
+    # `ran` (:403-404) in float32, operation by operation
+    rng = np.random.default_rng(5)
+    cn = np.concatenate([[0], rng.integers(1, 10**7, 2000)]).astype(np.int64)
+    for train_words, sample in ((int(cn.sum()), 1e-3), (17_000_000, 1e-4), (123, 1e-3)):
+        got = w2b.host_keep_thresholds(cn, train_words, sample)
+        S = np.float32(sample) * np.float32(train_words)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            c = cn.astype(np.float32)
+            want = (np.sqrt(c / S, dtype=np.float32) + np.float32(1)) * S / c
+        assert np.array_equal(got[1:].view(np.uint32), want[1:].astype(np.float32).view(np.uint32))
+
+
+def test_host_lcg_jump_tables():
+    """r_k = r*ja[k] + jc[k] is k steps of the reference's LCG (:352,:405,:428,:455); pa/pc are the 2^j-step
+    constants InitNet's jump-ahead uses."""
+    import word2bits_b200 as w2b
+    ja, jc, pa, pc = w2b.host_lcg_tables()
+    M = (1 << 64) - 1
+    L = po.lib()
+    for r0 in (0, 1, 11, 147, 2**63 + 12345, M):
+        r = r0
+        for k in range(65):
+            assert (r0 * int(ja[k]) + int(jc[k])) & M == r, (r0, k)
+            r = L.w2bo_lcg(r)
+    r = 1
+    steps = 0
+    for j in range(20):  # 2^j steps by repeated single steps, j < 20
+        while steps < (1 << j):
+            r = L.w2bo_lcg(r)
+            steps += 1
+        assert (1 * int(pa[j]) + int(pc[j])) & M == r, j
+    for j in range(1, 64):  # squaring rule for the rest
+        assert int(pa[j]) == (int(pa[j - 1]) ** 2) & M
+        assert int(pc[j]) == (int(pa[j - 1]) * int(pc[j - 1]) + int(pc[j - 1])) & M
+
+
+def test_null_arguments_are_errors_not_crashes():
+    import ctypes as C
+    import word2bits_b200 as w2b
+    from word2bits_b200._lib import lib, EINVAL
+    assert lib.w2b_train_step(None, 10, None) == EINVAL and b"null" in lib.w2b_last_error()
+    for fn in ("w2b_init_tables", "w2b_epoch_begin", "w2b_sync"):
+        assert getattr(lib, fn)(None) == EINVAL
+    assert lib.w2b_export(None, None) == EINVAL
+    assert lib.w2b_create(None, C.byref(C.c_void_p())) == EINVAL
+    assert lib.w2b_ring_plan_query(None, None) == EINVAL
+    assert lib.w2b_corpus_shards(None, 2, None, None) == EINVAL
+    assert lib.w2b_host_unigram_bounds(None, 5, None) == EINVAL
+    assert lib.w2b_destroy(None) == 0  # like free(NULL)
+    with pytest.raises(w2b.W2BError) as e:
+        w2b.Corpus(os.path.join(ROOT, "tests"), 1)  # a directory is not a training file
+    assert e.value.code == 3

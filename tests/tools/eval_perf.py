@@ -1,7 +1,8 @@
-"""Timing of the 8(f) rows on the GPU box: analogy evaluator at the Google-set shape and the host
-tokenizer.  python tools/eval_perf.py [V] [D] [questions]"""
+"""TEST INFRASTRUCTURE (runs the compiled reference under oracle/_ref next to the product).
+Timing of the 8(f) rows on the GPU box: analogy evaluator at the Google-set shape and the host
+tokenizer.  python tests/tools/eval_perf.py [V] [D] [questions]"""
 import os, sys, time, subprocess, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import word2bits_b200 as w2b
 import bench
@@ -34,7 +35,7 @@ wall = time.time() - t0
 flops = 2.0 * acc["questions_seen"] * acc["vocab"] * acc["size"]
 print("GPU evaluator: %d questions x V=%d x D=%d: kernels %.1f ms (%.1f TFLOP/s fp32), wall %.1f s (file read + H2D included)"
       % (acc["questions_seen"], acc["vocab"], acc["size"], acc["gpu_ms"], flops / acc["gpu_ms"] / 1e9, wall), flush=True)
-refbin = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "compute_accuracy")
+refbin = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle", "_ref", "compute_accuracy")
 if os.path.exists(refbin):
     qs = os.path.join(tmp, "qs.txt")
     nsmall = 40

@@ -1,13 +1,14 @@
-"""SURVEY Appendix B quality protocol at full size: planted-topic corpus (V=20000, 50 topics, 250k
+"""TEST INFRASTRUCTURE (runs the compiled reference under oracle/_ref next to the product).
+SURVEY Appendix B quality protocol at full size: planted-topic corpus (V=20000, 50 topics, 250k
 sentences x 20 tokens), D=200 W=8 neg=24 bitlevel 1, 3 epochs.  Reference (16 CPU threads) vs the GPU
 CLI at its default shard count (hundreds of concurrent shards) and at 16 shards.  Prints epoch losses
 and same-topic purity of the top-10 neighbours of the 3000 most frequent words."""
 import os, re, subprocess, sys, tempfile, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from tests.util import planted_topic_corpus, topic_purity
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 tmp = tempfile.mkdtemp()
 path = planted_topic_corpus(os.path.join(tmp, "topics.txt"), vocab=20000, topics=50, sentences=250000, length=20)
 common = ["-train", path, "-size", "200", "-window", "8", "-negative", "24", "-bitlevel", "1", "-iter", "3",
