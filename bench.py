@@ -8,6 +8,9 @@ synthetic Zipf(1.0) corpus, V=400k, window 10 — BASELINE.json configs[1].  N>1
 under torchrun (one rank per GPU): every GPU trains its own shard range on a full replica of
 u/v and the replicas are all-reduce-averaged over NCCL every --sync-every steps.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each field means.
+
+--workload c3|c4|c5 runs the other BASELINE.json configurations through the same harness (they
+are parity-test shapes, not the headline: the default, and what the driver runs, is c2).
 """
 import argparse
 import ctypes
@@ -27,6 +30,20 @@ sys.path.insert(0, ROOT)
 METRIC = "words/sec training throughput, bitlevel=1 size=800 neg=24; HBM GB/s vs peak"
 V, D, WINDOW, NEG, BITS = 400_000, 800, 10, 24, 1
 SAMPLE, ALPHA = 1e-3, 0.05
+# BASELINE.json configs[1..4]: name -> (V, D, window, negative, bitlevel, workload text)
+WORKLOADS = {
+    "c2": (400_000, 800, 10, 24, 1, "synthetic Zipf corpus vocab=400k, bitlevel=1, size=800, window=10, negative=24"),
+    "c3": (400_000, 400, 10, 12, 2, "synthetic Zipf corpus vocab=400k, bitlevel=2, size=400, window=10, negative=12"),
+    "c4": (400_000, 400, 10, 24, 0, "synthetic Zipf corpus vocab=400k, bitlevel=0 (fp32), size=400, window=10, negative=24"),
+    "c5": (3_700_000, 800, 10, 24, 1, "synthetic Zipf corpus vocab=3.7M, bitlevel=1, size=800, window=10, negative=24"),
+}
+WORKLOAD, WORKLOAD_TEXT = "c2", WORKLOADS["c2"][5]
+
+
+def select_workload(name):
+    global V, D, WINDOW, NEG, BITS, WORKLOAD, WORKLOAD_TEXT
+    V, D, WINDOW, NEG, BITS, WORKLOAD_TEXT = WORKLOADS[name]
+    WORKLOAD = name
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -109,6 +126,8 @@ def measured_peak():
 
 
 def ncu_traffic_per_position():
+    if WORKLOAD != "c2":  # the committed ncu capture is of the headline shape
+        return None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return float(json.load(f)["dram_bytes_per_position"])
@@ -190,7 +209,7 @@ def run_reference(args, rank, budget_s=100.0):
     return {"metric": METRIC, "value": value, "unit": "words/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "synthetic Zipf corpus vocab=400k, bitlevel=1, size=800, window=10, negative=24 (CPU, bounded sample)",
+            "config": {"workload": WORKLOAD_TEXT + " (CPU, bounded sample)",
                        "threads": threads, "host_threads": cores},
             "cpu_baseline": {"value": value, "unit": "words/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "words/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -216,7 +235,9 @@ def main():
     ap.add_argument("--words-per-shard", type=int, default=65536)
     ap.add_argument("--sync-every", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -334,7 +355,8 @@ def main():
     tpp = ncu_traffic_per_position()
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": (tpp * a["positions"] / max(a["launches"], 1)) if tpp else None,
-            "peak_source": peak_src, "kernel": "train_ring_kernel<1,7> (one launch per step)",
+            "peak_source": peak_src,
+            "kernel": "train_ring_kernel<%d,%d,2> (one launch per step)" % (BITS if BITS in (0, 1, 2) else 9, (D // 4 + 31) // 32),
             "algorithmic_bytes_per_launch": alg_bytes / max(a["launches"], 1),
             "kernel_ms_per_launch": a["kernel_ms"] / max(a["launches"], 1),
             "bytes_per_position": alg_bytes / max(a["positions"], 1)}
@@ -352,11 +374,11 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "words/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "synthetic Zipf corpus vocab=400k, bitlevel=1, size=800, window=10, negative=24, 1xB200"
-                      if world == 1 else "synthetic Zipf corpus vocab=400k per-GPU shard, bitlevel=1, size=800, window=10, negative=24, %dxB200 data-parallel" % world,
+           "config": {"workload": WORKLOAD_TEXT + ", 1xB200" if world == 1 else
+                      WORKLOAD_TEXT + ", %dxB200 data-parallel (one corpus block per GPU)" % world,
                       "vocab": V, "size": D, "window": WINDOW, "negative": NEG, "bitlevel": BITS, "sample": SAMPLE,
                       "shards_per_gpu": S_local, "words_per_shard_per_step": B,
-                      "l2": "inputs larger than L2: 2 x 1.28 GB embedding tables + 400 MB unigram table per GPU, rows drawn at random",
+                      "l2": "inputs larger than L2: 2 x %.2f GB embedding tables + 400 MB unigram table per GPU, rows drawn at random" % ((V + 1) * D * 4 / 1e9),
                       "parallelism": "dp%d, replica all-reduce-average of u and v every %d steps (NCCL)" % (world, args.sync_every) if world > 1 else "single GPU, %d concurrent shards (one CTA each)" % S_local},
            "positions_per_s": positions / dev_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
            "sync_ms_per_step": a["sync_ms"] / args.steps,
