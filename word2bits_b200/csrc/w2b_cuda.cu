@@ -189,28 +189,38 @@ typedef void (*ring_fn)(TrainParams, int, int, int);
 // everywhere — R=3 at D=800 spills (a CTA with 9+ warps gets at most 168 registers per thread:
 // three warps share one SM sub-partition's 16K registers) and drops 5782 -> 4440 GB/s; R=4 at
 // D=400 costs the second CTA per SM (204 registers) and halves throughput.
-template <int BM>
+template <int BM, int OPT>
 static ring_fn ring_by_nj(int nj) {
   switch (nj) {
-    case 1: return train_ring_kernel<BM, 1, 2>;
-    case 2: return train_ring_kernel<BM, 2, 2>;
-    case 3: return train_ring_kernel<BM, 3, 2>;
-    case 4: return train_ring_kernel<BM, 4, 2>;
-    case 5: return train_ring_kernel<BM, 5, 2>;
-    case 6: return train_ring_kernel<BM, 6, 2>;
-    case 7: return train_ring_kernel<BM, 7, 2>;
-    case 8: return train_ring_kernel<BM, 8, 2>;
+    case 1: return train_ring_kernel<BM, 1, 2, OPT>;
+    case 2: return train_ring_kernel<BM, 2, 2, OPT>;
+    case 3: return train_ring_kernel<BM, 3, 2, OPT>;
+    case 4: return train_ring_kernel<BM, 4, 2, OPT>;
+    case 5: return train_ring_kernel<BM, 5, 2, OPT>;
+    case 6: return train_ring_kernel<BM, 6, 2, OPT>;
+    case 7: return train_ring_kernel<BM, 7, 2, OPT>;
+    case 8: return train_ring_kernel<BM, 8, 2, OPT>;
   }
   return nullptr;
 }
 static int ring_rows_in_flight(int) { return 2; }
+// cfg.kernel: 0 = the ring kernel measured in round 1, 2 = its OPT variant (same protocol, division-free
+// index arithmetic; bitlevel 0/1/2 only — other bit levels stay on the measured kernel), 1 = register kernel.
 static ring_fn pick_ring(const w2b_ctx *c) {
   const int nj = (c->ncol + 31) / 32;
+  if (c->cfg.kernel == 2) {
+    switch (bm_of(c->cfg.bitlevel)) {
+      case 0: return ring_by_nj<0, 1>(nj);
+      case 1: return ring_by_nj<1, 1>(nj);
+      case 2: return ring_by_nj<2, 1>(nj);
+      default: break;
+    }
+  }
   switch (bm_of(c->cfg.bitlevel)) {
-    case 0: return ring_by_nj<0>(nj);
-    case 1: return ring_by_nj<1>(nj);
-    case 2: return ring_by_nj<2>(nj);
-    default: return ring_by_nj<9>(nj);
+    case 0: return ring_by_nj<0, 0>(nj);
+    case 1: return ring_by_nj<1, 0>(nj);
+    case 2: return ring_by_nj<2, 0>(nj);
+    default: return ring_by_nj<9, 0>(nj);
   }
 }
 
@@ -393,6 +403,19 @@ extern "C" int w2b_host_lcg_tables(uint64_t *ja, uint64_t *jc, uint64_t *pa, uin
   lcg_tables(JA, JC, PA, PC);
   for (int i = 0; i < 65; ++i) { ja[i] = JA[i]; jc[i] = JC[i]; }
   for (int i = 0; i < 64; ++i) { pa[i] = PA[i]; pc[i] = PC[i]; }
+  return W2B_OK;
+}
+
+// The division-free row index of the kernel = 2 variant, evaluated by the very same inline helpers on the
+// host (tests compare it with % and / over the kernel's whole operand range).
+extern "C" int w2b_host_ring_index(int vs0, int i, int nv, int G, int *slot, int *group) {
+  NEED(slot);
+  NEED(group);
+  if (nv < 1 || G < 1 || vs0 < 0 || vs0 >= nv || i < 0) { w2b_set_error("w2b_host_ring_index: bad argument"); return W2B_EINVAL; }
+  unsigned us = 0, ug = 0;
+  ring_row_index((unsigned)vs0, (unsigned)i, (unsigned)nv, ring_magic((unsigned)nv), ring_magic((unsigned)G), &us, &ug);
+  *slot = (int)us;
+  *group = (int)ug;
   return W2B_OK;
 }
 

@@ -145,7 +145,34 @@ __device__ __forceinline__ int mod_small(unsigned long long r, unsigned w) {
   return (int)(((hi % w) * two32 + lo % w) % w);
 }
 
-template <int BM, int NJ, int R>
+// Division-free index arithmetic of the OPT = 1 variant: floor(x / d) == umulhi(x, ceil(2^32 / d)) exactly
+// whenever x * d < 2^32 and d >= 2; d == 1 is encoded as magic == 0 (tests/test_host_cpu.py checks the
+// identity exhaustively over the kernel's operand ranges through w2b_host_ring_index).
+__host__ __device__ inline unsigned ring_magic(unsigned d) {
+  return d <= 1u ? 0u : (unsigned)((0x100000000ull + d - 1u) / d);
+}
+__host__ __device__ inline unsigned ring_div(unsigned x, unsigned magic) {
+#ifdef __CUDA_ARCH__
+  return magic ? __umulhi(x, magic) : x;
+#else
+  return magic ? (unsigned)(((unsigned long long)x * magic) >> 32) : x;
+#endif
+}
+// slot of target row i of a position whose first row sits in slot vs0 (< nv), and the landing barrier
+// (group) the row belongs to
+__host__ __device__ inline void ring_row_index(unsigned vs0, unsigned i, unsigned nv, unsigned nv_magic,
+                                               unsigned g_magic, unsigned *slot, unsigned *group) {
+  const unsigned x = vs0 + i;
+  *slot = x - ring_div(x, nv_magic) * nv;
+  *group = ring_div(i, g_magic);
+}
+
+// OPT = 0: the kernel measured in round 1.  OPT = 1 (cfg.kernel = 2): same protocol
+// and arithmetic, fewer instructions on the consumer warps' critical path — slot / group indices without
+// integer division (the signed / and % by run-time nv and G cost ~100 SASS instructions per 2-row batch in
+// front of the first row load), compile-time column offsets for all but the last float4 column group, and
+// running slot counters in the loader.  Kept as a variant until it has been measured on the GPU.
+template <int BM, int NJ, int R, int OPT = 0>
 __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -356,6 +383,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
     const int ngmax = (p.negative + 1 + G - 1) / G;
     int u_alloc = 0;
     int v_alloc = 0;  // rows handed to the v-ring so far; row i lives in slot i % nv on its (i / nv)-th use
+    int u_slot = 0, v_slot = 0, v_use = 0;  // OPT: u_alloc % nu, v_alloc % nv, v_alloc / nv kept incrementally
     for (int q = 0;; ++q) {
       while (ctl->desc_ready <= q) __nanosleep(p.sleep_ns);
       __threadfence_block();
@@ -370,13 +398,23 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
       // ---- context rows -> u-ring
       while (u_alloc + cw - ctl->urel > nu) __nanosleep(p.sleep_ns);
       if (lane == 0) {
-        d->us0 = u_alloc % nu;
-        d->vs0 = v_alloc % nv;
+        d->us0 = OPT ? u_slot : u_alloc % nu;
+        d->vs0 = OPT ? v_slot : v_alloc % nv;
         mbar_expect_tx(ubar, (unsigned)cw * rowb);
       }
       __syncwarp();
-      for (int k = lane; k < cw; k += 32)
-        bulk_load(uring + (unsigned)((u_alloc + k) % nu) * rowb, p.u + (long long)d->ctx[k] * p.D, rowb, ubar);
+      if constexpr (OPT) {
+        for (int k = lane; k < cw; k += 32) {  // cw <= 2 * window <= nu: one wrap at most
+          int us = u_slot + k;
+          if (us >= nu) us -= nu;
+          bulk_load(uring + (unsigned)us * rowb, p.u + (long long)d->ctx[k] * p.D, rowb, ubar);
+        }
+        u_slot += cw;
+        if (u_slot >= nu) u_slot -= nu;
+      } else {
+        for (int k = lane; k < cw; k += 32)
+          bulk_load(uring + (unsigned)((u_alloc + k) % nu) * rowb, p.u + (long long)d->ctx[k] * p.D, rowb, ubar);
+      }
       u_alloc += cw;
       // ---- target rows -> v-ring, group by group.  Every group barrier of the slot is armed
       // for every position (0 bytes when the position has fewer groups) so that all barriers
@@ -387,12 +425,25 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
         if (lane == 0) mbar_expect_tx(vbar, (unsigned)ng * rowb);
         __syncwarp();
         if (lane < ng) {  // each lane waits for its own slot to have been released by its last user
-          const int vi = v_alloc + lane, sl = vi % nv, uses = vi / nv;
+          int sl, uses;
+          if constexpr (OPT) {  // ng <= G <= nv / 2: one wrap at most
+            sl = v_slot + lane;
+            uses = v_use;
+            if (sl >= nv) { sl -= nv; ++uses; }
+          } else {
+            const int vi = v_alloc + lane;
+            sl = vi % nv;
+            uses = vi / nv;
+          }
           while (s_rc[sl] < uses) __nanosleep(p.sleep_ns);
           bulk_load(vring + (unsigned)sl * rowb, p.v + (long long)d->tg[g0 + lane] * p.D, rowb, vbar);
         }
         __syncwarp();
         v_alloc += ng;
+        if constexpr (OPT) {
+          v_slot += ng;
+          if (v_slot >= nv) { v_slot -= nv; ++v_use; }
+        }
       }
     }
   } else {
@@ -414,9 +465,17 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c = j * 32 + lane;
-      on[j] = c < D4;
-      coff[j] = (unsigned)(on[j] ? c : D4 - 1) * 16u;
+      if (OPT && j < NJ - 1) {
+        // NJ == ceil(D4 / 32) (pick_ring): every column group but the last is full, so its lanes are always
+        // on and its byte offset is lane * 16 + a compile-time constant (an LDS/STS immediate)
+        on[j] = true;
+        coff[j] = (unsigned)lane * 16u + (unsigned)j * 512u;
+      } else {
+        on[j] = c < D4;
+        coff[j] = (unsigned)(on[j] ? c : D4 - 1) * 16u;
+      }
     }
+    const unsigned nv_magic = ring_magic((unsigned)nv), g_magic = ring_magic((unsigned)G);
     const bool col_on = tid < D4;
     const unsigned colb = (unsigned)(col_on ? tid : 0) * 16u;
 
@@ -473,8 +532,16 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
           const int i = i0 + t * ncw;
           have[t] = i < nt;
           const int ii = have[t] ? i : i0;
-          if (have[t]) mbar_wait(vbar0 + (slot * kMaxGrp + ii / G) * 8, par);
-          const int s = (vs0 + ii) % nv;  // a position may be longer than the ring (1+negative > nv)
+          int s;
+          if constexpr (OPT) {
+            unsigned us, ug;
+            ring_row_index((unsigned)vs0, (unsigned)ii, (unsigned)nv, nv_magic, g_magic, &us, &ug);
+            if (have[t]) mbar_wait(vbar0 + ((unsigned)slot * kMaxGrp + ug) * 8u, par);
+            s = (int)us;
+          } else {
+            if (have[t]) mbar_wait(vbar0 + (slot * kMaxGrp + ii / G) * 8, par);
+            s = (vs0 + ii) % nv;  // a position may be longer than the ring (1+negative > nv)
+          }
           sl[t] = s;
           row[t] = vring + (unsigned)s * rowb;
         }
