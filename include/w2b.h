@@ -97,7 +97,8 @@ typedef struct {
   int32_t group;       /* fast mode: target rows in flight per CTA step (0 = default) */
   int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
   int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel,
-                          2 = ring kernel variant with division-free index arithmetic (experimental) */
+                          experimental variants of the ring kernel: 2 = division-free index arithmetic,
+                          3 / 4 = 2 + 16 / 8 lanes per target row (narrow rows, D <= 512 / 256) */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
   int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed */
 } w2b_config;
@@ -139,6 +140,8 @@ typedef struct {
   int32_t threads;         /* CTA size */
   int32_t desc_depth;      /* positions in flight (descriptor ring) */
   int32_t max_groups;      /* landing barriers per descriptor slot */
+  int32_t units_per_warp;  /* target rows a consumer warp works on side by side (1; 2 / 4 for cfg.kernel 3 / 4) */
+  int32_t reserved;
   int64_t smem_bytes;      /* dynamic shared memory per CTA */
 } w2b_ring_plan;
 int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out);

@@ -73,6 +73,7 @@ class RingModel:
     def __init__(self, plan, window, negative, positions, seed=0, kND=None):
         self.nu, self.nv = plan["u_rows"], plan["v_rows"]
         self.G, self.R, self.ncw = plan["group"], plan["rows_in_flight"], plan["consumer_warps"]
+        self.upw = plan.get("units_per_warp", 1) or 1  # row units per consumer warp (LPR < 32 variants)
         self.kND = kND or plan["desc_depth"]
         self.kMaxGrp = plan["max_groups"]
         self.ngmax = (negative + 1 + self.G - 1) // self.G
@@ -175,10 +176,11 @@ class RingModel:
         return lambda: self.bar_arrivals[name] >= (gen + 1) * self.ncw
 
     def consumer(self, warp):
-        ncw, R, G, nv, kND = self.ncw, self.R, self.G, self.nv, self.kND
+        ncw, R, G, nv, kND, upw = self.ncw, self.R, self.G, self.nv, self.kND, self.upw
+        nunits = ncw * upw
         issuer = warp == ncw - 1
-        bq = BulkQueue()          # lane 0's bulk groups
-        prev = [-1] * R
+        # one bulk-group queue and one prev[] per unit leader; lane 0 (the issuer's thread) leads unit 0
+        units = [dict(bq=BulkQueue(), prev=[-1] * R) for _ in range(upw)]
         pend = None               # issuer: (descriptor, q) whose u scatter is staged
         q = 0
         while True:
@@ -205,8 +207,8 @@ class RingModel:
                     eb = self.errbuf[pq & 1]
                     assert eb.get("holds") == pq, "staging row does not hold this position's error"
                     for _ in range(pd["cw"]):
-                        bq.issue(eb)
-                    bq.commit()
+                        units[0]["bq"].issue(eb)
+                    units[0]["bq"].commit()
                     self.u_scattered.add(pq)
                     pd["released"] = True
                     pend = None
@@ -214,39 +216,54 @@ class RingModel:
             if fin:
                 break
             nt, vs0 = d["nt"], d["vs0"]
-            i0 = warp
-            while i0 < nt:
-                rows = [i0 + t * ncw for t in range(R)]
-                have = [i < nt for i in rows]
-                for t in range(R):
-                    if have[t]:
-                        gi = rows[t] // G
-                        yield lambda slot=slot, gi=gi, phase=phase: self.vbar[slot][gi].completed >= phase + 1
-                        assert self.vbar[slot][gi].completed == phase + 1, "v barrier ran a phase ahead"
-                sl = [(vs0 + (rows[t] if have[t] else i0)) % nv for t in range(R)]
-                for t in range(R):
-                    if have[t]:
+            i0w = warp * upw
+            while i0w < nt:
+                batch = []
+                for sub in range(upw):
+                    i0 = i0w + sub
+                    ifall = i0 if (upw == 1 or i0 < nt) else i0w
+                    rows = [i0 + t * nunits for t in range(R)]
+                    have = [i < nt for i in rows]
+                    batch.append((rows, have, ifall))
+                # every lane waits for the barrier of the row it is going to read (LPR < 32: also the
+                # lanes without a row of their own, on the landed row they re-read)
+                for rows, have, ifall in batch:
+                    for t in range(R):
+                        if have[t] or upw > 1:
+                            gi = (rows[t] if have[t] else ifall) // G
+                            yield lambda slot=slot, gi=gi, phase=phase: self.vbar[slot][gi].completed >= phase + 1
+                            assert self.vbar[slot][gi].completed == phase + 1, "v barrier ran a phase ahead"
+                for u, (rows, have, ifall) in zip(units, batch):
+                    sl = [(vs0 + (rows[t] if have[t] else ifall)) % nv for t in range(R)]
+                    for t in range(R):
                         s = self.vslot[sl[t]]
-                        assert s["state"] == "full" and s["row"] == (q, rows[t]), \
-                            "target row (%d,%d) not in slot %d: %s" % (q, rows[t], sl[t], s)
-                        s["state"] = "update"   # overwritten in place with g * context_avg
-                        self.trained[q] += 1
-                for t in range(R):
-                    if have[t]:
-                        bq.issue(self.vslot[sl[t]])
-                bq.commit()
-                bq.wait_read(1)
-                for t in range(R):
-                    if prev[t] >= 0:
-                        self._release(prev[t])
-                    prev[t] = sl[t] if have[t] else -1
-                i0 += R * ncw
+                        if have[t]:
+                            assert s["state"] == "full" and s["row"] == (q, rows[t]), \
+                                "target row (%d,%d) not in slot %d: %s" % (q, rows[t], sl[t], s)
+                        else:  # re-read of a landed row of this position (gets g = 0)
+                            assert s["row"] == (q, ifall) and s["state"] in ("full", "update"), \
+                                "fallback row (%d,%d) not readable in slot %d: %s" % (q, ifall, sl[t], s)
+                    for t in range(R):
+                        if have[t]:
+                            self.vslot[sl[t]]["state"] = "update"   # overwritten in place with g * context_avg
+                            self.trained[q] += 1
+                    for t in range(R):
+                        if have[t]:
+                            u["bq"].issue(self.vslot[sl[t]])
+                    u["bq"].commit()
+                    u["bq"].wait_read(1)
+                    for t in range(R):
+                        if u["prev"][t] >= 0:
+                            self._release(u["prev"][t])
+                        u["prev"][t] = sl[t] if have[t] else -1
+                i0w += R * nunits
                 yield lambda: True  # a scheduling point between batches
-            bq.wait_read(0)
-            for t in range(R):
-                if prev[t] >= 0:
-                    self._release(prev[t])
-                prev[t] = -1
+            for u in units:
+                u["bq"].wait_read(0)
+                for t in range(R):
+                    if u["prev"][t] >= 0:
+                        self._release(u["prev"][t])
+                    u["prev"][t] = -1
             yield self._cta_barrier("B")
             if warp == 0:  # (thread-per-column in the kernel) partial sums -> staging row q & 1
                 eb = self.errbuf[q & 1]
@@ -255,7 +272,8 @@ class RingModel:
             if issuer:
                 pend = (d, q)
             q += 1
-        bq.wait_read(0)
+        for u in units:
+            u["bq"].wait_read(0)
         self.finished += 1
 
     def _release(self, sl):

@@ -103,3 +103,47 @@ def test_division_free_row_index_is_exact():
                     assert lib.w2b_host_ring_index(vs0, i, nv, G, C.byref(s), C.byref(g)) == 0
                     assert (s.value, g.value) == ((vs0 + i) % nv, i // G), (nv, G, vs0, i)
     assert lib.w2b_host_ring_index(5, 0, 5, 1, C.byref(s), C.byref(g)) != 0  # vs0 must be < nv
+
+
+@pytest.mark.parametrize("kernel", [2, 3, 4])
+def test_variant_geometries_are_live_and_safe(kernel):
+    """The experimental variants (cfg.kernel 2: same geometry as the default; 3 / 4: two / four row units per
+    consumer warp, which deepens the v-ring bound) through the same model."""
+    n = 0
+    for D in (8, 64, 100, 200, 256, 400, 512, 800):
+        for window in (2, 10, 32):
+            for negative in (0, 5, 12, 24, 40, 63):
+                p = w2b.ring_plan(size=D, window=window, negative=negative, kernel=kernel)
+                if not p["ring"]:
+                    continue
+                upw = p["units_per_warp"]
+                want = {2: 1, 3: 2 if D <= 512 else 1, 4: 4 if D <= 256 else 1}[kernel]
+                assert upw == want, (D, kernel, p)
+                nt, G, R, nunits = negative + 1, p["group"], p["rows_in_flight"], p["consumer_warps"] * upw
+                assert p["smem_bytes"] <= SMEM_LIMIT
+                assert p["v_rows"] >= nt or p["v_rows"] >= (2 * R - 1) * nunits + G + upw - 1, (D, window, negative, p)
+                n += 1
+                _check(p, window, negative, seeds=(n,), n=16)
+    assert n > 100
+    # bit levels other than 0/1/2 stay on the measured kernel
+    assert w2b.ring_plan(size=400, window=5, negative=5, bitlevel=5, kernel=3)["units_per_warp"] == 1
+
+
+def test_model_finds_the_unit_bound():
+    """Two row units per warp, positions longer than the ring: rings below (2R-1)*units + G rows dead-lock
+    in the model, the planner's choice and everything above that threshold is live."""
+    p = w2b.ring_plan(size=400, window=10, negative=63, kernel=3)
+    assert p["ring"] and p["units_per_warp"] == 2
+    nunits, G, R = p["consumer_warps"] * 2, p["group"], p["rows_in_flight"]
+    need = (2 * R - 1) * nunits + G
+    pos = [(20, 64)] * 6
+    for nv, ok in ((need - 1, False), (need, True), (need + 3, True)):
+        results = set()
+        for seed in range(12):
+            try:
+                RingModel(dict(p, v_rows=nv), 10, 63, pos, seed=seed).run()
+                results.add(True)
+            except (Deadlock, AssertionError):
+                results.add(False)
+        assert results == {ok}, (nv, need, results)
+    assert p["v_rows"] > need

@@ -48,7 +48,8 @@ class Accuracy(C.Structure):
 
 class RingPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ring", "group", "consumer_warps", "rows_in_flight", "u_rows", "v_rows",
-                                         "threads", "desc_depth", "max_groups")] + [("smem_bytes", C.c_int64)]
+                                         "threads", "desc_depth", "max_groups", "units_per_warp", "reserved")] + \
+               [("smem_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

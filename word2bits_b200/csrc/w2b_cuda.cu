@@ -105,6 +105,7 @@ struct w2b_ctx {
   int vec = 4, ncol = 0, threads = 0, group = 9;
   bool ring = false;       // production TMA-ring kernel usable for this configuration
   int ring_nu = 0, ring_nv = 0, ring_g = 13, ring_threads = 0;
+  int ring_lpr = 32;       // lanes per target row (32 = a warp per row; 16 / 8: cfg.kernel 3 / 4)
   size_t ring_smem = 0;
   int sm_count = 0;
   long long train_words = 0;
@@ -189,38 +190,44 @@ typedef void (*ring_fn)(TrainParams, int, int, int);
 // everywhere — R=3 at D=800 spills (a CTA with 9+ warps gets at most 168 registers per thread:
 // three warps share one SM sub-partition's 16K registers) and drops 5782 -> 4440 GB/s; R=4 at
 // D=400 costs the second CTA per SM (204 registers) and halves throughput.
-template <int BM, int OPT>
+template <int BM, int OPT, int LPR>
 static ring_fn ring_by_nj(int nj) {
   switch (nj) {
-    case 1: return train_ring_kernel<BM, 1, 2, OPT>;
-    case 2: return train_ring_kernel<BM, 2, 2, OPT>;
-    case 3: return train_ring_kernel<BM, 3, 2, OPT>;
-    case 4: return train_ring_kernel<BM, 4, 2, OPT>;
-    case 5: return train_ring_kernel<BM, 5, 2, OPT>;
-    case 6: return train_ring_kernel<BM, 6, 2, OPT>;
-    case 7: return train_ring_kernel<BM, 7, 2, OPT>;
-    case 8: return train_ring_kernel<BM, 8, 2, OPT>;
+    case 1: return train_ring_kernel<BM, 1, 2, OPT, LPR>;
+    case 2: return train_ring_kernel<BM, 2, 2, OPT, LPR>;
+    case 3: return train_ring_kernel<BM, 3, 2, OPT, LPR>;
+    case 4: return train_ring_kernel<BM, 4, 2, OPT, LPR>;
+    case 5: return train_ring_kernel<BM, 5, 2, OPT, LPR>;
+    case 6: return train_ring_kernel<BM, 6, 2, OPT, LPR>;
+    case 7: return train_ring_kernel<BM, 7, 2, OPT, LPR>;
+    case 8: return train_ring_kernel<BM, 8, 2, OPT, LPR>;
   }
   return nullptr;
 }
 static int ring_rows_in_flight(int) { return 2; }
-// cfg.kernel: 0 = the ring kernel measured in round 1, 2 = its OPT variant (same protocol, division-free
-// index arithmetic; bitlevel 0/1/2 only — other bit levels stay on the measured kernel), 1 = register kernel.
+// cfg.kernel: 0 = the ring kernel measured in round 1; 1 = register kernel; experimental variants of the
+// ring kernel (same protocol and arithmetic; bitlevel 0/1/2 only — other bit levels stay on kernel 0):
+// 2 = division-free index arithmetic (OPT), 3 / 4 = OPT + 16 / 8 lanes per target row for narrow rows.
+static int ring_lpr_of(const w2b_config &cfg, int ncol) {
+  const int bm = bm_of(cfg.bitlevel);
+  if (bm == 9) return 32;
+  if (cfg.kernel == 3 && (ncol + 15) / 16 <= 8) return 16;
+  if (cfg.kernel == 4 && (ncol + 7) / 8 <= 8) return 8;
+  return 32;
+}
+template <int BM>
+static ring_fn pick_ring_bm(int kernel, int lpr, int ncol) {
+  if (lpr == 16) return ring_by_nj<BM, 1, 16>((ncol + 15) / 16);
+  if (lpr == 8) return ring_by_nj<BM, 1, 8>((ncol + 7) / 8);
+  if (kernel >= 2) return ring_by_nj<BM, 1, 32>((ncol + 31) / 32);
+  return ring_by_nj<BM, 0, 32>((ncol + 31) / 32);
+}
 static ring_fn pick_ring(const w2b_ctx *c) {
-  const int nj = (c->ncol + 31) / 32;
-  if (c->cfg.kernel == 2) {
-    switch (bm_of(c->cfg.bitlevel)) {
-      case 0: return ring_by_nj<0, 1>(nj);
-      case 1: return ring_by_nj<1, 1>(nj);
-      case 2: return ring_by_nj<2, 1>(nj);
-      default: break;
-    }
-  }
   switch (bm_of(c->cfg.bitlevel)) {
-    case 0: return ring_by_nj<0, 0>(nj);
-    case 1: return ring_by_nj<1, 0>(nj);
-    case 2: return ring_by_nj<2, 0>(nj);
-    default: return ring_by_nj<9, 0>(nj);
+    case 0: return pick_ring_bm<0>(c->cfg.kernel, c->ring_lpr, c->ncol);
+    case 1: return pick_ring_bm<1>(c->cfg.kernel, c->ring_lpr, c->ncol);
+    case 2: return pick_ring_bm<2>(c->cfg.kernel, c->ring_lpr, c->ncol);
+    default: return ring_by_nj<9, 0, 32>((c->ncol + 31) / 32);
   }
 }
 
@@ -239,6 +246,9 @@ static void plan_ring(w2b_ctx *c) {
   // consumer warps: one per 128 columns, but at least 4 — the target phase deals whole rows to
   // warps, so narrow rows (D < 512) still get enough warps to walk 1+negative rows quickly
   const int ncw = std::max(nj, 4);
+  // row units: a warp per target row, or (experimental narrow-row variants) 2 / 4 units per warp
+  c->ring_lpr = ring_lpr_of(c->cfg, c->ncol);
+  const int upw = 32 / c->ring_lpr, nunits = ncw * upw;
   const long long D = c->cfg.layer1_size;
   // Small rows: aim for several CTAs per SM (more warps hide the per-row dependency chains);
   // k CTAs share the 227 KB (minus 1 KB reserved per CTA).  Take the largest k <= 4 whose
@@ -248,13 +258,15 @@ static void plan_ring(w2b_ctx *c) {
   const int R = ring_rows_in_flight(ncw);
   // ... unless the ring holds a whole position (nv >= 1+negative): then no row of a position can
   // wait for a slot of the same position, and everything older was confirmed at its position's end
-  const int nv_min = std::max(2 * G, std::min((2 * R - 1) * ncw + G + 1, nt));
+  // (with several units per warp the batch a unit waits for also holds its warp-mates' rows: + upw - 1)
+  const int nv_min = std::max(2 * G, std::min((2 * R - 1) * nunits + G + upw, nt));
   const int nv_good = std::max(nv_min, (5 * G + 1) / 2);
   int nu = 2 * c->cfg.window + 4;
   int nv = 0;
   for (int k = 4; k >= 1 && !nv; --k) {
     const size_t cap = (size_t)(227 * 1024) / k - 1024;
     int cand = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
+    if (upw > 1) cand = std::max(cand, nv_min);  // many row units: the bound can exceed four groups
     while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
     if (cand >= (k > 1 ? nv_good : nv_min)) nv = cand;
   }
@@ -262,6 +274,7 @@ static void plan_ring(w2b_ctx *c) {
     nu = 2 * c->cfg.window;
     const size_t cap = (size_t)(227 * 1024) - 1024;
     int cand = 4 * G;
+    if (upw > 1) cand = std::max(cand, nv_min);
     while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
     if (cand < nv_min) return;
     nv = cand;
@@ -391,6 +404,7 @@ extern "C" int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out) {
   out->threads = tmp.ring_threads;
   out->consumer_warps = tmp.ring_threads / 32 - 2;
   out->rows_in_flight = ring_rows_in_flight(out->consumer_warps);
+  out->units_per_warp = 32 / tmp.ring_lpr;
   out->desc_depth = kND;
   out->max_groups = kMaxGrp;
   out->smem_bytes = (int64_t)tmp.ring_smem;

@@ -172,12 +172,21 @@ __host__ __device__ inline void ring_row_index(unsigned vs0, unsigned i, unsigne
 // integer division (the signed / and % by run-time nv and G cost ~100 SASS instructions per 2-row batch in
 // front of the first row load), compile-time column offsets for all but the last float4 column group, and
 // running slot counters in the loader.  Kept as a variant until it has been measured on the GPU.
-template <int BM, int NJ, int R, int OPT = 0>
-__global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_kernel(TrainParams p, int nu, int nv, int G) {
+//
+// LPR (lanes per row, cfg.kernel = 3: 16, cfg.kernel = 4: 8; always with OPT = 1) is the narrow-row variant:
+// a warp is split into 32 / LPR row units that each own a target row of the batch, so one pass of the row
+// loop serves 2 (4) x R rows — the per-batch fixed costs (barrier waits, index arithmetic, shuffle tree,
+// expTable lookup, bulk-reduce issue) are shared by twice (four times) as many rows, the shuffle tree is one
+// (two) steps shorter, and D = 400 fills 100 of 112 lane slots instead of 100 of 128.  NJ counts float4
+// columns per lane: ceil(D / 4 / LPR).  Each unit's leader lane issues and confirms its own bulk reduces.
+template <int BM, int NJ, int R, int OPT = 0, int LPR = 32>
+__global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 31) / 32) + 2) * 32, LPR == 32 ? 1 : 2)
+    train_ring_kernel(TrainParams p, int nu, int nv, int G) {  // narrow-row variants: two CTAs per SM (<= 168 registers)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncw = (blockDim.x >> 5) - 2;  // consumer warps; then the loader warp, then the sampler warp
   const int nct = ncw * 32;
+  constexpr int UPW = 32 / LPR;  // row units per warp
   const RingLayout L = ring_layout(p.D, nu, nv, ncw);
   const unsigned s_base = smem_u32(smem);
   const unsigned uring = s_base + (unsigned)L.off_uring;
@@ -452,7 +461,12 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
     qp.bits = p.bitlevel;
     qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
     double loss = 0.0;                 // warp 0: one lane per target
-    int prev[R];                       // lane 0: slots whose reduce is committed but not yet confirmed read
+    // row units: LPR lanes that own one target row of a batch (the whole warp when LPR == 32)
+    const int sub = (LPR == 32) ? 0 : lane / LPR;
+    const int ul = (LPR == 32) ? lane : lane % LPR;  // lane within its unit
+    const int nunits = ncw * UPW;
+    const bool leader = ul == 0;       // issues and confirms the unit's bulk reduces
+    int prev[R];                       // leader: slots whose reduce is committed but not yet confirmed read
 #pragma unroll
     for (int t = 0; t < R; ++t) prev[t] = -1;
     const bool issuer = (warp == ncw - 1) && lane == 0;  // the last warp has the fewest rows: it scatters u
@@ -464,12 +478,12 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
     unsigned coff[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = j * 32 + lane;
+      const int c = j * LPR + ul;
       if (OPT && j < NJ - 1) {
-        // NJ == ceil(D4 / 32) (pick_ring): every column group but the last is full, so its lanes are always
-        // on and its byte offset is lane * 16 + a compile-time constant (an LDS/STS immediate)
+        // NJ == ceil(D4 / LPR) (pick_ring): every column group but the last is full, so its lanes are always
+        // on and its byte offset is ul * 16 + a compile-time constant (an LDS/STS immediate)
         on[j] = true;
-        coff[j] = (unsigned)lane * 16u + (unsigned)j * 512u;
+        coff[j] = (unsigned)ul * 16u + (unsigned)j * (unsigned)(LPR * 16);
       } else {
         on[j] = c < D4;
         coff[j] = (unsigned)(on[j] ? c : D4 - 1) * 16u;
@@ -522,21 +536,25 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
 #pragma unroll
       for (int j = 0; j < NJ; ++j) e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       float *sf = ctl->sf[q & 1];
-      for (int i0 = warp; i0 < nt; i0 += R * ncw) {
-        // rows i0, i0+ncw, ... of this warp; a missing row re-reads row i0 and gets g = 0
+      for (int i0w = warp * UPW; i0w < nt; i0w += R * nunits) {
+        // rows i0, i0+nunits, ... of this unit; a missing row re-reads a landed row and gets g = 0
+        const int i0 = i0w + sub;
+        // LPR < 32: a unit may have no row at all in the warp's last batch; it then re-reads the row of the
+        // warp's first unit (i0w < nt) and, like every lane, waits for that row's barrier before touching it
+        const int ifall = (LPR == 32) ? i0 : (i0 < nt ? i0 : i0w);
         int sl[R];
         unsigned row[R];
         bool have[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) {
-          const int i = i0 + t * ncw;
+          const int i = i0 + t * nunits;
           have[t] = i < nt;
-          const int ii = have[t] ? i : i0;
+          const int ii = have[t] ? i : ifall;
           int s;
           if constexpr (OPT) {
             unsigned us, ug;
             ring_row_index((unsigned)vs0, (unsigned)ii, (unsigned)nv, nv_magic, g_magic, &us, &ug);
-            if (have[t]) mbar_wait(vbar0 + ((unsigned)slot * kMaxGrp + ug) * 8u, par);
+            if (have[t] || LPR < 32) mbar_wait(vbar0 + ((unsigned)slot * kMaxGrp + ug) * 8u, par);
             s = (int)us;
           } else {
             if (have[t]) mbar_wait(vbar0 + (slot * kMaxGrp + ii / G) * 8, par);
@@ -573,15 +591,15 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
           for (int t = 0; t < R; ++t) f[t] = (d0[t] + d1[t]) + (d2[t] + d3[t]);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)  // R interleaved butterflies: every lane ends with the full sums
+        for (int o = LPR / 2; o > 0; o >>= 1)  // R interleaved butterflies: every lane of a unit ends with the full sums
 #pragma unroll
           for (int t = 0; t < R; ++t) f[t] += __shfl_xor_sync(kFull, f[t], o);
         float g[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) {
-          const int i = i0 + t * ncw;
+          const int i = i0 + t * nunits;
           g[t] = have[t] ? grad_scalar(f[t], i == 0 ? 1 : 0, alpha, p.exptab) : 0.f;
-          if (lane == 0 && have[t]) sf[i] = (i == 0) ? f[t] : -f[t];
+          if (leader && have[t]) sf[i] = (i == 0) ? f[t] : -f[t];
         }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -598,10 +616,10 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (leader) {
 #pragma unroll
           for (int t = 0; t < R; ++t)
-            if (have[t]) bulk_reduce_add(p.v + (long long)d->tg[i0 + t * ncw] * p.D, row[t], rowb);
+            if (have[t]) bulk_reduce_add(p.v + (long long)d->tg[i0 + t * nunits] * p.D, row[t], rowb);
           bulk_commit();
           if (p.serial) bulk_wait_all(); else bulk_wait_read<1>();
           // everything this lane committed before the group above has left shared memory
@@ -614,7 +632,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
         }
         __syncwarp();
       }
-      if (lane == 0) {  // confirm this warp's last rows (and, for the issuer, the u scatter) right away
+      if (leader) {  // confirm this unit's last rows (and, for the issuer, the u scatter) right away
         bulk_wait_read<0>();
 #pragma unroll
         for (int t = 0; t < R; ++t) {
@@ -623,9 +641,20 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
         }
       }
       // ---- error partials -> staging row (its scatter, :494-503, is issued after the next barrier A)
+      if constexpr (LPR < 32) {  // the row units of a warp hold partials of the same columns: add them up first
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            e[j].x += __shfl_xor_sync(kFull, e[j].x, o);
+            e[j].y += __shfl_xor_sync(kFull, e[j].y, o);
+            e[j].z += __shfl_xor_sync(kFull, e[j].z, o);
+            e[j].w += __shfl_xor_sync(kFull, e[j].w, o);
+          }
+      }
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
-        if (on[j]) sts128(s_errp + (unsigned)warp * rowb + coff[j], e[j]);
+        if (on[j] && (LPR == 32 || sub == 0)) sts128(s_errp + (unsigned)warp * rowb + coff[j], e[j]);
       consumer_bar(nct);  // B
       if (col_on) {
         float4 acc = lds128(s_errp + colb);
@@ -652,7 +681,7 @@ __global__ void __launch_bounds__(((NJ < 4 ? 4 : NJ) + 2) * 32, 1) train_ring_ke
         }
       }
     }
-    if (lane == 0) bulk_wait_all();
+    if (leader) bulk_wait_all();
     if (warp == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
