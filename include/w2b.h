@@ -76,6 +76,14 @@ int w2b_host_exptable(float *out /* 1000 */);
 int w2b_host_keep_thresholds(const int64_t *cn, int64_t V, int64_t train_words, float sample, float *out /* V */);
 int w2b_host_lcg_tables(uint64_t *ja /*65*/, uint64_t *jc /*65*/, uint64_t *pa /*64*/, uint64_t *pc /*64*/);
 
+/* The host half of a streaming step (w2b_set_corpus resident = 0): the next L tokens of every unfinished shard are
+ * gathered into one pinned staging buffer (slice i at stage[i*L]) by a few host threads before the single H2D copy.
+ * xlate[i] = global token index - staging index, limit[i] = global end of the slice, limit_is_eof[i] = slice reaches
+ * the end of the stream.  Outputs of finished shards are left untouched.  nthreads <= 0: chosen from the size. */
+int w2b_host_gather_slices(const int32_t *ids, int64_t n_tokens, int64_t L, int nshards, const int64_t *cursor,
+                           const int32_t *done, int32_t *stage /* nshards*L */, int64_t *xlate, int64_t *limit,
+                           int32_t *limit_is_eof, int nthreads);
+
 /* ------------------------------------------------------------------------ device path */
 typedef struct w2b_ctx w2b_ctx;
 

@@ -251,3 +251,38 @@ def test_null_arguments_are_errors_not_crashes():
     with pytest.raises(w2b.W2BError) as e:
         w2b.Corpus(os.path.join(ROOT, "tests"), 1)  # a directory is not a training file
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("nthreads", [1, 2, 3, 8, 0])
+def test_streaming_slice_gather(nthreads):
+    """The host half of a streaming step (w2b_train_step with host token buffers): every unfinished shard's next L
+    tokens land in its slice of the staging buffer whatever the number of host threads; finished shards are skipped;
+    a pending override token (cursor -1) starts the slice at 0; the last slice is clipped at the end of the stream."""
+    import ctypes as C
+    from word2bits_b200._lib import lib, ptr
+    rng = np.random.default_rng(9)
+    n, S, L = 3_000_000, 37, 70_000
+    ids = rng.integers(0, 1 << 20, n).astype(np.int32)
+    cursor = np.sort(rng.integers(0, n, S)).astype(np.int64)
+    cursor[0] = -1
+    cursor[-1] = n - 1234          # clipped at EOF
+    cursor[-2] = n                 # nothing left to read
+    done = np.zeros(S, np.int32)
+    done[5] = done[20] = 1
+    stage = np.full(S * L, -7, np.int32)
+    xl = np.full(S, -99, np.int64); lim = np.full(S, -99, np.int64); eof = np.full(S, -99, np.int32)
+    assert lib.w2b_host_gather_slices(ptr(ids), n, L, S, ptr(cursor), ptr(done), ptr(stage), ptr(xl), ptr(lim), ptr(eof),
+                                      nthreads) == 0
+    for i in range(S):
+        sl = stage[i * L:(i + 1) * L]
+        if done[i]:
+            assert (sl == -7).all() and (xl[i], lim[i], eof[i]) == (-99, -99, -99)
+            continue
+        b = max(int(cursor[i]), 0)
+        e = min(b + L, n)
+        assert np.array_equal(sl[:e - b], ids[b:e]) and (sl[e - b:] == -7).all()
+        assert (xl[i], lim[i], eof[i]) == (b - i * L, e, int(e == n))
+        # the kernel reads token g at staging index g - xlate
+        if e > b:
+            assert stage[b - xl[i]] == ids[b]
+    assert lib.w2b_host_gather_slices(None, n, L, S, ptr(cursor), ptr(done), ptr(stage), ptr(xl), ptr(lim), ptr(eof), 1) != 0

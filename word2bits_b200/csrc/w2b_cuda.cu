@@ -640,15 +640,18 @@ static int stage_slices(w2b_ctx *c, long long want, w2b_step_stats *acc) {
     c->stage_cap = need;
   }
   c->stage_len = L;
-  for (int i = 0; i < c->nlocal; ++i) {
-    ShardState &s = c->h_shards[i];
-    if (s.done) continue;
-    long long b = std::max<long long>(s.cursor, 0);  // cursor -1 = pending override token
-    long long e = std::min<long long>(b + L, c->n_tokens);
-    if (e > b) memcpy(c->h_stage + (long long)i * L, c->h_ids + b, (e - b) * sizeof(int));
-    s.xlate = b - (long long)i * L;
-    s.limit = e;
-    s.limit_is_eof = (e == c->n_tokens);
+  {  // gather every unfinished shard's next L tokens (host threads: w2b_gather_slices, tested on the CPU)
+    std::vector<long long> cursor(c->nlocal), xlate(c->nlocal), limit(c->nlocal);
+    std::vector<int> done(c->nlocal), eof(c->nlocal);
+    for (int i = 0; i < c->nlocal; ++i) { cursor[i] = c->h_shards[i].cursor; done[i] = c->h_shards[i].done; }
+    w2b_gather_slices(c->h_ids, c->n_tokens, L, c->nlocal, cursor.data(), done.data(), c->h_stage, xlate.data(),
+                      limit.data(), eof.data(), 0);
+    for (int i = 0; i < c->nlocal; ++i) {
+      if (done[i]) continue;
+      c->h_shards[i].xlate = xlate[i];
+      c->h_shards[i].limit = limit[i];
+      c->h_shards[i].limit_is_eof = eof[i];
+    }
   }
   CK(cudaMemcpyAsync(c->d_tokens, c->h_stage, need * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice,

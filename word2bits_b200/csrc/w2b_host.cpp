@@ -75,6 +75,56 @@ extern "C" int w2b_host_keep_thresholds(const int64_t *cn, int64_t V, int64_t tr
   return W2B_OK;
 }
 
+void w2b_gather_slices(const int32_t *ids, long long n_tokens, long long L, int nshards, const long long *cursor,
+                       const int *done, int32_t *stage, long long *xlate, long long *limit, int *limit_is_eof,
+                       int nthreads) {
+  auto gather = [=](int lo, int hi) {  // shard i only touches its own outputs and its own slice of the staging buffer
+    for (int i = lo; i < hi; ++i) {
+      if (done[i]) continue;
+      const long long b = std::max<long long>(cursor[i], 0);  // cursor -1 = pending override token
+      const long long e = std::min<long long>(b + L, n_tokens);
+      if (e > b) memcpy(stage + (long long)i * L, ids + b, (size_t)(e - b) * sizeof(int32_t));
+      xlate[i] = b - (long long)i * L;
+      limit[i] = e;
+      limit_is_eof[i] = (e == n_tokens);
+    }
+  };
+  if (nthreads <= 0) {  // >= 1 M tokens per thread, at most 8 threads / half the host / one per shard
+    const long long by_size = L * nshards / (1 << 20);
+    const long long by_host = std::max(1u, std::thread::hardware_concurrency() / 2);
+    nthreads = (int)std::min<long long>(std::min<long long>(8, by_host), std::min<long long>(nshards, by_size));
+  }
+  nthreads = std::min(nthreads, nshards);
+  if (nthreads <= 1) {
+    gather(0, nshards);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t)
+    th.emplace_back(gather, (int)((long long)nshards * t / nthreads), (int)((long long)nshards * (t + 1) / nthreads));
+  gather(0, (int)((long long)nshards / nthreads));
+  for (auto &x : th) x.join();
+}
+
+extern "C" int w2b_host_gather_slices(const int32_t *ids, int64_t n_tokens, int64_t L, int nshards, const int64_t *cursor,
+                                      const int32_t *done, int32_t *stage, int64_t *xlate, int64_t *limit,
+                                      int32_t *limit_is_eof, int nthreads) {
+  if (!ids || !cursor || !done || !stage || !xlate || !limit || !limit_is_eof || L < 1 || nshards < 1 || n_tokens < 0) {
+    w2b_set_error("w2b_host_gather_slices: bad argument");
+    return W2B_EINVAL;
+  }
+  std::vector<long long> cur(cursor, cursor + nshards), xl(nshards, 0), lim(nshards, 0);
+  std::vector<int> dn(done, done + nshards), eof(nshards, 0);
+  w2b_gather_slices(ids, n_tokens, L, nshards, cur.data(), dn.data(), stage, xl.data(), lim.data(), eof.data(), nthreads);
+  for (int i = 0; i < nshards; ++i) {
+    if (dn[i]) continue;
+    xlate[i] = xl[i];
+    limit[i] = lim[i];
+    limit_is_eof[i] = eof[i];
+  }
+  return W2B_OK;
+}
+
 // ----------------------------------------------------------------------------- tokeniser
 namespace {
 

@@ -11,3 +11,9 @@ void w2b_unigram_bounds(const int64_t *cn, int64_t V, int32_t *start);
 void w2b_exptable(float *out /*1000*/);
 // Sub-sampling thresholds `ran` (:403-404), float32.
 void w2b_keep_thresholds(const int64_t *cn, int64_t V, int64_t train_words, float sample, float *out /*V*/);
+// Streaming mode: copy tokens [max(cursor,0), +L) of every unfinished shard into its slice stage[i*L ..) and
+// report where the slice sits (xlate = global index - staging index, limit = global end, eof flag).  A plain
+// memcpy of tens of MB per step, spread over a few host threads (nthreads <= 0: pick from the size).
+void w2b_gather_slices(const int32_t *ids, long long n_tokens, long long L, int nshards, const long long *cursor,
+                       const int *done, int32_t *stage, long long *xlate, long long *limit, int *limit_is_eof,
+                       int nthreads);
