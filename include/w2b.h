@@ -106,7 +106,8 @@ typedef struct {
   int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
   int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel,
                           experimental variants of the ring kernel: 2 = division-free index arithmetic,
-                          3 / 4 = 2 + 16 / 8 lanes per target row (narrow rows, D <= 512 / 256) */
+                          3 / 4 = 2 + 16 / 8 lanes per target row (narrow rows, D <= 512 / 256),
+                          5 = 2 + two more consumer warps (wide rows, D > 512) */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
   int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed */
 } w2b_config;

@@ -1,5 +1,6 @@
 """GPU tests of the experimental variants of the production kernel (word2bits_b200/csrc/w2b_ring.cuh):
-cfg.kernel = 2 (division-free index arithmetic), 3 and 4 (2 + 16 / 8 lanes per target row for narrow rows).
+cfg.kernel = 2 (division-free index arithmetic), 3 and 4 (2 + 16 / 8 lanes per target row for narrow rows), 5 (2 + two
+more consumer warps for wide rows).
 They were written at the end of round 1 with no GPU time left, so these tests are opt-in until the variants
 have been run once:  W2B_TEST_EXPERIMENTAL=1 python -m pytest -m gpu tests/test_gpu_variant.py.  Same bars as
 the default kernel (tests/test_gpu_parity.py), plus equality of everything that is integer (draw trace,
@@ -16,7 +17,7 @@ from tests.util import bits, zipf_corpus
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("W2B_TEST_EXPERIMENTAL") != "1",
                                  reason="experimental kernel variants not yet run on a GPU: set W2B_TEST_EXPERIMENTAL=1")]
-VARIANTS = [2, 3, 4]
+VARIANTS = [2, 3, 4, 5]
 
 w2b = pytest.importorskip("word2bits_b200")
 
@@ -80,7 +81,7 @@ def test_variant_serial_single_shard_equals_default(variant, b, D, medium):
         lg, st = t.train_epoch()
         out.append((lg, t.download_raw()))
         t.close()
-    same_order = variant == 2 or w2b.ring_plan(size=D, window=5, negative=6, bitlevel=b, kernel=variant)["units_per_warp"] == 1
+    same_order = variant in (2, 5) or w2b.ring_plan(size=D, window=5, negative=6, bitlevel=b, kernel=variant)["units_per_warp"] == 1
     if same_order:
         assert out[0][0] == out[1][0]
         assert np.array_equal(bits(out[0][1][0]), bits(out[1][1][0])) and np.array_equal(bits(out[0][1][1]), bits(out[1][1][1]))

@@ -105,7 +105,7 @@ def test_division_free_row_index_is_exact():
     assert lib.w2b_host_ring_index(5, 0, 5, 1, C.byref(s), C.byref(g)) != 0  # vs0 must be < nv
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4])
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5])
 def test_variant_geometries_are_live_and_safe(kernel):
     """The experimental variants (cfg.kernel 2: same geometry as the default; 3 / 4: two / four row units per
     consumer warp, which deepens the v-ring bound) through the same model."""
@@ -117,8 +117,11 @@ def test_variant_geometries_are_live_and_safe(kernel):
                 if not p["ring"]:
                     continue
                 upw = p["units_per_warp"]
-                want = {2: 1, 3: 2 if D <= 512 else 1, 4: 4 if D <= 256 else 1}[kernel]
+                want = {2: 1, 3: 2 if D <= 512 else 1, 4: 4 if D <= 256 else 1, 5: 1}[kernel]
                 assert upw == want, (D, kernel, p)
+                base = w2b.ring_plan(size=D, window=window, negative=negative)
+                if base["ring"]:
+                    assert p["consumer_warps"] == base["consumer_warps"] + (2 if kernel == 5 and D > 512 else 0)
                 nt, G, R, nunits = negative + 1, p["group"], p["rows_in_flight"], p["consumer_warps"] * upw
                 assert p["smem_bytes"] <= SMEM_LIMIT
                 assert p["v_rows"] >= nt or p["v_rows"] >= (2 * R - 1) * nunits + G + upw - 1, (D, window, negative, p)

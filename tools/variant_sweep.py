@@ -1,5 +1,5 @@
 """A/B of the ring kernel variants on one GPU (CUDA events, inputs resident; not the bench):
-    python tools/variant_sweep.py [--out gpurun_out/variants.md] [--shapes c2,c3,c4,d200,d100] [--kernels 0,2,3,4]
+    python tools/variant_sweep.py [--out gpurun_out/variants.md] [--shapes c2,c3,c4,d200,d100] [--kernels 0,2,3,4,5]
 For every BASELINE-shaped configuration and every cfg.kernel value: positions/s, algorithmic GB/s, fraction of the
 measured HBM peak, shards (CTAs) used, and the loss per position as a sanity check that the variant trains the same
 thing.  Suggested first GPU call of a round:
@@ -31,7 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/variants.md")
     ap.add_argument("--shapes", default="c2,c3,c4,d200,d100")
-    ap.add_argument("--kernels", default="0,2,3,4")
+    ap.add_argument("--kernels", default="0,2,3,4,5")
     ap.add_argument("--vocab", type=int, default=400000)
     ap.add_argument("--tokens", type=int, default=40_000_000)
     ap.add_argument("--words", type=int, default=16384)
@@ -46,7 +46,8 @@ def main():
         for kernel in [int(k) for k in a.kernels.split(",")]:
             plan = w2b.ring_plan(size=D, window=W, negative=neg, bitlevel=b, kernel=kernel, vocab_size=a.vocab + 1)
             lpr = 32 // max(plan["units_per_warp"], 1)
-            if kernel >= 3 and lpr == 32:
+            base = w2b.ring_plan(size=D, window=W, negative=neg, bitlevel=b, kernel=2, vocab_size=a.vocab + 1)
+            if kernel >= 3 and (lpr, plan["consumer_warps"]) == (32, base["consumer_warps"]):
                 continue  # variant does not apply to this width: it would repeat kernel 2
             t = w2b.Trainer(None, vocab_size=a.vocab + 1, size=D, window=W, negative=neg, bitlevel=b, iter=1, threads=None,
                             kernel=kernel)

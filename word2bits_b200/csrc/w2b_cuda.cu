@@ -106,6 +106,7 @@ struct w2b_ctx {
   bool ring = false;       // production TMA-ring kernel usable for this configuration
   int ring_nu = 0, ring_nv = 0, ring_g = 13, ring_threads = 0;
   int ring_lpr = 32;       // lanes per target row (32 = a warp per row; 16 / 8: cfg.kernel 3 / 4)
+  int ring_xw = 0;         // consumer warps beyond one per 128 columns (cfg.kernel 5: 2)
   size_t ring_smem = 0;
   int sm_count = 0;
   long long train_words = 0;
@@ -207,7 +208,8 @@ static ring_fn ring_by_nj(int nj) {
 static int ring_rows_in_flight(int) { return 2; }
 // cfg.kernel: 0 = the ring kernel measured in round 1; 1 = register kernel; experimental variants of the
 // ring kernel (same protocol and arithmetic; bitlevel 0/1/2 only — other bit levels stay on kernel 0):
-// 2 = division-free index arithmetic (OPT), 3 / 4 = OPT + 16 / 8 lanes per target row for narrow rows.
+// 2 = division-free index arithmetic (OPT), 3 / 4 = OPT + 16 / 8 lanes per target row for narrow rows,
+// 5 = OPT + two more consumer warps for wide rows (D > 512).
 static int ring_lpr_of(const w2b_config &cfg, int ncol) {
   const int bm = bm_of(cfg.bitlevel);
   if (bm == 9) return 32;
@@ -216,7 +218,21 @@ static int ring_lpr_of(const w2b_config &cfg, int ncol) {
   return 32;
 }
 template <int BM>
+static ring_fn ring_xw2(int nj) {  // wide rows only (narrow rows have the lanes-per-row variants)
+  switch (nj) {
+    case 5: return train_ring_kernel<BM, 5, 2, 1, 32, 2>;
+    case 6: return train_ring_kernel<BM, 6, 2, 1, 32, 2>;
+    case 7: return train_ring_kernel<BM, 7, 2, 1, 32, 2>;
+    case 8: return train_ring_kernel<BM, 8, 2, 1, 32, 2>;
+  }
+  return nullptr;
+}
+static int ring_xw_of(const w2b_config &cfg, int ncol) {
+  return (cfg.kernel == 5 && bm_of(cfg.bitlevel) != 9 && (ncol + 31) / 32 >= 5) ? 2 : 0;
+}
+template <int BM>
 static ring_fn pick_ring_bm(int kernel, int lpr, int ncol) {
+  if (kernel == 5 && (ncol + 31) / 32 >= 5) return ring_xw2<BM>((ncol + 31) / 32);
   if (lpr == 16) return ring_by_nj<BM, 1, 16>((ncol + 15) / 16);
   if (lpr == 8) return ring_by_nj<BM, 1, 8>((ncol + 7) / 8);
   if (kernel >= 2) return ring_by_nj<BM, 1, 32>((ncol + 31) / 32);
@@ -245,7 +261,8 @@ static void plan_ring(w2b_ctx *c) {
   if (nj > 8) return;  // kernels are instantiated for D <= 1024
   // consumer warps: one per 128 columns, but at least 4 — the target phase deals whole rows to
   // warps, so narrow rows (D < 512) still get enough warps to walk 1+negative rows quickly
-  const int ncw = std::max(nj, 4);
+  c->ring_xw = ring_xw_of(c->cfg, c->ncol);
+  const int ncw = std::max(nj, 4) + c->ring_xw;
   // row units: a warp per target row, or (experimental narrow-row variants) 2 / 4 units per warp
   c->ring_lpr = ring_lpr_of(c->cfg, c->ncol);
   const int upw = 32 / c->ring_lpr, nunits = ncw * upw;

@@ -179,8 +179,12 @@ __host__ __device__ inline void ring_row_index(unsigned vs0, unsigned i, unsigne
 // expTable lookup, bulk-reduce issue) are shared by twice (four times) as many rows, the shuffle tree is one
 // (two) steps shorter, and D = 400 fills 100 of 112 lane slots instead of 100 of 128.  NJ counts float4
 // columns per lane: ceil(D / 4 / LPR).  Each unit's leader lane issues and confirms its own bulk reduces.
-template <int BM, int NJ, int R, int OPT = 0, int LPR = 32>
-__global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 31) / 32) + 2) * 32, LPR == 32 ? 1 : 2)
+//
+// XW (cfg.kernel = 5: 2, with OPT = 1) adds consumer warps beyond one per 128 columns: ncu shows the measured
+// kernel stalled on fixed-latency dependencies with 2.25 warps per scheduler; at D = 800 the register file holds
+// 11 warps of this kernel, and 25 target rows over 9 warps need a 2 + 1-row second pass instead of 2 + 2.
+template <int BM, int NJ, int R, int OPT = 0, int LPR = 32, int XW = 0>
+__global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 31) / 32) + 2 + XW) * 32, LPR == 32 ? 1 : 2)
     train_ring_kernel(TrainParams p, int nu, int nv, int G) {  // narrow-row variants: two CTAs per SM (<= 168 registers)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
