@@ -17,7 +17,7 @@ from tests.util import bits, zipf_corpus
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("W2B_TEST_EXPERIMENTAL") != "1",
                                  reason="experimental kernel variants not yet run on a GPU: set W2B_TEST_EXPERIMENTAL=1")]
-VARIANTS = [2, 3, 4, 5]
+VARIANTS = [int(v) for v in os.environ.get("W2B_VARIANTS", "2,3,4,5").split(",")]  # subset per run
 
 w2b = pytest.importorskip("word2bits_b200")
 
