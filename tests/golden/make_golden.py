@@ -18,6 +18,7 @@ CASES = [  # D, W, neg, bits, shards, min_count, sample, reg, iters
     (8, 3, 4, 0, 1, 1, 1e-3, 0.0, 2),
     (8, 3, 4, 5, 3, 2, 1e-2, 0.0, 1),
     (8, 3, 4, 1, 2, 1, 1e-3, 0.01, 1),
+    (200, 8, 24, 1, 1, 1, 1e-3, 0.0, 1),   # BASELINE.json configs[0] shape (bitlevel 1, size 200, window 8, negative 24, 1 thread)
 ]
 
 

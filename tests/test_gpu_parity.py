@@ -153,7 +153,7 @@ def test_strict_trajectory_bit_exact(case, small, medium):
     assert np.array_equal(bits(t.export()), bits(m.export()))
 
 
-@pytest.mark.parametrize("k", range(5))
+@pytest.mark.parametrize("k", range(6))
 def test_strict_vs_reference_golden(k):
     """Straight against vectors produced by the unmodified reference (tests/golden)."""
     gold = np.load(os.path.join(G, "reference_strict.npz"))

@@ -54,7 +54,7 @@ def test_init_and_table(gold):
     assert np.array_equal(t[s[:-1]], np.arange(c.vocab_size)) and np.array_equal(t[s[1:] - 1], np.arange(c.vocab_size))
 
 
-@pytest.mark.parametrize("k", range(5))
+@pytest.mark.parametrize("k", range(6))
 def test_trajectories(gold, k):
     D, W, neg, b, shards, mc, iters = [int(x) for x in gold["case%d_cfg" % k]]
     sample, reg = [float(x) for x in gold["case%d_fcfg" % k]]
