@@ -13,8 +13,10 @@
 #include <unistd.h>
 
 #include <algorithm>
-#include <numeric>
+#include <atomic>
 #include <chrono>
+#include <functional>
+#include <numeric>
 #include <string>
 #include <thread>
 #include <vector>
@@ -166,50 +168,79 @@ inline uint64_t hash_bytes(const char *s, int len) {
   return h;
 }
 
+// Open-addressing word table.  A slot holds (upper 32 hash bits << 32 | entry + 1), so a probe touches the
+// entry / the string only when the tag matches; entries keep their hash (no re-hash on growth or merge).
 struct WordMap {
-  std::vector<uint32_t> slot;   // entry index + 1, 0 = empty
-  std::vector<uint64_t> off;    // arena offset per entry
-  std::vector<uint32_t> wlen;
-  std::vector<int64_t> count;
+  struct Entry {  // 32 bytes: a hit on a short word touches one cache line besides the slot
+    uint64_t hash;
+    int64_t count;
+    uint32_t len;
+    uint32_t aux;
+    union {
+      char inl[8];   // len <= 7: the NUL-terminated string itself
+      uint64_t off;  // longer: arena offset of the NUL-terminated string
+    };
+  };
+  std::vector<uint64_t> slot;
+  std::vector<Entry> ent;
   std::string arena;
   uint64_t mask = 0;
 
-  WordMap() { slot.assign(1u << 16, 0); mask = slot.size() - 1; }
-  const char *str(uint32_t e) const { return arena.data() + off[e]; }
+  WordMap() { slot.assign(1u << 12, 0); mask = slot.size() - 1; }
+  size_t size() const { return ent.size(); }
+  const char *str(uint32_t e) const { return ent[e].len <= 7 ? ent[e].inl : arena.data() + ent[e].off; }
+  void prefetch_slot(uint64_t h) const { __builtin_prefetch(&slot[h & mask]); }
+  void prefetch_entry(uint64_t h) const {  // second stage: the entry the first slot of the probe points at
+    const uint64_t sv = slot[h & mask];
+    if (sv) __builtin_prefetch(&ent[(uint32_t)sv - 1]);
+  }
   void grow() {
-    std::vector<uint32_t> ns(slot.size() * 2, 0);
+    std::vector<uint64_t> ns(slot.size() * 2, 0);
     const uint64_t m = ns.size() - 1;
-    for (uint32_t e = 0; e < off.size(); ++e) {
-      uint64_t h = hash_bytes(str(e), (int)wlen[e]) & m;
-      while (ns[h]) h = (h + 1) & m;
-      ns[h] = e + 1;
+    for (uint32_t e = 0; e < ent.size(); ++e) {
+      uint64_t i = ent[e].hash & m;
+      while (ns[i]) i = (i + 1) & m;
+      ns[i] = (ent[e].hash & 0xffffffff00000000ULL) | (uint64_t)(e + 1);
     }
     slot.swap(ns);
     mask = m;
   }
-  int64_t find(const char *w, int len) const {
-    uint64_t h = hash_bytes(w, len) & mask;
-    while (slot[h]) {
-      const uint32_t e = slot[h] - 1;
-      if ((int)wlen[e] == len && !memcmp(str(e), w, len)) return e;
-      h = (h + 1) & mask;
+  int64_t find(const char *w, int len, uint64_t h) const {
+    const uint64_t tag = h & 0xffffffff00000000ULL;
+    for (uint64_t i = h & mask; slot[i]; i = (i + 1) & mask) {
+      if ((slot[i] & 0xffffffff00000000ULL) != tag) continue;
+      const uint32_t e = (uint32_t)slot[i] - 1;
+      if ((int)ent[e].len == len && !memcmp(str(e), w, len)) return e;
     }
     return -1;
   }
-  uint32_t insert(const char *w, int len) {
-    if ((off.size() + 1) * 2 > slot.size()) grow();
-    const uint32_t e = (uint32_t)off.size();
-    off.push_back(arena.size());
-    wlen.push_back((uint32_t)len);
-    count.push_back(0);
-    arena.append(w, len);
-    arena.push_back('\0');
-    uint64_t h = hash_bytes(w, len) & mask;
-    while (slot[h]) h = (h + 1) & mask;
-    slot[h] = e + 1;
+  int64_t find(const char *w, int len) const { return find(w, len, hash_bytes(w, len)); }
+  uint32_t insert(const char *w, int len, uint64_t h) {
+    if ((ent.size() + 1) * 2 > slot.size()) grow();
+    const uint32_t e = (uint32_t)ent.size();
+    Entry ne;
+    ne.hash = h;
+    ne.count = 0;
+    ne.len = (uint32_t)len;
+    ne.aux = 0;
+    if (len <= 7) {
+      memset(ne.inl, 0, sizeof ne.inl);
+      memcpy(ne.inl, w, len);
+    } else {
+      ne.off = arena.size();
+      arena.append(w, len);
+      arena.push_back('\0');
+    }
+    ent.push_back(ne);
+    uint64_t i = h & mask;
+    while (slot[i]) i = (i + 1) & mask;
+    slot[i] = (h & 0xffffffff00000000ULL) | (uint64_t)(e + 1);
     return e;
   }
 };
+
+constexpr int kParts = 64;  // merge partitions (by the top hash bits)
+inline int part_of(uint64_t h) { return (int)(h >> 58); }
 
 }  // namespace
 
@@ -217,15 +248,27 @@ struct w2b_corpus {
   const uint8_t *buf = nullptr;
   int64_t file_size = 0;
   int fd = -1;
-  WordMap map;
-  std::vector<int32_t> final_id;  // map entry -> vocab id or -1
+  // vocabulary lookup after loading: kParts tables over all distinct words of the file
+  std::vector<WordMap> parts;
+  std::vector<std::vector<int32_t>> part_final;  // [partition][entry] -> vocab id or -1
+  std::string eos_storage;
   std::vector<const char *> words;
   std::vector<int64_t> cn;
   int64_t train_words = 0;
   std::vector<int32_t> ids;
   // every kCkptEvery raw tokens: byte offset of the token and #in-vocab tokens before it
   std::vector<int64_t> ck_begin, ck_comp;
+
+  int32_t lookup(const char *w, int len) const {  // vocab id of a word, -1 if absent / below min_count
+    if (parts.empty()) return -1;
+    const uint64_t h = hash_bytes(w, len);
+    const int p = part_of(h);
+    const int64_t e = parts[p].find(w, len, h);
+    return e < 0 ? -1 : part_final[p][(size_t)e];
+  }
 };
+
+namespace {
 
 // Pass 1 over one chunk [begin, end) of the mapped file: chunk-local vocabulary in first-appearance
 // order + the chunk's tokens as local ids.  Chunks start right after a whitespace byte, so the
@@ -234,21 +277,110 @@ struct ChunkResult {
   WordMap map;
   std::vector<uint32_t> raw;        // local entry id per token
   std::vector<int64_t> ck_begin;    // byte offset of every kCkptEvery-th token of the chunk
+  std::vector<uint32_t> by_part[kParts];  // local entries of every merge partition, in first-appearance order
+  std::vector<uint32_t> l2g;        // local entry -> global entry (after the merge)
 };
 
-static void tokenize_chunk(const uint8_t *buf, int64_t begin, int64_t end, ChunkResult *out) {
-  out->raw.reserve((size_t)((end - begin) / 5 + 16));
-  char word[kMaxWord];
-  int len = 0;
-  int64_t pos = begin, tb = 0;
-  while (next_token(buf, end, pos, word, len, tb)) {
-    int64_t e = out->map.find(word, len);
-    if (e < 0) e = out->map.insert(word, len);
-    out->map.count[e]++;
-    if ((int64_t)out->raw.size() % kCkptEvery == 0) out->ck_begin.push_back(tb);
-    out->raw.push_back((uint32_t)e);
+// byte classes of ReadWord (:131-155): 0 regular, 1 space / tab, 2 newline, 3 carriage return (skipped
+// everywhere), 4 NUL (ends the C string the reference compares and hashes)
+struct ByteClass {
+  uint8_t c[256];
+  ByteClass() {
+    memset(c, 0, sizeof c);
+    c[' '] = c['\t'] = 1;
+    c['\n'] = 2;
+    c[13] = 3;
+    c[0] = 4;
   }
+};
+const ByteClass kClass;
+
+void tokenize_chunk(const uint8_t *buf, int64_t begin, int64_t end, ChunkResult *out) {
+  out->raw.reserve((size_t)((end - begin) / 5 + 16));
+  WordMap &map = out->map;
+  char word[kMaxWord];
+  int64_t pos = begin;
+  // Tokens are resolved in batches: the scanner only records (pointer, length, hash, offset); a batch is
+  // looked up after its slots and entries have been prefetched, in token order (so first-appearance order
+  // and the checkpoints are those of the sequential reader).  Pointers into `word` are copied: the buffer
+  // is reused by the next slow-path token.
+  constexpr int kBatch = 32;
+  struct Pending { const char *w; int len; uint64_t h; int64_t tb; };
+  Pending pend[kBatch];
+  char slow[kBatch][64];  // slow-path tokens up to 63 bytes are parked here, longer ones flush the batch first
+  int npend = 0;
+  auto flush = [&] {
+    for (int i = 0; i < npend; ++i) map.prefetch_slot(pend[i].h);
+    for (int i = 0; i < npend; ++i) map.prefetch_entry(pend[i].h);
+    for (int i = 0; i < npend; ++i) {
+      const Pending &t = pend[i];
+      int64_t e = map.find(t.w, t.len, t.h);
+      if (e < 0) e = map.insert(t.w, t.len, t.h);
+      map.ent[(size_t)e].count++;
+      if ((int64_t)out->raw.size() % kCkptEvery == 0) out->ck_begin.push_back(t.tb);
+      out->raw.push_back((uint32_t)e);
+    }
+    npend = 0;
+  };
+  auto emit = [&](const char *w, int len, uint64_t h, int64_t tb) {
+    if (w == word) {  // slow-path token in the scratch buffer
+      if (len < 64) {
+        memcpy(slow[npend], w, len);
+        w = slow[npend];
+      } else {
+        flush();
+        pend[0] = Pending{w, len, h, tb};
+        npend = 1;
+        flush();
+        return;
+      }
+    }
+    pend[npend++] = Pending{w, len, h, tb};
+    if (npend == kBatch) flush();
+  };
+  const uint64_t eos_hash = hash_bytes("</s>", 4);
+  while (pos < end) {
+    const uint8_t cls = kClass.c[buf[pos]];
+    if (cls == 1 || cls == 3) { ++pos; continue; }
+    if (cls == 2) {  // a newline outside a word is the token </s>
+      emit("</s>", 4, eos_hash, pos);
+      ++pos;
+      continue;
+    }
+    // a word starts here.  Fast path: its bytes are contiguous in the file (no CR, no NUL, shorter than
+    // MAX_STRING) — hash while scanning, look up straight from the mapping.
+    const int64_t start = pos;
+    uint64_t h = 1469598103934665603ULL;
+    int64_t q = pos;
+    uint8_t stop = 0;
+    if (cls == 0) {
+      while (q < end && (stop = kClass.c[buf[q]]) == 0) {
+        h = (h ^ buf[q]) * 1099511628211ULL;
+        ++q;
+      }
+    } else {
+      stop = cls;  // the word starts with a NUL byte
+    }
+    if (q >= end) {
+      if (q - start < kMaxWord - 1) break;  // cut short by the end of the file: dropped, as in the reference (:279,:180)
+      stop = 3;                              // over-long word at EOF: let the reference-shaped reader decide
+    }
+    if (stop <= 2 && q - start < kMaxWord - 1) {
+      emit((const char *)buf + start, (int)(q - start), h, start);
+      pos = q;  // the delimiter is looked at again: a newline becomes </s>
+      continue;
+    }
+    // slow path (CR or NUL inside the word, or 4095+ bytes): the byte-by-byte reader
+    int len = 0;
+    int64_t tb = 0, p2 = start;
+    if (!next_token(buf, end, p2, word, len, tb)) break;
+    emit(word, len, hash_bytes(word, len), tb);
+    pos = p2;
+  }
+  flush();
 }
+
+}  // namespace
 
 extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out) {
   if (!out) {
@@ -279,6 +411,7 @@ extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out
       return W2B_EIO;
     }
     c->buf = (const uint8_t *)m;
+    madvise(m, st.st_size, MADV_SEQUENTIAL);
   }
   const bool dbg = getenv("W2B_TOKENIZER_DEBUG") != nullptr;
   auto t_start = std::chrono::steady_clock::now();
@@ -289,13 +422,13 @@ extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out
     t_start = now;
   };
   // ---- pass 1, parallel over chunks of the file (the reference's single fgetc loop, :277-293,
-  // runs at ~7 M words/s; the GPU consumes 30 M words/s)
+  // runs at ~7 M words/s; one GPU consumes 30 M words/s, eight consume 250 M)
   const int64_t n = c->file_size;
   int nthreads = (int)std::thread::hardware_concurrency();
   if (const char *e = getenv("W2B_TOKENIZER_THREADS")) nthreads = atoi(e);
   int64_t min_chunk = 4 << 20;
   if (const char *e = getenv("W2B_TOKENIZER_MIN_CHUNK")) min_chunk = atoll(e);
-  nthreads = std::max(1, std::min(nthreads, 64));
+  nthreads = std::max(1, std::min(nthreads, 256));
   nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, n / std::max<int64_t>(min_chunk, 1)));
   std::vector<int64_t> cut(nthreads + 1, n);
   cut[0] = 0;
@@ -306,82 +439,115 @@ extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out
     while (p < n && !(c->buf[p] == ' ' || c->buf[p] == '\t' || c->buf[p] == '\n')) ++p;
     cut[t] = p < n ? p + 1 : n;
   }
-  std::vector<ChunkResult> chunks(nthreads);
-  {
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t)
-      th.emplace_back(tokenize_chunk, c->buf, cut[t], cut[t + 1], &chunks[t]);
-    tokenize_chunk(c->buf, cut[0], cut[1], &chunks[0]);
-    for (auto &x : th) x.join();
-  }
-  lap("pass1");
-  // ---- merge in file order: global first-appearance order = chunk order, then local order; </s> first (:276)
-  WordMap &map = c->map;
-  map.insert("</s>", 4);
-  std::vector<std::vector<uint32_t>> l2g(nthreads);
-  for (int t = 0; t < nthreads; ++t) {
-    const WordMap &lm = chunks[t].map;
-    l2g[t].resize(lm.off.size());
-    for (uint32_t e = 0; e < lm.off.size(); ++e) {
-      int64_t g = map.find(lm.str(e), (int)lm.wlen[e]);
-      if (g < 0) g = map.insert(lm.str(e), (int)lm.wlen[e]);
-      map.count[g] += lm.count[e];
-      l2g[t][e] = (uint32_t)g;
+  auto run_parallel = [](int count, int threads, const std::function<void(int)> &fn) {
+    threads = std::max(1, std::min(threads, count));
+    if (threads == 1) {
+      for (int i = 0; i < count; ++i) fn(i);
+      return;
     }
-  }
+    std::atomic<int> next(0);
+    auto work = [&] { for (int i; (i = next.fetch_add(1)) < count;) fn(i); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; ++t) th.emplace_back(work);
+    work();
+    for (auto &x : th) x.join();
+  };
+  std::vector<ChunkResult> chunks(nthreads);
+  run_parallel(nthreads, nthreads, [&](int t) {
+    ChunkResult &ch = chunks[t];
+    tokenize_chunk(c->buf, cut[t], cut[t + 1], &ch);
+    for (uint32_t e = 0; e < ch.map.size(); ++e) ch.by_part[part_of(ch.map.ent[e].hash)].push_back(e);
+    ch.l2g.resize(ch.map.size());
+  });
+  lap("pass1");
+  // ---- merge, one thread per partition of the hash space.  Global first-appearance order = chunk order,
+  // then local order (what the reference's sequential pass produces): every global entry remembers the
+  // (chunk, local entry) that introduced it, and that pair is the tie-break of the sort below.
+  c->parts.resize(kParts);
+  struct First { uint32_t chunk, local; };
+  std::vector<std::vector<First>> first(kParts);
+  run_parallel(kParts, nthreads, [&](int p) {
+    WordMap &g = c->parts[p];
+    size_t total = 0;
+    for (int t = 0; t < nthreads; ++t) total += chunks[t].by_part[p].size();
+    first[p].reserve(total / std::max(1, nthreads / 2) + 16);
+    for (int t = 0; t < nthreads; ++t) {
+      const WordMap &lm = chunks[t].map;
+      for (uint32_t e : chunks[t].by_part[p]) {
+        const WordMap::Entry &le = lm.ent[e];
+        int64_t ge = g.find(lm.str(e), (int)le.len, le.hash);
+        if (ge < 0) {
+          ge = g.insert(lm.str(e), (int)le.len, le.hash);
+          first[p].push_back(First{(uint32_t)t, e});
+        }
+        g.ent[(size_t)ge].count += le.count;
+        chunks[t].l2g[e] = (uint32_t)ge;  // partition-local for now
+      }
+    }
+  });
+  std::vector<uint32_t> part_base(kParts + 1, 0);
+  for (int p = 0; p < kParts; ++p) part_base[p + 1] = part_base[p] + (uint32_t)c->parts[p].size();
   lap("merge");
-  // SortVocab (:215-242): </s> pinned at 0, the rest by count descending, ties in
-  // first-appearance order (what glibc's qsort yields here; asserted against the
-  // reference in tests), then the min_count cut.
-  const size_t m = map.off.size();
-  std::vector<uint32_t> order(m);
-  std::iota(order.begin(), order.end(), 0u);
-  std::stable_sort(order.begin() + 1, order.end(),
-                   [&](uint32_t a, uint32_t b) { return map.count[a] > map.count[b]; });
-  c->final_id.assign(m, -1);
-  for (size_t k = 0; k < m; ++k) {
-    const uint32_t e = order[k];
-    if (map.count[e] < min_count && k != 0) continue;
-    c->final_id[e] = (int32_t)c->words.size();
-    c->words.push_back(nullptr);
-    c->cn.push_back(map.count[e]);
-    c->train_words += map.count[e];
+  // SortVocab (:215-242): </s> pinned at 0 (AddWordToVocab("</s>") comes first, :276, even when the file
+  // has no newline), the rest by count descending, ties in first-appearance order (what glibc's qsort
+  // yields here; asserted against the reference in tests), then the min_count cut.
+  struct Key { int64_t count; uint32_t chunk, local, part, idx; };
+  std::vector<Key> order;
+  order.reserve(part_base[kParts]);
+  const uint64_t eos_hash = hash_bytes("</s>", 4);
+  const int eos_part = part_of(eos_hash);
+  const int64_t eos_entry = c->parts[eos_part].find("</s>", 4, eos_hash);
+  for (int p = 0; p < kParts; ++p)
+    for (uint32_t e = 0; e < c->parts[p].size(); ++e) {
+      if (p == eos_part && (int64_t)e == eos_entry) continue;
+      if (c->parts[p].ent[e].count < min_count) continue;  // never enters the vocabulary: no need to rank it
+      order.push_back(Key{c->parts[p].ent[e].count, first[p][e].chunk, first[p][e].local, (uint32_t)p, e});
+    }
+  std::sort(order.begin(), order.end(), [](const Key &a, const Key &b) {
+    if (a.count != b.count) return a.count > b.count;
+    if (a.chunk != b.chunk) return a.chunk < b.chunk;
+    return a.local < b.local;
+  });
+  c->part_final.resize(kParts);
+  for (int p = 0; p < kParts; ++p) c->part_final[p].assign(c->parts[p].size(), -1);
+  c->eos_storage = "</s>";
+  c->words.push_back(eos_entry >= 0 ? c->parts[eos_part].str((uint32_t)eos_entry) : c->eos_storage.c_str());
+  c->cn.push_back(eos_entry >= 0 ? c->parts[eos_part].ent[(size_t)eos_entry].count : 0);
+  c->train_words += c->cn[0];
+  if (eos_entry >= 0) c->part_final[eos_part][(size_t)eos_entry] = 0;
+  for (const Key &k : order) {
+    if (k.count < min_count) break;  // sorted by count: everything after is below the cut too
+    c->part_final[k.part][k.idx] = (int32_t)c->words.size();
+    c->words.push_back(c->parts[k.part].str(k.idx));
+    c->cn.push_back(k.count);
+    c->train_words += k.count;
   }
-  for (size_t e = 0; e < m; ++e)
-    if (c->final_id[e] >= 0) c->words[c->final_id[e]] = map.str((uint32_t)e);
   lap("sort");
   // ---- compact to the in-vocab stream (parallel per chunk), remembering where every checkpoint lands
   std::vector<int64_t> kept(nthreads, 0), base(nthreads + 1, 0);
-  {
-    auto count_kept = [&](int t) {
-      int64_t k = 0;
-      for (uint32_t le : chunks[t].raw) k += c->final_id[l2g[t][le]] >= 0;
-      kept[t] = k;
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t) th.emplace_back(count_kept, t);
-    count_kept(0);
-    for (auto &x : th) x.join();
-  }
+  std::vector<std::vector<int32_t>> lfinal(nthreads);  // chunk-local entry -> vocab id or -1
+  run_parallel(nthreads, nthreads, [&](int t) {
+    const ChunkResult &ch = chunks[t];
+    lfinal[t].resize(ch.map.size());
+    for (uint32_t e = 0; e < ch.map.size(); ++e)
+      lfinal[t][e] = c->part_final[part_of(ch.map.ent[e].hash)][ch.l2g[e]];
+    int64_t k = 0;
+    for (uint32_t le : ch.raw) k += lfinal[t][le] >= 0;
+    kept[t] = k;
+  });
   for (int t = 0; t < nthreads; ++t) base[t + 1] = base[t] + kept[t];
   c->ids.resize((size_t)base[nthreads]);
   std::vector<std::vector<int64_t>> ck_comp(nthreads);
-  {
-    auto fill = [&](int t) {
-      int64_t w = base[t];
-      const auto &raw = chunks[t].raw;
-      ck_comp[t].reserve(chunks[t].ck_begin.size());
-      for (size_t k = 0; k < raw.size(); ++k) {
-        if ((int64_t)k % kCkptEvery == 0) ck_comp[t].push_back(w);
-        const int32_t id = c->final_id[l2g[t][raw[k]]];
-        if (id >= 0) c->ids[(size_t)w++] = id;
-      }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t) th.emplace_back(fill, t);
-    fill(0);
-    for (auto &x : th) x.join();
-  }
+  run_parallel(nthreads, nthreads, [&](int t) {
+    int64_t w = base[t];
+    const auto &raw = chunks[t].raw;
+    ck_comp[t].reserve(chunks[t].ck_begin.size());
+    for (size_t k = 0; k < raw.size(); ++k) {
+      if ((int64_t)k % kCkptEvery == 0) ck_comp[t].push_back(w);
+      const int32_t id = lfinal[t][raw[k]];
+      if (id >= 0) c->ids[(size_t)w++] = id;
+    }
+  });
   for (int t = 0; t < nthreads; ++t) {
     c->ck_begin.insert(c->ck_begin.end(), chunks[t].ck_begin.begin(), chunks[t].ck_begin.end());
     c->ck_comp.insert(c->ck_comp.end(), ck_comp[t].begin(), ck_comp[t].end());
@@ -425,8 +591,7 @@ extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int
       start[i] = (int64_t)c->ids.size();
       continue;
     }
-    const int64_t e = c->map.find(word, len);
-    if (e >= 0) first[i] = c->final_id[e];
+    first[i] = c->lookup(word, len);
     // index of the first regular in-vocab token that begins at or after `pos`:
     // restart from the last checkpoint at or before it and count forward
     size_t k = std::upper_bound(c->ck_begin.begin(), c->ck_begin.end(), pos) - c->ck_begin.begin();
@@ -440,8 +605,7 @@ extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int
     for (;;) {
       if (!next_token(c->buf, c->file_size, p2, word, l2, b2)) break;
       if (b2 >= pos) break;
-      const int64_t e2 = c->map.find(word, l2);
-      if (e2 >= 0 && c->final_id[e2] >= 0) ++comp;
+      if (c->lookup(word, l2) >= 0) ++comp;
     }
     start[i] = comp;
   }
