@@ -286,3 +286,36 @@ def test_streaming_slice_gather(nthreads):
         if e > b:
             assert stage[b - xl[i]] == ids[b]
     assert lib.w2b_host_gather_slices(None, n, L, S, ptr(cursor), ptr(done), ptr(stage), ptr(xl), ptr(lim), ptr(eof), 1) != 0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_tokenizer_fuzz_against_oracle(tmp_path, monkeypatch, seed):
+    """Random bytes from a hostile alphabet (CR and NUL inside words, control characters, high bytes, runs of
+    newlines, words longer than MAX_STRING, no trailing whitespace), cut into many chunks: the fast path (words
+    hashed straight from the mapping) and the byte-by-byte slow path must reproduce the reference's reader for
+    every thread count — words, counts, token stream and shard starts."""
+    import word2bits_b200 as w2b
+    rng = np.random.default_rng(100 + seed)
+    alphabet = np.frombuffer(b"abcde" * 6 + b"  \t\n\n\r\x00\x01\xff\xc3\xa9", np.uint8)
+    body = alphabet[rng.integers(0, len(alphabet), 400_000)].tobytes()
+    long_words = b" " + b"x" * 4094 + b" " + b"y" * 4095 + b" " + b"z" * 4096 + b"q " + b"k" * 9000 + b"\n"
+    data = body[:150_000] + long_words + body[150_000:] + (b"" if seed == 0 else b" tail" if seed == 1 else b"\r")
+    p = tmp_path / "fuzz.txt"
+    p.write_bytes(data)
+    o = po.Corpus(str(p), 2)
+    monkeypatch.setenv("W2B_TOKENIZER_MIN_CHUNK", "20000")
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("W2B_TOKENIZER_THREADS", threads)
+        c = w2b.Corpus(str(p), 2)
+        assert c.words() == o.words(), threads
+        assert np.array_equal(c.counts, o.counts) and np.array_equal(c.tokens, o.tokens), threads
+        assert (c.train_words, c.file_size, c.num_tokens) == (o.train_words, o.file_size, o.num_tokens)
+        for n in (1, 7, 64):
+            s, f = c.shards(n)
+            assert [o.shard_start(i, n) for i in range(n)] == list(zip(s.tolist(), f.tolist())), (threads, n)
+    if po.ref_available("strict"):
+        ref = po.Ref("strict")
+        ref.configure(str(p), 8, 3, 4, 1, min_count=2)
+        ref.learn_vocab()
+        assert c.words() == ref.words() and np.array_equal(c.counts, ref.counts())
+        assert c.train_words == ref.train_words
