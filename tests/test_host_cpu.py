@@ -319,3 +319,30 @@ def test_tokenizer_fuzz_against_oracle(tmp_path, monkeypatch, seed):
         ref.learn_vocab()
         assert c.words() == ref.words() and np.array_equal(c.counts, ref.counts())
         assert c.train_words == ref.train_words
+
+
+def test_text_writer_parallel_and_cached_formatting(tmp_path, monkeypatch):
+    """The text writer formats blocks of rows on several threads through a per-thread value cache: the bytes
+    must not depend on the thread count and must equal "%lf " of every value (checked with Python's own
+    correctly-rounded formatting for finite floats; NaN / inf / -0.0 only for thread-independence)."""
+    import word2bits_b200 as w2b
+    path = zipf_corpus(str(tmp_path / "c.txt"), 30000, 3000, seed=4)
+    c = w2b.Corpus(path, 1)
+    V, D = c.vocab_size, 37
+    rng = np.random.default_rng(8)
+    vec = (rng.standard_normal((V, D)) * np.exp(rng.uniform(-20, 20, (V, D)))).astype(np.float32)
+    vec[rng.random((V, D)) < 0.5] = np.float32(1 / 3)             # cache hits, like trained 1-bit vectors
+    vec[5, :6] = [np.nan, -np.nan, np.inf, -np.inf, -0.0, np.float32(3.4e38)]
+    outs = []
+    for threads in ("1", "4", "32"):
+        monkeypatch.setenv("W2B_WRITER_THREADS", threads)
+        out = str(tmp_path / ("v%s.txt" % threads))
+        c.write_vectors(out, vec, 0)
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] == outs[2]
+    lines = outs[0].split(b"\n")
+    assert lines[0] == b"%d %d" % (V, D) and lines[-1] == b"" and len(lines) == V + 2
+    words = c.words()
+    for a in (0, 1, 2, 77, V - 1):
+        want = words[a].encode("latin1") + b" " + b"".join(b"%f " % float(x) for x in vec[a])
+        assert lines[1 + a] == want, a

@@ -612,6 +612,47 @@ extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int
   return W2B_OK;
 }
 
+// "%lf " of a float, through a small direct-mapped cache keyed by the bit pattern: trained vectors hold
+// 2^bitlevel distinct values (2 at bitlevel 1), so almost every value is a table hit; a miss is formatted by
+// snprintf itself, which keeps the bytes identical to the reference's fprintf for every input (:571).
+namespace {
+struct FmtCache {
+  struct Slot { uint32_t bits; uint8_t len, valid; char s[58]; };
+  Slot slot[512];
+  FmtCache() { memset(slot, 0, sizeof slot); }
+  // "%lf " of one value.  A float times 10^6 is exact in double (24-bit x 20-bit significands), so rounding it
+  // to the nearest integer, ties to even, is exactly the correctly rounded 6-decimal expansion printf produces
+  // (round-to-nearest mode); everything that does not fit that scheme goes to snprintf itself.
+  static int format(float x, char *out, size_t cap) {
+    const double ax = fabs((double)x);
+    if (!(ax < 1e12)) return snprintf(out, cap, "%lf ", (double)x);  // huge, inf, nan (<= 48 bytes for any float)
+    const unsigned long long n = (unsigned long long)nearbyint(ax * 1e6);
+    unsigned long long ip = n / 1000000ULL;
+    unsigned fr = (unsigned)(n % 1000000ULL);
+    char tmp[32];
+    int k = 0;
+    tmp[k++] = ' ';
+    for (int i = 0; i < 6; ++i) { tmp[k++] = (char)('0' + fr % 10); fr /= 10; }
+    tmp[k++] = '.';
+    do { tmp[k++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    if (signbit(x)) tmp[k++] = '-';
+    for (int i = 0; i < k; ++i) out[i] = tmp[k - 1 - i];
+    return k;
+  }
+  inline void append(float x, std::string &out) {
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    Slot &e = slot[(b * 2654435761u) >> 23];
+    if (!e.valid || e.bits != b) {
+      e.len = (uint8_t)format(x, e.s, sizeof e.s);
+      e.bits = b;
+      e.valid = 1;
+    }
+    out.append(e.s, e.len);
+  }
+};
+}  // namespace
+
 extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
                                  int binary) {
   if (!path || !c || !vec || V < 0 || V > (int64_t)c->words.size() || D < 1) {
@@ -623,16 +664,46 @@ extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const fl
     w2b_set_error("cannot open %s for writing", path);
     return W2B_EIO;
   }
-  std::vector<char> iobuf(1 << 20);  // per call: two writers may run on two host threads
+  std::vector<char> iobuf(4 << 20);  // per call: two writers may run on two host threads
   setvbuf(fo, iobuf.data(), _IOFBF, iobuf.size());
   fprintf(fo, "%lld %lld\n", (long long)V, (long long)D);
-  for (int64_t a = 0; a < V; ++a) {
-    fprintf(fo, "%s ", c->words[a]);
-    const float *row = vec + a * D;
-    if (binary) fwrite(row, sizeof(float), D, fo);
-    else
-      for (int64_t b = 0; b < D; ++b) fprintf(fo, "%lf ", row[b]);
-    fprintf(fo, "\n");
+  if (binary) {
+    for (int64_t a = 0; a < V; ++a) {
+      fputs(c->words[a], fo);
+      fputc(' ', fo);
+      fwrite(vec + a * D, sizeof(float), D, fo);
+      fputc('\n', fo);
+    }
+  } else {
+    // text: V * D values (3.2 GB at V = 400 k, D = 800).  Blocks of rows are formatted by a few threads into
+    // private buffers and written in order.
+    int nthr = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (const char *e = getenv("W2B_WRITER_THREADS")) nthr = std::max(1, atoi(e));
+    const int64_t rows_per_task = std::max<int64_t>(1, (1 << 18) / (D * 10));  // ~256 KB of text per task
+    nthr = (int)std::max<int64_t>(1, std::min<int64_t>(nthr, (V + rows_per_task - 1) / rows_per_task));
+    std::vector<std::string> bufs(nthr);
+    std::vector<FmtCache> caches(nthr);
+    auto format_rows = [&](int t, int64_t lo, int64_t hi) {
+      std::string &out = bufs[t];
+      out.clear();
+      for (int64_t a = lo; a < hi; ++a) {
+        out.append(c->words[a]);
+        out.push_back(' ');
+        const float *row = vec + a * D;
+        for (int64_t b = 0; b < D; ++b) caches[t].append(row[b], out);
+        out.push_back('\n');
+      }
+    };
+    for (int64_t base = 0; base < V; base += rows_per_task * nthr) {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nthr; ++t) {
+        const int64_t lo = std::min(V, base + t * rows_per_task), hi = std::min(V, lo + rows_per_task);
+        th.emplace_back(format_rows, t, lo, hi);
+      }
+      format_rows(0, base, std::min(V, base + rows_per_task));
+      for (auto &x : th) x.join();
+      for (int t = 0; t < nthr; ++t) fwrite(bufs[t].data(), 1, bufs[t].size(), fo);
+    }
   }
   const bool bad = ferror(fo) != 0;
   if (fclose(fo) != 0 || bad) {  // the reference ignores write errors; a truncated vector file is worse
