@@ -1,0 +1,135 @@
+"""The production kernel's own source on the CPU (tests/emu: word2bits_b200/csrc/w2b_ring.cuh compiled with
+-DW2B_EMULATE, one fiber per CUDA thread, mbarrier / TMA bulk copy / bulk reduce semantics emulated with
+adversarially late completion).  It is test infrastructure, not a fallback and not a timing model; it exists so
+that a kernel variant can be checked functionally — control flow, index arithmetic, slot protocol, arithmetic
+against the oracle — before (or without) a GPU run.  What the emulated default kernel produces matches what the
+real one produced on the B200 in round 1 (tests/test_gpu_parity.py bars), which is what makes the variants'
+results below meaningful."""
+import numpy as np
+import pytest
+
+import word2bits_b200 as w2b
+from oracle import pyoracle as po
+from tests.emu import emu
+from tests.util import zipf_corpus
+
+
+@pytest.fixture(scope="module")
+def tiny(tmp_path_factory):
+    path = zipf_corpus(str(tmp_path_factory.mktemp("e") / "tiny.txt"), 4000, 300, seed=5, newline_every=40)
+    c, o = w2b.Corpus(path, 1), po.Corpus(path, 1)
+    return c, o, po.unigram_table(o.counts)
+
+
+@pytest.fixture(scope="module")
+def medium(tmp_path_factory):
+    path = zipf_corpus(str(tmp_path_factory.mktemp("e") / "medium.txt"), 24000, 1500, seed=2)
+    c, o = w2b.Corpus(path, 5), po.Corpus(path, 5)
+    return c, o, po.unigram_table(o.counts)
+
+
+def _run(c, table, D, W, neg, b, S, kernel, **kw):
+    u, v = po.init_net(c.vocab_size, D)
+    out = emu.train_epoch(c, table, u, v, size=D, window=W, negative=neg, bitlevel=b, shards=S, kernel=kernel, **kw)
+    assert out["done"].tolist() == [1] * S
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    return u, v, out
+
+
+def test_emulated_default_kernel_tracks_the_oracle(medium):
+    """Calibration of the emulator itself: the measured kernel (cfg.kernel 0), one shard, prefetch off, fp32 —
+    the same bar the real kernel meets on the GPU (test_fast_single_shard_tracks_oracle: 5e-3, loss 1e-3)."""
+    c, o, table = medium
+    m = po.OracleModel(o, 64, 5, 6, 0, shards=1, iters=1, table=table)
+    lo = m.train_shard(0)
+    u, v, out = _run(c, table, 64, 5, 6, 0, 1, 0, serial=1)
+    assert abs(out["loss"].sum() - lo) <= 1e-3 * abs(lo)
+    assert np.abs(u - m.u).max() < 5e-3 and np.abs(v - m.v).max() < 5e-3
+    assert (out["wca"], out["words"].sum()) == (m.word_count_actual, m.word_count_actual)
+    assert np.float32(out["alpha"]) == np.float32(m.alpha)
+
+
+SHAPES = [  # D, window, negative, bitlevel, shards — BASELINE shapes, a wrap-around (1+negative > v-ring), edges
+    (800, 10, 24, 1, 2), (400, 10, 12, 2, 2), (400, 10, 24, 0, 2), (200, 8, 24, 1, 3), (100, 5, 63, 1, 2),
+    (64, 30, 12, 0, 2), (8, 2, 1, 2, 2), (4, 1, 0, 1, 2),
+]
+
+
+@pytest.mark.parametrize("D,W,neg,b,S", SHAPES)
+def test_variants_against_the_default_kernel(D, W, neg, b, S, tiny):
+    """cfg.kernel 2..5 on the emulator, prefetch off (deterministic): exactly the positions / rows / words of
+    the default; kernel 2 (division-free indices, same order of float operations) bit-identical tables and
+    loss; the row-unit / extra-warp variants sum in another order — fp tolerance at bitlevel 0, loss within
+    0.5 % where sign flips make the trajectory chaotic (bitlevel 1 / 2 on a 300-word vocabulary)."""
+    c, o, table = tiny
+    u0, v0, base = _run(c, table, D, W, neg, b, S, 0, serial=1)
+    for kernel in (2, 3, 4, 5):
+        u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=1)
+        for k in ("n_pos", "n_ctx", "n_tgt", "words"):
+            assert out[k].tolist() == base[k].tolist(), (kernel, k)
+        assert (out["wca"], np.float32(out["alpha"])) == (base["wca"], np.float32(base["alpha"]))
+        same_order = out["plan"]["units_per_warp"] == 1 and out["plan"]["consumer_warps"] == base["plan"]["consumer_warps"]
+        if same_order:
+            assert np.array_equal(u, u0) and np.array_equal(v, v0) and out["loss"].tolist() == base["loss"].tolist(), kernel
+        else:
+            assert abs(out["loss"].sum() - base["loss"].sum()) <= 5e-3 * abs(base["loss"].sum()), kernel
+            if b == 0:  # reordered fp32 sums on a 300-word vocabulary (rows revisited thousands of times)
+                d = float(max(np.abs(u - u0).max(), np.abs(v - v0).max()))
+                assert d < 1e-2, (kernel, d)
+
+
+@pytest.mark.parametrize("D", [200, 800])
+def test_variants_are_as_close_to_the_oracle_as_the_default(D, medium):
+    """Several shards one after another, fp32, prefetch off, against the oracle's shards one after another.
+    On this 900-word vocabulary duplicate targets inside a position (read before either update lands — the
+    documented within-position Hogwild effect) put the default kernel 5e-3 .. 4e-2 from the oracle; a variant
+    must not be further away than the kernel that was measured on the GPU."""
+    c, o, table = medium
+    W, neg, S = 5, 6, 3
+    m = po.OracleModel(o, D, W, neg, 0, shards=S, iters=1, table=table)
+    lo = sum(m.train_shard(s) for s in range(S))
+    dev = {}
+    for kernel in ((0, 2, 5) if D == 800 else (0, 2, 3, 4)):
+        u, v, out = _run(c, table, D, W, neg, 0, S, kernel, serial=1)
+        assert abs(out["loss"].sum() - lo) <= 3e-3 * abs(lo), kernel
+        assert out["wca"] == m.word_count_actual
+        dev[kernel] = float(max(np.abs(u - m.u).max(), np.abs(v - m.v).max()))
+    assert dev[0] < (1e-2 if D == 200 else 6e-2), dev
+    for kernel, d in dev.items():
+        assert d <= 1.25 * dev[0] + 1e-4, dev
+
+
+@pytest.mark.parametrize("kernel", [0, 2, 3, 4, 5])
+def test_prefetching_mode_under_shuffled_scheduling(kernel, tiny):
+    """Default (prefetching) mode with the fibers scheduled in random order and asynchronous copies / reduces
+    completing at random times: terminates, trains every position; the loss stays within 6 % of the oracle's
+    (rows are read one or two updates stale, which weighs heavily on a 300-word vocabulary: the measured
+    default kernel itself is 3 % off here; on the GPU tests' 3000-word corpus the bar is 2 %)."""
+    c, o, table = tiny
+    D, W, neg, b, S = (800, 10, 24, 1, 2) if kernel == 5 else (200, 8, 24, 1, 3)
+    m = po.OracleModel(o, D, W, neg, b, shards=S, iters=1, table=table)
+    lo = sum(m.train_shard(s) for s in range(S))
+    for seed in (1, 2):
+        u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=0, async_mode=2, seed=seed)
+        assert abs(out["loss"].sum() - lo) <= 0.06 * abs(lo), (kernel, seed, out["loss"].sum(), lo)
+        assert out["wca"] == m.word_count_actual
+
+
+@pytest.mark.parametrize("kernel", [0, 3])
+def test_emulated_sampler_trace_equals_oracle(kernel, tiny):
+    c, o, table = tiny
+    for shard in (0, 2):
+        tr = emu.train_epoch(c, table, *po.init_net(c.vocab_size, 200), size=200, window=8, negative=40, bitlevel=1,
+                             shards=3, kernel=kernel, trace_shard=shard, trace_cap=8000)["trace"]
+        m = po.OracleModel(o, 4, 8, 40, 1, shards=3, table=table)
+        _, want = m.train_shard(shard, trace_cap=8000)
+        assert tr == want
+
+
+def test_emulator_detects_a_ring_that_is_too_small(tiny):
+    """Negative control: a v-ring below the planner's bound hangs the real kernel; here it is reported."""
+    c, o, table = tiny
+    u, v = po.init_net(c.vocab_size, 100)
+    with pytest.raises(emu.EmuError, match="dead-locked"):
+        emu.train_epoch(c, table, u, v, size=100, window=5, negative=63, bitlevel=1, shards=2, kernel=0,
+                        plan_override=dict(v_rows=20))

@@ -63,6 +63,11 @@ struct RingCtl {
 };
 
 // ------------------------------------------------------------------------ PTX wrappers
+#ifdef W2B_EMULATE
+// tests/emu: the kernels below compiled for the host and run on fibers (test infrastructure; the macro is
+// defined by tests/emu/Makefile only, never by the product build)
+#include "w2b_emu_ptx.h"
+#else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -111,6 +116,8 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 __device__ __forceinline__ void sts128(unsigned addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+#endif  // W2B_EMULATE
 
 // Shared-memory carve-up (host and device agree through this helper).
 struct RingLayout {
@@ -218,7 +225,9 @@ __global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 3
     ctl->urel = 0;
     ctl->prog = 0;
     ctl->loss_out = 0.0;
+#ifndef W2B_EMULATE
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   }
   for (int i = tid; i < nv; i += blockDim.x) s_rc[i] = 0;
   __syncthreads();
