@@ -109,7 +109,8 @@ typedef struct {
                           3 / 4 = 2 + 16 / 8 lanes per target row (narrow rows, D <= 512 / 256),
                           5 = 2 + two more consumer warps (wide rows, D > 512) */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
-  int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed */
+  int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed;
+                          2 (kernel >= 2 only, experimental) = prefetching with early slot release */
 } w2b_config;
 
 typedef struct {

@@ -70,7 +70,8 @@ class BulkQueue:
 
 
 class RingModel:
-    def __init__(self, plan, window, negative, positions, seed=0, kND=None):
+    def __init__(self, plan, window, negative, positions, seed=0, kND=None, early_release=False):
+        self.early_release = early_release  # variant kernels, TrainParams::serial == 2
         self.nu, self.nv = plan["u_rows"], plan["v_rows"]
         self.G, self.R, self.ncw = plan["group"], plan["rows_in_flight"], plan["consumer_warps"]
         self.upw = plan.get("units_per_warp", 1) or 1  # row units per consumer warp (LPR < 32 variants)
@@ -218,6 +219,14 @@ class RingModel:
             nt, vs0 = d["nt"], d["vs0"]
             i0w = warp * upw
             while i0w < nt:
+                if self.early_release:  # leaders confirm the previous pass's reduces and free its slots first
+                    for u in units:
+                        if any(x >= 0 for x in u["prev"]):
+                            u["bq"].wait_read(0)
+                            for t in range(R):
+                                if u["prev"][t] >= 0:
+                                    self._release(u["prev"][t])
+                                    u["prev"][t] = -1
                 batch = []
                 for sub in range(upw):
                     i0 = i0w + sub

@@ -122,6 +122,28 @@ def test_variant_statistical(variant, b, D, neg, large):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("b,D,neg", [(1, 800, 24), (2, 400, 12), (1, 200, 63)])
+def test_variant_early_release(variant, b, D, neg, large):
+    """ring_serial = 2 (variants only): prefetching with the slots of a pass released at the top of the next pass.
+    Same positions / rows as the default release policy, loss within the statistical bar of the oracle."""
+    shards = 16
+    c = w2b.Corpus(large, 5)
+    o = po.Corpus(large, 5)
+    t = w2b.Trainer(c, size=D, window=8, negative=neg, bitlevel=b, threads=shards, iter=1, kernel=variant, ring_serial=2)
+    t0 = w2b.Trainer(c, size=D, window=8, negative=neg, bitlevel=b, threads=shards, iter=1, kernel=variant)
+    m = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=1)
+    lo = m.train_epoch_threads()
+    lg, st = t.train_epoch()
+    lg0, st0 = t0.train_epoch()
+    assert st["shards_done"] == shards
+    assert (st["positions"], st["context_rows"], st["target_rows"], st["words"]) == \
+        (st0["positions"], st0["context_rows"], st0["target_rows"], st0["words"])
+    assert abs(lg - lo) <= (0.03 if D >= 800 else 0.015) * abs(lo), (lg, lo)
+    u, v = t.download_raw()
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_variant_streaming_steps(variant, large):
     c = w2b.Corpus(large, 5)
     tot = []

@@ -133,3 +133,16 @@ def test_emulator_detects_a_ring_that_is_too_small(tiny):
     with pytest.raises(emu.EmuError, match="dead-locked"):
         emu.train_epoch(c, table, u, v, size=100, window=5, negative=63, bitlevel=1, shards=2, kernel=0,
                         plan_override=dict(v_rows=20))
+
+
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5])
+def test_early_release_mode(kernel, tiny):
+    """TrainParams::serial == 2 (variant kernels): prefetching with the slots of a pass released at the top of
+    the next pass.  Same positions and rows; the loss stays where the default prefetching mode puts it."""
+    c, o, table = tiny
+    D, W, neg, b, S = (800, 10, 24, 1, 2) if kernel == 5 else (200, 8, 63, 1, 2)
+    u0, v0, base = _run(c, table, D, W, neg, b, S, kernel, serial=0, async_mode=2, seed=4)
+    u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=2, async_mode=2, seed=4)
+    for k in ("n_pos", "n_ctx", "n_tgt", "words"):
+        assert out[k].tolist() == base[k].tolist()
+    assert abs(out["loss"].sum() - base["loss"].sum()) <= 0.02 * abs(base["loss"].sum())

@@ -150,3 +150,22 @@ def test_model_finds_the_unit_bound():
                 results.add(False)
         assert results == {ok}, (nv, need, results)
     assert p["v_rows"] > need
+
+
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5])
+def test_early_release_mode_is_live_and_safe(kernel):
+    """Variant kernels with TrainParams::serial == 2: slots of a pass are handed back at the top of the next pass
+    (after a wait_group.read 0) instead of at its commit."""
+    n = 0
+    for D in (64, 200, 400, 800):
+        for window in (2, 10):
+            for negative in (5, 24, 63):
+                p = w2b.ring_plan(size=D, window=window, negative=negative, kernel=kernel)
+                if not p["ring"]:
+                    continue
+                n += 1
+                for style in ("typical", "extreme", "any"):
+                    rng = random.Random(n)
+                    pos = random_positions(rng, 16, window, negative, style)
+                    RingModel(p, window, negative, pos, seed=n, early_release=True).run()
+    assert n >= 20

@@ -39,8 +39,8 @@ def main():
     a = ap.parse_args()
     ids, cn = synth(a.vocab, a.tokens)
     pk = peak()
-    rows = ["| shape | kernel | lanes/row | shards | positions/s | algorithmic GB/s | of %.0f GB/s | loss/position |" % pk,
-            "|---|---|---|---|---|---|---|---|"]
+    rows = ["| shape | kernel | release | lanes/row | consumer warps | shards | positions/s | algorithmic GB/s | of %.0f GB/s | loss/position |" % pk,
+            "|---|---|---|---|---|---|---|---|---|---|"]
     for name in a.shapes.split(","):
         D, neg, b, W = SHAPES[name]
         for kernel in [int(k) for k in a.kernels.split(",")]:
@@ -49,23 +49,25 @@ def main():
             base = w2b.ring_plan(size=D, window=W, negative=neg, bitlevel=b, kernel=2, vocab_size=a.vocab + 1)
             if kernel >= 3 and (lpr, plan["consumer_warps"]) == (32, base["consumer_warps"]):
                 continue  # variant does not apply to this width: it would repeat kernel 2
-            t = w2b.Trainer(None, vocab_size=a.vocab + 1, size=D, window=W, negative=neg, bitlevel=b, iter=1, threads=None,
-                            kernel=kernel)
-            S = t.threads
-            t.set_vocab_counts(cn, int(a.tokens))
-            t.set_corpus(ids, np.arange(S, dtype=np.int64) * (a.tokens // S), np.full(S, -1, np.int32), True)
-            t.train_step(2000)
-            pos = rows_ = 0
-            ms = loss = 0.0
-            for _ in range(a.steps):
-                st = t.train_step(a.words)
-                pos += st["positions"]; rows_ += st["context_rows"] + st["target_rows"]; ms += st["kernel_ms"]; loss += st["loss"]
-            t.close()
-            gbs = rows_ * D * 4 * 2 / 1e9 / (ms / 1e3)
-            line = "| %s D=%d neg=%d b=%d | %d | %d | %d | %.2f M | %.0f | %.3f | %.4f |" % (
-                name, D, neg, b, kernel, lpr, S, pos / ms / 1e3, gbs, gbs / pk, loss / max(pos, 1))
-            print(line, flush=True)
-            rows.append(line)
+            for release in ((0,) if kernel < 2 else (0, 2)):  # ring_serial 2 = early slot release (variants only)
+                t = w2b.Trainer(None, vocab_size=a.vocab + 1, size=D, window=W, negative=neg, bitlevel=b, iter=1,
+                                threads=None, kernel=kernel, ring_serial=release)
+                S = t.threads
+                t.set_vocab_counts(cn, int(a.tokens))
+                t.set_corpus(ids, np.arange(S, dtype=np.int64) * (a.tokens // S), np.full(S, -1, np.int32), True)
+                t.train_step(2000)
+                pos = rows_ = 0
+                ms = loss = 0.0
+                for _ in range(a.steps):
+                    st = t.train_step(a.words)
+                    pos += st["positions"]; rows_ += st["context_rows"] + st["target_rows"]; ms += st["kernel_ms"]; loss += st["loss"]
+                t.close()
+                gbs = rows_ * D * 4 * 2 / 1e9 / (ms / 1e3)
+                line = "| %s D=%d neg=%d b=%d | %d | %s | %d | %d | %d | %.2f M | %.0f | %.3f | %.4f |" % (
+                    name, D, neg, b, kernel, "early" if release == 2 else "at commit", lpr, plan["consumer_warps"], S,
+                    pos / ms / 1e3, gbs, gbs / pk, loss / max(pos, 1))
+                print(line, flush=True)
+                rows.append(line)
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     with open(a.out, "w") as f:
         f.write("# ring kernel variants, tools/variant_sweep.py (CUDA events; %d words per shard per step, %d steps)\n\n" % (a.words, a.steps))

@@ -336,7 +336,8 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.shard_base = 0;
   p.train = 1;
   p.plain_store = c->cfg.plain_store;
-  p.serial = c->cfg.ring_serial;
+  // ring_serial 2 ("early release", experimental) exists in the variant kernels only
+  p.serial = (c->cfg.ring_serial == 2 && c->cfg.kernel < 2) ? 0 : c->cfg.ring_serial;
   {
     const char *e = getenv("W2B_SLEEP_NS");  // tuning hook
     p.sleep_ns = e ? (unsigned)atoi(e) : 128u;  // flat between 32 and 512 ns on B200 (measured)

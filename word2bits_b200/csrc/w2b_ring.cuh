@@ -174,6 +174,15 @@ __host__ __device__ inline void ring_row_index(unsigned vs0, unsigned i, unsigne
   *group = ring_div(i, g_magic);
 }
 
+// TrainParams::serial: 0 = production (prefetching), 1 = parity aid (no prefetch across positions).  The
+// variants (OPT = 1) also know 2 = "early release": a unit leader confirms the previous pass's bulk reduces at
+// the top of its next pass (they were issued a whole pass earlier, so the wait is free) and hands their slots
+// back one pass sooner than the measured kernel, which releases them when the next pass commits — i.e., with
+// two passes per position, only at the end of the position, so that most target rows of position p+1 cannot even
+// be requested before position p is finished.  The measured kernel (OPT = 0) treats any non-zero value as 1.
+template <int OPT>
+__device__ __forceinline__ bool ring_serial(const TrainParams &p) { return OPT ? p.serial == 1 : p.serial != 0; }
+
 // OPT = 0: the kernel measured in round 1.  OPT = 1 (cfg.kernel = 2): same protocol
 // and arithmetic, fewer instructions on the consumer warps' critical path — slot / group indices without
 // integer division (the signed / and % by run-time nv and G cost ~100 SASS instructions per 2-row batch in
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 3
       const int b = mod_small(r1, (unsigned)W);
       // descriptor slot: free once every consumer is done with position q - kND
       const int slot = q % kND;
-      while (q - ctl->prog >= (p.serial ? 1 : kND)) __nanosleep(p.sleep_ns);
+      while (q - ctl->prog >= (ring_serial<OPT>(p) ? 1 : kND)) __nanosleep(p.sleep_ns);
       RingDesc *d = &desc[slot];
       const int center = len ? s_sen[sp] : -1;
       int cw = 0;
@@ -555,6 +564,19 @@ __global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 3
         // LPR < 32: a unit may have no row at all in the warp's last batch; it then re-reads the row of the
         // warp's first unit (i0w < nt) and, like every lane, waits for that row's barrier before touching it
         const int ifall = (LPR == 32) ? i0 : (i0 < nt ? i0 : i0w);
+        if constexpr (OPT) {
+          if (p.serial == 2 && leader) {  // early release of the previous pass's slots (see ring_serial)
+            bool any = false;
+#pragma unroll
+            for (int t = 0; t < R; ++t) any |= prev[t] >= 0;
+            if (any) {
+              bulk_wait_read<0>();
+#pragma unroll
+              for (int t = 0; t < R; ++t)
+                if (prev[t] >= 0) { s_rc[prev[t]] = s_rc[prev[t]] + 1; prev[t] = -1; }
+            }
+          }
+        }
         int sl[R];
         unsigned row[R];
         bool have[R];
@@ -634,13 +656,13 @@ __global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 3
           for (int t = 0; t < R; ++t)
             if (have[t]) bulk_reduce_add(p.v + (long long)d->tg[i0 + t * nunits] * p.D, row[t], rowb);
           bulk_commit();
-          if (p.serial) bulk_wait_all(); else bulk_wait_read<1>();
+          if (ring_serial<OPT>(p)) bulk_wait_all(); else bulk_wait_read<1>();
           // everything this lane committed before the group above has left shared memory
 #pragma unroll
           for (int t = 0; t < R; ++t) {
             if (prev[t] >= 0) s_rc[prev[t]] = s_rc[prev[t]] + 1;
             prev[t] = have[t] ? sl[t] : -1;
-            if (p.serial && have[t]) { s_rc[sl[t]] = s_rc[sl[t]] + 1; prev[t] = -1; }
+            if (ring_serial<OPT>(p) && have[t]) { s_rc[sl[t]] = s_rc[sl[t]] + 1; prev[t] = -1; }
           }
         }
         __syncwarp();
@@ -681,7 +703,7 @@ __global__ void __launch_bounds__((((NJ * LPR + 31) / 32 < 4 ? 4 : (NJ * LPR + 3
       if (warp == 0)  // reported loss (:480-483): one lane per target, off the row loop's critical path
         for (int k = lane; k < nt; k += 32) loss += (double)logf(sigmoid_report(sf[k]));
       if (issuer) { pend_u = d; pend_q = q; }
-      if (p.serial) {  // parity aid: everything of this position lands before the next one is fetched
+      if (ring_serial<OPT>(p)) {  // parity aid: everything of this position lands before the next one is fetched
         consumer_bar(nct);
         if (issuer) {
           const unsigned eb = errbuf + (unsigned)(q & 1) * rowb;
