@@ -45,12 +45,12 @@ class EmuError(RuntimeError):
 
 def train_epoch(corpus, table, u, v, *, size, window, negative, bitlevel, shards, kernel=0, serial=0, alpha=0.05,
                 sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                plan_override=None):
+                plan_override=None, group=0, ring_rows=0):
     """One pass of every shard (one CTA after another) through the emulated ring kernel variant `kernel`
     (cfg.kernel numbering).  u, v are updated in place.  Returns a dict of per-shard statistics; `state` carries
     (alpha, word_count_actual) across epochs."""
     plan = w2b.ring_plan(size=size, window=window, negative=negative, bitlevel=bitlevel, kernel=kernel,
-                         vocab_size=corpus.vocab_size)
+                         vocab_size=corpus.vocab_size, group=group, ring_rows=ring_rows)
     if not plan["ring"]:
         raise EmuError("the ring kernel does not apply to this shape")
     plan.update(plan_override or {})

@@ -64,11 +64,14 @@ def test_variants_against_the_default_kernel(D, W, neg, b, S, tiny):
     c, o, table = tiny
     u0, v0, base = _run(c, table, D, W, neg, b, S, 0, serial=1)
     for kernel in (2, 3, 4, 5):
-        u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=1)
+        # same ring depth as the default (the variants' planner takes a deeper ring when shared memory allows;
+        # with positions longer than the ring the depth decides whether a duplicate target sees the earlier update)
+        u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=1, ring_rows=base["plan"]["v_rows"])
         for k in ("n_pos", "n_ctx", "n_tgt", "words"):
             assert out[k].tolist() == base[k].tolist(), (kernel, k)
         assert (out["wca"], np.float32(out["alpha"])) == (base["wca"], np.float32(base["alpha"]))
-        same_order = out["plan"]["units_per_warp"] == 1 and out["plan"]["consumer_warps"] == base["plan"]["consumer_warps"]
+        same_order = out["plan"]["units_per_warp"] == 1 and out["plan"]["consumer_warps"] == base["plan"]["consumer_warps"] \
+            and out["plan"]["v_rows"] == base["plan"]["v_rows"]
         if same_order:
             assert np.array_equal(u, u0) and np.array_equal(v, v0) and out["loss"].tolist() == base["loss"].tolist(), kernel
         else:
@@ -142,7 +145,8 @@ def test_early_release_mode(kernel, tiny):
     c, o, table = tiny
     D, W, neg, b, S = (800, 10, 24, 1, 2) if kernel == 5 else (200, 8, 63, 1, 2)
     u0, v0, base = _run(c, table, D, W, neg, b, S, kernel, serial=0, async_mode=2, seed=4)
-    u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=2, async_mode=2, seed=4)
-    for k in ("n_pos", "n_ctx", "n_tgt", "words"):
-        assert out[k].tolist() == base[k].tolist()
-    assert abs(out["loss"].sum() - base["loss"].sum()) <= 0.02 * abs(base["loss"].sum())
+    for group in (0, 7):  # 7: the landing-group size the model favours with early release at the C2 shape
+        u, v, out = _run(c, table, D, W, neg, b, S, kernel, serial=2, async_mode=2, seed=4, group=group)
+        for k in ("n_pos", "n_ctx", "n_tgt", "words"):
+            assert out[k].tolist() == base[k].tolist()
+        assert abs(out["loss"].sum() - base["loss"].sum()) <= 0.02 * abs(base["loss"].sum())

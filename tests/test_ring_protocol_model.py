@@ -160,12 +160,13 @@ def test_early_release_mode_is_live_and_safe(kernel):
     for D in (64, 200, 400, 800):
         for window in (2, 10):
             for negative in (5, 24, 63):
-                p = w2b.ring_plan(size=D, window=window, negative=negative, kernel=kernel)
-                if not p["ring"]:
-                    continue
-                n += 1
-                for style in ("typical", "extreme", "any"):
-                    rng = random.Random(n)
-                    pos = random_positions(rng, 16, window, negative, style)
-                    RingModel(p, window, negative, pos, seed=n, early_release=True).run()
-    assert n >= 20
+                for group in (0, 7):
+                    p = w2b.ring_plan(size=D, window=window, negative=negative, kernel=kernel, group=group)
+                    if not p["ring"]:
+                        continue
+                    n += 1
+                    for style in ("typical", "extreme", "any"):
+                        rng = random.Random(n)
+                        pos = random_positions(rng, 16, window, negative, style)
+                        RingModel(p, window, negative, pos, seed=n, early_release=True).run()
+    assert n >= 40

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/variants.md")
     ap.add_argument("--shapes", default="c2,c3,c4,d200,d100")
     ap.add_argument("--kernels", default="0,2,3,4,5")
+    ap.add_argument("--groups", default="0,7", help="landing-group sizes to try with the variants (0 = default 13)")
     ap.add_argument("--vocab", type=int, default=400000)
     ap.add_argument("--tokens", type=int, default=40_000_000)
     ap.add_argument("--words", type=int, default=16384)
@@ -49,9 +50,11 @@ def main():
             base = w2b.ring_plan(size=D, window=W, negative=neg, bitlevel=b, kernel=2, vocab_size=a.vocab + 1)
             if kernel >= 3 and (lpr, plan["consumer_warps"]) == (32, base["consumer_warps"]):
                 continue  # variant does not apply to this width: it would repeat kernel 2
-            for release in ((0,) if kernel < 2 else (0, 2)):  # ring_serial 2 = early slot release (variants only)
+            combos = [(0, 0)] if kernel < 2 else [(r, g) for r in (0, 2) for g in [int(x) for x in a.groups.split(",")]
+                                                  if not (r == 0 and g)]  # other group sizes only with early release
+            for release, group in combos:  # ring_serial 2 = early slot release (variants only)
                 t = w2b.Trainer(None, vocab_size=a.vocab + 1, size=D, window=W, negative=neg, bitlevel=b, iter=1,
-                                threads=None, kernel=kernel, ring_serial=release)
+                                threads=None, kernel=kernel, ring_serial=release, group=group)
                 S = t.threads
                 t.set_vocab_counts(cn, int(a.tokens))
                 t.set_corpus(ids, np.arange(S, dtype=np.int64) * (a.tokens // S), np.full(S, -1, np.int32), True)
@@ -64,7 +67,7 @@ def main():
                 t.close()
                 gbs = rows_ * D * 4 * 2 / 1e9 / (ms / 1e3)
                 line = "| %s D=%d neg=%d b=%d | %d | %s | %d | %d | %d | %.2f M | %.0f | %.3f | %.4f |" % (
-                    name, D, neg, b, kernel, "early" if release == 2 else "at commit", lpr, plan["consumer_warps"], S,
+                    name, D, neg, b, kernel, ("early, G=%d" % (group or 13)) if release == 2 else "at commit", lpr, plan["consumer_warps"], S,
                     pos / ms / 1e3, gbs, gbs / pk, loss / max(pos, 1))
                 print(line, flush=True)
                 rows.append(line)

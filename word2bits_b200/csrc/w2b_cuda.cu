@@ -284,6 +284,9 @@ static void plan_ring(w2b_ctx *c) {
     const size_t cap = (size_t)(227 * 1024) / k - 1024;
     int cand = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
     if (upw > 1) cand = std::max(cand, nv_min);  // many row units: the bound can exceed four groups
+    // variants: the ring depth is what hides the latency of the next position's rows (profiles/
+    // r01_static_sass_variants.md); do not tie it to the group size — take what the share of shared memory holds
+    if (c->cfg.kernel >= 2 && c->cfg.ring_rows <= 0) cand = std::max(cand, std::min(96, 2 * nt + G));
     while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
     if (cand >= (k > 1 ? nv_good : nv_min)) nv = cand;
   }
@@ -292,6 +295,7 @@ static void plan_ring(w2b_ctx *c) {
     const size_t cap = (size_t)(227 * 1024) - 1024;
     int cand = 4 * G;
     if (upw > 1) cand = std::max(cand, nv_min);
+    if (c->cfg.kernel >= 2) cand = std::max(cand, std::min(96, 2 * nt + G));
     while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
     if (cand < nv_min) return;
     nv = cand;
