@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of a round (run through gpurun from the repo root):
-#   gpurun --timeout 3000 -- 'bash tools/first_gpu_call.sh'
+#   gpurun --timeout 4500 -- 'bash tools/first_gpu_call.sh'
 # 1. the opt-in tests of the experimental ring-kernel variants (cfg.kernel 2..5), each pytest under its own
 #    timeout so that a wedged kernel ends the step instead of the box;
 # 2. the A/B sweep of the variants against the measured default on the BASELINE shapes (CUDA events);
@@ -14,7 +14,7 @@ for v in 2 5 3 4; do
     > gpurun_out/variant_tests_k$v.log 2>&1
   echo "variant $v tests: exit $?" | tee -a gpurun_out/first_call_summary.txt
 done
-timeout 900 python tools/variant_sweep.py --out gpurun_out/variants.md > gpurun_out/variant_sweep.log 2>&1
+timeout 1500 python tools/variant_sweep.py --out gpurun_out/variants.md > gpurun_out/variant_sweep.log 2>&1
 echo "variant sweep: exit $?" | tee -a gpurun_out/first_call_summary.txt
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 echo "bench: exit $?" | tee -a gpurun_out/first_call_summary.txt
