@@ -278,7 +278,10 @@ static void plan_ring(w2b_ctx *c) {
   // (with several units per warp the batch a unit waits for also holds its warp-mates' rows: + upw - 1)
   const int nv_min = std::max(2 * G, std::min((2 * R - 1) * nunits + G + upw, nt));
   const int nv_good = std::max(nv_min, (5 * G + 1) / 2);
-  int nu = 2 * c->cfg.window + 4;
+  // u-ring: one full window plus slack in the measured kernel.  The variants keep exactly one window (the
+  // largest cw): the rows of position p+1 that do not fit are requested at p's barrier A, a whole target phase
+  // before they are needed, and the four rows go to the v-ring, whose depth is what hides latency
+  int nu = c->cfg.kernel >= 2 ? 2 * c->cfg.window : 2 * c->cfg.window + 4;
   int nv = 0;
   for (int k = 4; k >= 1 && !nv; --k) {
     const size_t cap = (size_t)(227 * 1024) / k - 1024;
