@@ -350,3 +350,19 @@ def test_text_writer_parallel_and_cached_formatting(tmp_path, monkeypatch):
     for a in (0, 1, 2, 77, V - 1):
         want = words[a].encode("latin1") + b" " + b"".join(b"%f " % float(x) for x in vec[a])
         assert lines[1 + a] == want, a
+
+
+def test_default_kernels_are_the_measured_binary():
+    """profiles/r01_sass_fingerprints_measured_build.json holds a fingerprint (instruction text, labels renumbered)
+    of every kernel of the build whose numbers are in profiles/ (commit 3b82bf5).  Variants were added to the
+    production kernel's template afterwards; the OPT = 0, LPR = 32, XW = 0 instantiations — what cfg.kernel = 0 runs —
+    must still be that machine code, instruction for instruction, until a new default has been measured."""
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("CUDA toolkit not on PATH")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_fingerprint.py"), LIB, "--compare",
+                        os.path.join(ROOT, "profiles", "r01_sass_fingerprints_measured_build.json"), "--map",
+                        "ELi2EEEvNS_11TrainParamsEiii=ELi2ELi0ELi32ELi0EEEvNS_11TrainParamsEiii"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "72 kernels compared, 0 differ" in r.stdout, r.stdout[-2000:] + r.stderr[-500:]
