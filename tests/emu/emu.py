@@ -26,7 +26,8 @@ class EmuRun(C.Structure):
                 ("seed", C.c_uint64), ("async_mode", C.c_int32), ("train", C.c_int32),
                 ("loss", C.c_void_p), ("words", C.c_void_p), ("n_pos", C.c_void_p), ("n_ctx", C.c_void_p),
                 ("n_tgt", C.c_void_p), ("done", C.c_void_p),
-                ("trace", C.c_void_p), ("trace_cap", C.c_int64), ("trace_n", C.c_void_p), ("only_shard", C.c_int32)]
+                ("trace", C.c_void_p), ("trace_cap", C.c_int64), ("trace_n", C.c_void_p), ("only_shard", C.c_int32),
+                ("fault", C.c_int32)]
 
 
 def lib():
@@ -45,7 +46,7 @@ class EmuError(RuntimeError):
 
 def train_epoch(corpus, table, u, v, *, size, window, negative, bitlevel, shards, kernel=0, serial=0, alpha=0.05,
                 sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                plan_override=None, group=0, ring_rows=0):
+                plan_override=None, group=0, ring_rows=0, fault=0):
     """One pass of every shard (one CTA after another) through the emulated ring kernel variant `kernel`
     (cfg.kernel numbering).  u, v are updated in place.  Returns a dict of per-shard statistics; `state` carries
     (alpha, word_count_actual) across epochs."""
@@ -77,7 +78,8 @@ def train_epoch(corpus, table, u, v, *, size, window, negative, bitlevel, shards
                loss=p(out["loss"]), words=p(out["words"]), n_pos=p(out["n_pos"]), n_ctx=p(out["n_ctx"]),
                n_tgt=p(out["n_tgt"]), done=p(out["done"]),
                trace=C.cast(trace, C.c_void_p) if trace_cap else None, trace_cap=trace_cap,
-               trace_n=p(trace_n) if trace_cap else None, only_shard=-1 if trace_shard is None else trace_shard)
+               trace_n=p(trace_n) if trace_cap else None, only_shard=-1 if trace_shard is None else trace_shard,
+               fault=fault)
     rc = lib().emu_run_ring(C.byref(r))
     if rc:
         raise EmuError(lib().emu_last_error().decode())

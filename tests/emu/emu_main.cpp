@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <random>
 #include <vector>
 
@@ -52,6 +53,7 @@ struct Fiber {
   bool done = false;
   std::vector<BulkOp> open;
   std::vector<std::vector<BulkOp>> groups;
+  std::vector<unsigned> unfenced;  // 16-byte chunks this thread stored to since its last fence.proxy.async
 };
 constexpr size_t kStack = 256 * 1024;
 std::vector<Fiber> g_fib;
@@ -60,6 +62,7 @@ int g_cur = -1;
 void (*g_entry)() = nullptr;
 std::mt19937_64 g_rng;
 int g_async_mode = 0;
+int g_fault = 0;  // negative controls of the checkers: 1 = fence.proxy.async dropped, 2 = wait_group.read returns early
 const char *g_error = nullptr;
 unsigned long long g_progress = 0;  // bumped by everything except spinning: lets the scheduler tell a dead-lock from work
 
@@ -76,6 +79,19 @@ void fail(const char *msg) {
   if (!g_error) g_error = msg;
 }
 
+// planned carve-up of the running CTA (ring_layout of the launch geometry): bounds of the checked accesses
+size_t g_smem_total = sizeof(w2b::smem), g_rows_end = 0, g_ring_end = 0;
+unsigned g_rowb = 0;
+// per 16-byte chunk: 1 + id of the thread whose generic-proxy store has not been fenced yet (0 = none)
+std::vector<unsigned short> g_unfenced(sizeof(w2b::smem) / 16, 0);
+// per row of the row regions: bulk reduces issued or committed whose source it is and that have not executed
+std::vector<int> g_pending_rows;
+void pending_rows_add(const BulkOp &op, int delta) {
+  if (!g_rowb) return;
+  for (unsigned r = op.src_off / g_rowb; r <= (op.src_off + op.bytes - 1) / g_rowb && r < g_pending_rows.size(); ++r)
+    g_pending_rows[r] += delta;
+}
+
 void fiber_trampoline() {
   g_entry();
   g_fib[g_cur].done = true;
@@ -88,6 +104,7 @@ void make_fiber(Fiber &f) {
   f.done = false;
   f.open.clear();
   f.groups.clear();
+  f.unfenced.clear();
   // initial frame: six callee-saved registers, then the return address of emu_switch's `ret`; the stack is
   // 16-byte aligned at the trampoline's entry as the ABI wants after a call
   void **top = (void **)(f.stack + kStack - 64);
@@ -113,6 +130,7 @@ void exec_group(std::vector<BulkOp> &g) {
   for (const BulkOp &op : g) {  // the source is read NOW: whatever the slot holds at this moment is what gets added
     const float *src = (const float *)(w2b::smem + op.src_off);
     for (unsigned i = 0; i < op.bytes / 4; ++i) op.dst[i] += src[i];
+    pending_rows_add(op, -1);
   }
   g.clear();
 }
@@ -159,7 +177,42 @@ void emu_block_barrier(int id, int nthreads) {
 }
 
 namespace w2b {
+void emu_check_smem(unsigned off, unsigned bytes, const char *what) {
+  static char msg[160];
+  if (g_error) return;  // keep the first report
+  if ((size_t)off + bytes > g_smem_total) {
+    snprintf(msg, sizeof msg, "%s at shared offset %u (+%u) beyond the planned %zu bytes", what, off, bytes, g_smem_total);
+    fail(msg);
+  } else if (off < g_rows_end && g_rowb && off % g_rowb + bytes > g_rowb) {
+    snprintf(msg, sizeof msg, "%s at shared offset %u (+%u) crosses a row boundary (rows of %u bytes)", what, off, bytes, g_rowb);
+    fail(msg);
+  }
+}
+static bool pending_reduce_reads(unsigned off, unsigned bytes) {  // issued or committed, not yet executed
+  if (!g_rowb || off >= g_rows_end) return false;
+  for (unsigned r = off / g_rowb; r <= (off + bytes - 1) / g_rowb && r < g_pending_rows.size(); ++r)
+    if (g_pending_rows[r] > 0) return true;
+  return false;
+}
+void emu_generic_store(unsigned off, unsigned bytes) {
+  if (g_error) return;
+  if (pending_reduce_reads(off, bytes)) { fail("store into the source of a bulk reduce that has not been confirmed read (wait_group.read)"); return; }
+  Fiber &f = g_fib[g_cur];
+  for (unsigned c = off / 16; c <= (off + bytes - 1) / 16; ++c) {
+    g_unfenced[c] = (unsigned short)(g_cur + 1);
+    f.unfenced.push_back(c);
+  }
+}
+void emu_fence_async() {
+  if (g_fault == 1) return;
+  Fiber &f = g_fib[g_cur];
+  for (unsigned c : f.unfenced)
+    if (g_unfenced[c] == (unsigned short)(g_cur + 1)) g_unfenced[c] = 0;
+  f.unfenced.clear();
+}
 void emu_mbar_init(unsigned off, int count) {
+  emu_check_smem(off, 8, "mbarrier.init");
+  if (off < g_rows_end) fail("mbarrier inside the row regions");
   MBar &m = g_mbar[off / 8];
   m = MBar();
   m.count = m.pending = count;
@@ -180,14 +233,23 @@ bool emu_mbar_try_wait(unsigned off, unsigned parity) {
 }
 void emu_bulk_load(unsigned dst_off, const void *src, unsigned bytes, unsigned bar_off) {
   if (bytes % 16 || dst_off % 16 || ((uintptr_t)src) % 16) fail("bulk copy operands must be 16-byte aligned");
+  emu_check_smem(dst_off, bytes, "cp.async.bulk (load)");
+  emu_check_smem(bar_off, 8, "cp.async.bulk mbarrier");
+  if (dst_off >= g_ring_end || dst_off % g_rowb || bytes != g_rowb) fail("bulk load is not one whole row into a ring slot");
+  if (pending_reduce_reads(dst_off, bytes)) fail("bulk load into the source of a bulk reduce that has not been confirmed read");
   Load l{dst_off, bytes, bar_off, src};
   if (g_async_mode == 0) land(l);
   else g_loads.push_back(l);
 }
 void emu_bulk_reduce_add(void *dst, unsigned src_off, unsigned bytes) {
   if (bytes % 16 || src_off % 16 || ((uintptr_t)dst) % 16) fail("bulk reduce operands must be 16-byte aligned");
+  emu_check_smem(src_off, bytes, "cp.reduce.async.bulk");
+  if (src_off >= g_rows_end) fail("bulk reduce source outside the row regions");
+  for (unsigned c = src_off / 16; c < (src_off + bytes) / 16 && !g_error; ++c)
+    if (g_unfenced[c]) fail("bulk reduce reads bytes stored through the generic proxy without the storing thread's fence.proxy.async");
   ++g_progress;
   g_fib[g_cur].open.push_back(BulkOp{(float *)dst, src_off, bytes});
+  pending_rows_add(g_fib[g_cur].open.back(), +1);
 }
 void emu_bulk_commit() {
   Fiber &f = g_fib[g_cur];
@@ -195,6 +257,7 @@ void emu_bulk_commit() {
   f.open.clear();
 }
 void emu_bulk_wait(int keep) {
+  if (g_fault == 2) return;
   Fiber &f = g_fib[g_cur];
   while ((int)f.groups.size() > keep) {
     exec_group(f.groups.front());
@@ -212,6 +275,8 @@ bool run_block(int nthreads, void (*entry)()) {
   g_warp.assign((nthreads + 31) / 32, WarpX());
   for (auto &b : g_bar) b = BlockBar();
   for (auto &m : g_mbar) m = MBar();
+  std::fill(g_unfenced.begin(), g_unfenced.end(), 0);
+  g_pending_rows.assign(g_rowb ? g_rows_end / g_rowb + 1 : 0, 0);
   g_loads.clear();
   for (int t = 0; t < nthreads; ++t) make_fiber(g_fib[t]);
   blockDim.x = nthreads;
@@ -310,15 +375,28 @@ struct EmuRun {
   int64_t trace_cap;
   uint64_t *trace_n;
   int32_t only_shard;  // >= 0: run just this shard
+  int32_t fault;       // 0; 1 / 2: injected protocol faults (negative controls, see g_fault)
 };
 
 const char *emu_last_error() { return g_error ? g_error : ""; }
+
+// negative control of the shared-memory checks: would an access of `bytes` at `off` be reported under the
+// carve-up of the last run?  (returns the planned total through *total)
+int emu_check_probe(unsigned off, unsigned bytes, uint64_t *total) {
+  g_error = nullptr;
+  w2b::emu_check_smem(off, bytes, "probe");
+  if (total) *total = g_smem_total;
+  const int bad = g_error != nullptr;
+  g_error = nullptr;
+  return bad;
+}
 
 int emu_run_ring(const EmuRun *r) {
   using namespace w2b;
   g_error = nullptr;
   g_rng.seed(r->seed);
   g_async_mode = r->async_mode;
+  g_fault = r->fault;
   // LCG jump tables (csrc/w2b_cuda.cu: lcg_tables)
   c_JA[0] = 1; c_JC[0] = 0;
   for (int k = 1; k <= 64; ++k) { c_JA[k] = c_JA[k - 1] * kLcgA; c_JC[k] = c_JC[k - 1] * kLcgA + kLcgC; }
@@ -358,6 +436,14 @@ int emu_run_ring(const EmuRun *r) {
   p.plain_store = 0; p.serial = r->serial; p.sleep_ns = 0; p.wca_scale = 1;
   p.trace = r->trace; p.trace_cap = r->trace_cap; p.trace_n = (unsigned long long *)r->trace_n;
   g_p = p; g_nu = r->nu; g_nv = r->nv; g_G = r->G;
+  {
+    const RingLayout L = ring_layout(r->D, r->nu, r->nv, r->threads / 32 - 2);
+    if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }
+    g_smem_total = L.total;
+    g_rows_end = L.off_rc;    // rows of 4*D bytes from offset 0: u-ring, v-ring, staging, context_avg, partials
+    g_ring_end = L.off_err;   // ... of which the two rings take bulk loads
+    g_rowb = (unsigned)L.rowb;
+  }
   gridDim.x = r->num_shards;
   for (int b = 0; b < r->num_shards; ++b) {
     if (r->only_shard >= 0 && b != r->only_shard) continue;

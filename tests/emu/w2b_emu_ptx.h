@@ -13,6 +13,15 @@ void emu_bulk_load(unsigned dst_off, const void *src, unsigned bytes, unsigned b
 void emu_bulk_reduce_add(void *dst, unsigned src_off, unsigned bytes);
 void emu_bulk_commit();
 void emu_bulk_wait(int keep_groups);
+// every checked shared-memory access lies inside the planned carve-up and, in the row-structured regions
+// (u-ring, v-ring, staging rows, context_avg, error partials), inside ONE row: a column index that runs past
+// the row would read or clobber the neighbouring slot on the GPU without any fault
+void emu_check_smem(unsigned off, unsigned bytes, const char *what);
+// cross-proxy rules of the bulk (TMA) engine, which reads and writes shared memory through the async proxy:
+// a generic-proxy store must be followed by the storing thread's fence.proxy.async before a bulk reduce may
+// read those bytes, and nothing may overwrite the source of a bulk reduce that has not been confirmed read
+void emu_generic_store(unsigned off, unsigned bytes);
+void emu_fence_async();
 
 inline unsigned smem_u32(const void *p) { return (unsigned)((const unsigned char *)p - smem); }
 inline void mbar_init(unsigned long long *bar, int count) { emu_mbar_init(smem_u32(bar), count); }
@@ -28,11 +37,16 @@ inline void bulk_commit() { emu_bulk_commit(); }
 template <int N>
 inline void bulk_wait_read() { emu_bulk_wait(N); }
 inline void bulk_wait_all() { emu_bulk_wait(0); }
-inline void fence_async_smem() {}
+inline void fence_async_smem() { emu_fence_async(); }
 inline void consumer_bar(int nthreads) { emu_block_barrier(1, nthreads); }
 inline float4 lds128(unsigned addr) {
   float4 v;
+  emu_check_smem(addr, 16, "ld.shared.v4");
   memcpy(&v, smem + addr, sizeof v);
   return v;
 }
-inline void sts128(unsigned addr, float4 v) { memcpy(smem + addr, &v, sizeof v); }
+inline void sts128(unsigned addr, float4 v) {
+  emu_check_smem(addr, 16, "st.shared.v4");
+  emu_generic_store(addr, 16);
+  memcpy(smem + addr, &v, sizeof v);
+}

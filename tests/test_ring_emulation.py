@@ -138,6 +138,40 @@ def test_emulator_detects_a_ring_that_is_too_small(tiny):
                         plan_override=dict(v_rows=20))
 
 
+def test_emulator_checks_shared_memory_accesses(tiny):
+    """Every ld/st.shared.v4, bulk copy, bulk reduce and mbarrier of the emulated kernels is checked against the
+    planned carve-up: inside the planned bytes, and inside one row in the row-structured regions (a column index
+    past the end of a row reads or clobbers the neighbouring ring slot on the GPU without a fault).  All the tests
+    in this file run with the checks on; this is their negative control."""
+    import ctypes as C
+    c, o, table = tiny
+    u, v = po.init_net(c.vocab_size, 100)
+    out = emu.train_epoch(c, table, u, v, size=100, window=5, negative=5, bitlevel=1, shards=1, kernel=2)
+    total = C.c_uint64()
+    probe = emu.lib().emu_check_probe
+    probe.argtypes = [C.c_uint, C.c_uint, C.POINTER(C.c_uint64)]
+    assert probe(384, 16, C.byref(total)) == 0 and total.value == out["plan"]["smem_bytes"]
+    assert probe(392, 16, None) == 1                       # rows of 400 bytes: crosses into the next slot
+    rows = (out["plan"]["u_rows"] + out["plan"]["v_rows"] + 3 + out["plan"]["consumer_warps"]) * 400
+    assert probe(rows - 16, 16, None) == 0 and probe(rows + 8, 16, None) == 0   # control words: no row rule
+    assert probe(total.value - 8, 16, None) == 1           # beyond the planned size
+
+
+@pytest.mark.parametrize("kernel", [0, 2, 4])
+def test_emulator_checks_the_async_proxy_rules(kernel, tiny):
+    """The bulk (TMA) engine reads shared memory through the async proxy.  Checked on every emulated run: (1) bytes
+    stored with st.shared are covered by the storing thread's fence.proxy.async before a bulk reduce is issued on
+    them; (2) nothing — neither a store nor a bulk load — overwrites the source row of a bulk reduce before a
+    wait_group.read of its issuer has confirmed it.  Negative controls: with the fences dropped, and with
+    wait_group.read returning early, the run is reported instead of passing."""
+    c, o, table = tiny
+    for fault, msg in ((1, "fence.proxy.async"), (2, "not been confirmed read")):
+        u, v = po.init_net(c.vocab_size, 200)
+        with pytest.raises(emu.EmuError, match=msg):
+            emu.train_epoch(c, table, u, v, size=200, window=8, negative=24, bitlevel=1, shards=1, kernel=kernel,
+                            async_mode=2, seed=3, fault=fault)
+
+
 @pytest.mark.parametrize("kernel", [2, 3, 4, 5])
 def test_early_release_mode(kernel, tiny):
     """TrainParams::serial == 2 (variant kernels): prefetching with the slots of a pass released at the top of
