@@ -333,7 +333,9 @@ entry_fn by_nj(int nj) {
     case 3: return entry<BM, 3, OPT, LPR, XW>;
     case 4: return entry<BM, 4, OPT, LPR, XW>;
     case 5: return entry<BM, 5, OPT, LPR, XW>;
+    case 6: return entry<BM, 6, OPT, LPR, XW>;
     case 7: return entry<BM, 7, OPT, LPR, XW>;
+    case 8: return entry<BM, 8, OPT, LPR, XW>;
   }
   return nullptr;
 }
