@@ -366,3 +366,41 @@ def test_default_kernels_are_the_measured_binary():
                         "ELi2EEEvNS_11TrainParamsEiii=ELi2ELi0ELi32ELi0EEEvNS_11TrainParamsEiii"],
                        capture_output=True, text=True)
     assert r.returncode == 0 and "72 kernels compared, 0 differ" in r.stdout, r.stdout[-2000:] + r.stderr[-500:]
+
+
+def _vector_file(path, words, D, seed=0):
+    rng = np.random.default_rng(seed)
+    with open(path, "wb") as f:
+        f.write(b"%d %d\n" % (len(words), D))
+        for w in words:
+            f.write(w.encode() + b" " + rng.standard_normal(D).astype(np.float32).tobytes() + b"\n")
+
+
+def test_evaluator_host_side_errors_and_empty_report(tmp_path):
+    """w2b_compute_accuracy before any GPU work: bad arguments and unreadable / hostile vector files
+    are error codes, never crashes or exceptions across the C ABI; a question stream in which no question can be
+    answered (every line has an out-of-vocabulary word) needs no device and prints what src/compute-accuracy.c prints."""
+    import ctypes as C
+    import word2bits_b200 as w2b
+    from word2bits_b200._lib import lib, EINVAL
+    acc = w2b._lib.Accuracy()
+    buf = C.create_string_buffer(4096)
+    qf = tmp_path / "q.txt"
+    qf.write_text(": capital-common-countries\nathens greece baghdad iraq\nzzz yyy xxx www\n: family\nboy girl zzz sister\n")
+    call = lambda vf: lib.w2b_compute_accuracy(vf, 0, 0, str(qf).encode(), 0, C.byref(acc), buf, len(buf))
+    assert call(None) == EINVAL
+    assert call(str(tmp_path / "missing.bin").encode()) == 3 and b"not found" in lib.w2b_last_error()
+    for name, content in (("text.bin", b"hello world\n"), ("neg.bin", b"-5 10\n"), ("zero.bin", b"10 0\n"),
+                          ("huge.bin", b"999999999999 999999\n"), ("big.bin", b"2000000000 1000000\n"),
+                          ("short.bin", b"3 8\nathens " + b"\0" * 32 + b"\ngreece " + b"\0" * 7)):
+        p = tmp_path / name
+        p.write_bytes(content)
+        assert call(str(p).encode()) == 3, name  # W2B_EIO
+    vf = str(tmp_path / "vec.bin")
+    _vector_file(vf, ["athens", "greece", "baghdad", "boy", "girl", "sister"], 8)
+    got, counters = w2b.compute_accuracy(vf, str(qf))
+    assert counters["questions_total"] == 3 and counters["questions_seen"] == 0 and counters["gpu_ms"] == 0.0
+    refbin = os.path.join(ROOT, "oracle", "_ref", "compute_accuracy")
+    if os.path.exists(refbin):
+        want = subprocess.run([refbin, vf, "0", "0"], stdin=open(qf), capture_output=True, text=True).stdout
+        assert got == want

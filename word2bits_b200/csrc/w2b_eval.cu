@@ -34,6 +34,22 @@ using namespace w2b;
 
 namespace {
 
+// device buffers / events released on every return path
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+struct DevEvent {
+  cudaEvent_t e = nullptr;
+  ~DevEvent() { if (e) cudaEventDestroy(e); }
+};
+struct FileCloser {
+  FILE *f;
+  ~FileCloser() { if (f && f != stdin) fclose(f); }
+};
+
 // quantize (:102) + L2 normalise (:103-106): one warp per row.
 __global__ void eval_normalize_kernel(float *M, long long words, long long D, int bits) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -146,9 +162,15 @@ static int read_vectors(const char *path, long long threshold, std::vector<std::
     w2b_set_error("Input file not found");
     return W2B_EIO;
   }
-  if (fscanf(f, "%lld", &words) != 1) { fclose(f); w2b_set_error("bad header"); return W2B_EIO; }
-  if (threshold && words > threshold) words = threshold;
-  if (fscanf(f, "%lld", &size) != 1) { fclose(f); w2b_set_error("bad header"); return W2B_EIO; }
+  FileCloser closer{f};
+  if (fscanf(f, "%lld", &words) != 1) { w2b_set_error("bad header"); return W2B_EIO; }
+  if (threshold > 0 && words > threshold) words = threshold;
+  if (fscanf(f, "%lld", &size) != 1) { w2b_set_error("bad header"); return W2B_EIO; }
+  // (the reference mallocs words * size floats unchecked; a header this library cannot hold is an error, not a crash)
+  if (words < 1 || size < 1 || words > 0x7fffffffLL || size > (1LL << 20) || words > (1LL << 40) / size) {
+    w2b_set_error("bad header: %lld words of size %lld", words, size);
+    return W2B_EIO;
+  }
   names.resize(words);
   M.resize((size_t)words * size);
   for (long long b = 0; b < words; ++b) {
@@ -160,18 +182,35 @@ static int read_vectors(const char *path, long long threshold, std::vector<std::
     }
     names[b] = upper(w);
     if (fread(&M[(size_t)b * size], sizeof(float), size, f) != (size_t)size) {
-      fclose(f);
       w2b_set_error("vector file truncated at word %lld", b);
       return W2B_EIO;
     }
   }
-  fclose(f);
   return W2B_OK;
 }
 
+static int compute_accuracy_impl(const char *vectors_file, int bitlevel, int64_t threshold,
+                                 const char *questions_file, int device, w2b_accuracy *acc, char *report,
+                                 int64_t report_cap);
 extern "C" int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int64_t threshold,
                                     const char *questions_file, int device, w2b_accuracy *acc, char *report,
                                     int64_t report_cap) {
+  if (!vectors_file) { w2b_set_error("w2b_compute_accuracy: null vectors_file"); return W2B_EINVAL; }
+  if (report && report_cap > 0) report[0] = 0;
+  try {  // nothing is thrown across the C ABI (std::bad_alloc on a huge vocabulary, ...)
+    return compute_accuracy_impl(vectors_file, bitlevel, threshold, questions_file, device, acc, report, report_cap);
+  } catch (const std::exception &ex) {
+    w2b_set_error("w2b_compute_accuracy: %s", ex.what());
+    return W2B_EINVAL;
+  } catch (...) {
+    w2b_set_error("w2b_compute_accuracy: unexpected exception");
+    return W2B_EINVAL;
+  }
+}
+
+static int compute_accuracy_impl(const char *vectors_file, int bitlevel, int64_t threshold,
+                                 const char *questions_file, int device, w2b_accuracy *acc, char *report,
+                                 int64_t report_cap) {
   std::vector<std::string> names;
   std::vector<float> M;
   long long words = 0, size = 0;
@@ -189,9 +228,9 @@ extern "C" int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int6
   if (!qf) { w2b_set_error("questions file not found"); return W2B_EIO; }
   std::vector<std::string> tok;
   {
+    FileCloser closer{qf};
     char buf[2048];
     while (fscanf(qf, "%2000s", buf) == 1) tok.push_back(buf);
-    if (questions_file) fclose(qf);
   }
   struct Ev { int kind; std::string name; long long b1, b2, b3; std::string st4; int qidx; };  // 0 = section, 1 = question
   std::vector<Ev> events;
@@ -232,30 +271,29 @@ extern "C" int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int6
       return W2B_ECUDA;
     }
     CKE(cudaSetDevice(device));
-    float *dM = nullptr, *dQ = nullptr;
-    int *dq3 = nullptr;
-    unsigned long long *dbest = nullptr;
-    CKE(cudaMalloc(&dM, M.size() * sizeof(float)));
-    CKE(cudaMalloc(&dQ, (size_t)nq * size * sizeof(float)));
-    CKE(cudaMalloc(&dq3, q3.size() * sizeof(int)));
-    CKE(cudaMalloc(&dbest, nq * sizeof(unsigned long long)));
+    DevBuf bM, bQ, bq3, bbest;
+    CKE(bM.alloc(M.size() * sizeof(float)));
+    CKE(bQ.alloc((size_t)nq * size * sizeof(float)));
+    CKE(bq3.alloc(q3.size() * sizeof(int)));
+    CKE(bbest.alloc(nq * sizeof(unsigned long long)));
+    float *dM = bM.as<float>(), *dQ = bQ.as<float>();
+    int *dq3 = bq3.as<int>();
+    unsigned long long *dbest = bbest.as<unsigned long long>();
     CKE(cudaMemcpy(dM, M.data(), M.size() * sizeof(float), cudaMemcpyHostToDevice));
     CKE(cudaMemcpy(dq3, q3.data(), q3.size() * sizeof(int), cudaMemcpyHostToDevice));
     CKE(cudaMemset(dbest, 0, nq * sizeof(unsigned long long)));
-    cudaEvent_t e0, e1;
-    CKE(cudaEventCreate(&e0));
-    CKE(cudaEventCreate(&e1));
-    CKE(cudaEventRecord(e0));
+    DevEvent e0, e1;
+    CKE(cudaEventCreate(&e0.e));
+    CKE(cudaEventCreate(&e1.e));
+    CKE(cudaEventRecord(e0.e));
     eval_normalize_kernel<<<(unsigned)((words + 7) / 8), 256>>>(dM, words, size, bitlevel);
     eval_query_kernel<<<(unsigned)((nq * size + 255) / 256), 256>>>(dM, dq3, dQ, nq, size);
     dim3 grid((unsigned)((words + TN - 1) / TN), (unsigned)((nq + TM - 1) / TM));
     eval_score_kernel<<<grid, 256>>>(dQ, dM, dq3, dbest, nq, words, size);
     CKE(cudaGetLastError());
-    CKE(cudaEventRecord(e1));
+    CKE(cudaEventRecord(e1.e));
     CKE(cudaMemcpy(best.data(), dbest, nq * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CKE(cudaEventElapsedTime(&ms, e0, e1));
-    cudaFree(dM); cudaFree(dQ); cudaFree(dq3); cudaFree(dbest);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CKE(cudaEventElapsedTime(&ms, e0.e, e1.e));
   }
 
   // ---- replay the control flow of :113-187 to produce the same report
