@@ -23,6 +23,7 @@ extern "C" {
 #define W2B_EIO 3      /* file not found / unreadable / unwritable */
 #define W2B_ESTATE 4   /* call sequence error (e.g. train before set_corpus) */
 #define W2B_ENCCL 5    /* NCCL error / NCCL not loadable */
+#define W2B_ENOMEM 6   /* host allocation failed (nothing is thrown across the ABI) */
 
 #define W2B_TABLE_SIZE 100000000 /* table_size, :60 */
 #define W2B_MAX_SENTENCE 1000    /* MAX_SENTENCE_LENGTH, :32 */

@@ -9,7 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libw2b.so")
 
-OK, EINVAL, ECUDA, EIO, ESTATE, ENCCL = range(6)
+OK, EINVAL, ECUDA, EIO, ESTATE, ENCCL, ENOMEM = range(7)
 TABLE_SIZE = 100_000_000
 MODE_FAST, MODE_STRICT = 0, 1
 

@@ -464,7 +464,7 @@ extern "C" int w2b_create(const w2b_config *cfg, w2b_ctx **out) {
   *out = nullptr;
   NEED(cfg);
   w2b_ctx *c = nullptr;
-  const int rc = create_impl(cfg, &c);
+  const int rc = w2b_guarded("w2b_create", [&] { return create_impl(cfg, &c); });
   if (rc) {
     const std::string keep = w2b_last_error();  // destroy must not clobber the message
     if (c) w2b_destroy(c);
@@ -555,7 +555,11 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
 }
 
 // ------------------------------------------------------------------------------- tables
+static int w2b_set_vocab_counts_impl(w2b_ctx *c, const int64_t *cn, int64_t V, int64_t train_words);
 extern "C" int w2b_set_vocab_counts(w2b_ctx *c, const int64_t *cn, int64_t V, int64_t train_words) {
+  return w2b_guarded("w2b_set_vocab_counts", [&] { return w2b_set_vocab_counts_impl(c, cn, V, train_words); });
+}
+static int w2b_set_vocab_counts_impl(w2b_ctx *c, const int64_t *cn, int64_t V, int64_t train_words) {
   NEED(c);
   NEED(cn);
   if (V != c->cfg.vocab_size) { w2b_set_error("V mismatch"); return W2B_EINVAL; }
@@ -594,7 +598,13 @@ extern "C" int w2b_init_tables(w2b_ctx *c) {
   return W2B_OK;
 }
 
+static int w2b_set_corpus_impl(w2b_ctx *c, const int32_t *ids, int64_t n, const int64_t *shard_start,
+                              const int32_t *shard_first, int resident);
 extern "C" int w2b_set_corpus(w2b_ctx *c, const int32_t *ids, int64_t n, const int64_t *shard_start,
+                              const int32_t *shard_first, int resident) {
+  return w2b_guarded("w2b_set_corpus", [&] { return w2b_set_corpus_impl(c, ids, n, shard_start, shard_first, resident); });
+}
+static int w2b_set_corpus_impl(w2b_ctx *c, const int32_t *ids, int64_t n, const int64_t *shard_start,
                               const int32_t *shard_first, int resident) {
   NEED(c);
   NEED(shard_start);
@@ -734,7 +744,11 @@ static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
   return W2B_OK;
 }
 
+static int w2b_train_step_impl(w2b_ctx *c, int64_t words_per_shard, w2b_step_stats *stats);
 extern "C" int w2b_train_step(w2b_ctx *c, int64_t words_per_shard, w2b_step_stats *stats) {
+  return w2b_guarded("w2b_train_step", [&] { return w2b_train_step_impl(c, words_per_shard, stats); });
+}
+static int w2b_train_step_impl(w2b_ctx *c, int64_t words_per_shard, w2b_step_stats *stats) {
   NEED(c);
   if (!c->have_corpus || !c->have_tables || !c->have_counts) {
     w2b_set_error("train_step before set_vocab_counts/set_corpus/init_tables");
@@ -823,7 +837,13 @@ extern "C" int w2b_train_epoch(w2b_ctx *c, double *loss, w2b_step_stats *stats) 
 }
 
 // --------------------------------------------------------------------------- parity hooks
+static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trace_rec *out, int64_t cap,
+                         int64_t *n_out);
 extern "C" int w2b_trace(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trace_rec *out, int64_t cap,
+                         int64_t *n_out) {
+  return w2b_guarded("w2b_trace", [&] { return w2b_trace_impl(c, shard, max_iterations, out, cap, n_out); });
+}
+static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_trace_rec *out, int64_t cap,
                          int64_t *n_out) {
   NEED(c);
   NEED(n_out);
@@ -1003,7 +1023,11 @@ struct CkptHeader {
   float alpha;
   int32_t pad;
 };
+static int w2b_checkpoint_save_impl(w2b_ctx *c, const char *path, int64_t epochs_done);
 extern "C" int w2b_checkpoint_save(w2b_ctx *c, const char *path, int64_t epochs_done) {
+  return w2b_guarded("w2b_checkpoint_save", [&] { return w2b_checkpoint_save_impl(c, path, epochs_done); });
+}
+static int w2b_checkpoint_save_impl(w2b_ctx *c, const char *path, int64_t epochs_done) {
   NEED(c);
   NEED(path);
   CK(cudaSetDevice(c->cfg.device));
@@ -1035,7 +1059,11 @@ extern "C" int w2b_checkpoint_save(w2b_ctx *c, const char *path, int64_t epochs_
   return W2B_OK;
 }
 
+static int w2b_checkpoint_load_impl(w2b_ctx *c, const char *path, int64_t *epochs_done);
 extern "C" int w2b_checkpoint_load(w2b_ctx *c, const char *path, int64_t *epochs_done) {
+  return w2b_guarded("w2b_checkpoint_load", [&] { return w2b_checkpoint_load_impl(c, path, epochs_done); });
+}
+static int w2b_checkpoint_load_impl(w2b_ctx *c, const char *path, int64_t *epochs_done) {
   NEED(c);
   NEED(path);
   CK(cudaSetDevice(c->cfg.device));

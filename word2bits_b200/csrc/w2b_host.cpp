@@ -108,7 +108,15 @@ void w2b_gather_slices(const int32_t *ids, long long n_tokens, long long L, int 
   for (auto &x : th) x.join();
 }
 
+static int w2b_host_gather_slices_impl(const int32_t *ids, int64_t n_tokens, int64_t L, int nshards, const int64_t *cursor,
+                                      const int32_t *done, int32_t *stage, int64_t *xlate, int64_t *limit,
+                                      int32_t *limit_is_eof, int nthreads);
 extern "C" int w2b_host_gather_slices(const int32_t *ids, int64_t n_tokens, int64_t L, int nshards, const int64_t *cursor,
+                                      const int32_t *done, int32_t *stage, int64_t *xlate, int64_t *limit,
+                                      int32_t *limit_is_eof, int nthreads) {
+  return w2b_guarded("w2b_host_gather_slices", [&] { return w2b_host_gather_slices_impl(ids, n_tokens, L, nshards, cursor, done, stage, xlate, limit, limit_is_eof, nthreads); });
+}
+static int w2b_host_gather_slices_impl(const int32_t *ids, int64_t n_tokens, int64_t L, int nshards, const int64_t *cursor,
                                       const int32_t *done, int32_t *stage, int64_t *xlate, int64_t *limit,
                                       int32_t *limit_is_eof, int nthreads) {
   if (!ids || !cursor || !done || !stage || !xlate || !limit || !limit_is_eof || L < 1 || nshards < 1 || n_tokens < 0) {
@@ -382,7 +390,11 @@ void tokenize_chunk(const uint8_t *buf, int64_t begin, int64_t end, ChunkResult 
 
 }  // namespace
 
+static int w2b_corpus_load_impl(const char *path, int min_count, w2b_corpus **out);
 extern "C" int w2b_corpus_load(const char *path, int min_count, w2b_corpus **out) {
+  return w2b_guarded("w2b_corpus_load", [&] { return w2b_corpus_load_impl(path, min_count, out); });
+}
+static int w2b_corpus_load_impl(const char *path, int min_count, w2b_corpus **out) {
   if (!out) {
     w2b_set_error("w2b_corpus_load: null out");
     return W2B_EINVAL;
@@ -572,7 +584,11 @@ extern "C" const int64_t *w2b_corpus_counts(const w2b_corpus *c) { return c->cn.
 extern "C" int64_t w2b_corpus_num_tokens(const w2b_corpus *c) { return (int64_t)c->ids.size(); }
 extern "C" const int32_t *w2b_corpus_tokens(const w2b_corpus *c) { return c->ids.data(); }
 
+static int w2b_corpus_shards_impl(const w2b_corpus *c, int n, int64_t *start, int32_t *first);
 extern "C" int w2b_corpus_shards(const w2b_corpus *c, int n, int64_t *start, int32_t *first) {
+  return w2b_guarded("w2b_corpus_shards", [&] { return w2b_corpus_shards_impl(c, n, start, first); });
+}
+static int w2b_corpus_shards_impl(const w2b_corpus *c, int n, int64_t *start, int32_t *first) {
   if (!c || !start || !first) {
     w2b_set_error("w2b_corpus_shards: null argument");
     return W2B_EINVAL;
@@ -653,7 +669,13 @@ struct FmtCache {
 };
 }  // namespace
 
+static int w2b_write_vectors_impl(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
+                                 int binary);
 extern "C" int w2b_write_vectors(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
+                                 int binary) {
+  return w2b_guarded("w2b_write_vectors", [&] { return w2b_write_vectors_impl(path, c, vec, V, D, binary); });
+}
+static int w2b_write_vectors_impl(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
                                  int binary) {
   if (!path || !c || !vec || V < 0 || V > (int64_t)c->words.size() || D < 1) {
     w2b_set_error("w2b_write_vectors: bad argument");
@@ -724,7 +746,13 @@ static inline float level_value(int code, int bits) {
   return (code & 1) ? -m : m;
 }
 
+static int w2b_write_packed_impl(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
+                                int bitlevel);
 extern "C" int w2b_write_packed(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
+                                int bitlevel) {
+  return w2b_guarded("w2b_write_packed", [&] { return w2b_write_packed_impl(path, c, vec, V, D, bitlevel); });
+}
+static int w2b_write_packed_impl(const char *path, const w2b_corpus *c, const float *vec, int64_t V, int64_t D,
                                 int bitlevel) {
   if (bitlevel != 1 && bitlevel != 2) {
     w2b_set_error("packed format supports bitlevel 1 and 2");
@@ -779,7 +807,11 @@ extern "C" int w2b_read_packed_header(const char *path, int64_t *V, int64_t *D, 
   return W2B_OK;
 }
 
+static int w2b_read_packed_impl(const char *path, float *vec, char *words, int max_word);
 extern "C" int w2b_read_packed(const char *path, float *vec, char *words, int max_word) {
+  return w2b_guarded("w2b_read_packed", [&] { return w2b_read_packed_impl(path, vec, words, max_word); });
+}
+static int w2b_read_packed_impl(const char *path, float *vec, char *words, int max_word) {
   int64_t V, D;
   int bits;
   int rc = w2b_read_packed_header(path, &V, &D, &bits);

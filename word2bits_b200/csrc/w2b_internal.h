@@ -2,7 +2,28 @@
 #pragma once
 #include <stdint.h>
 
+#include <exception>
+#include <new>
+
 void w2b_set_error(const char *fmt, ...);
+
+// Nothing is thrown across the C ABI: entry points that allocate host memory or start threads run their body
+// through this guard (std::bad_alloc -> W2B_ENOMEM, anything else -> W2B_EINVAL, message in w2b_last_error()).
+template <class F>
+static inline int w2b_guarded(const char *name, F &&body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc &) {
+    w2b_set_error("%s: out of host memory", name);
+    return 6;  // W2B_ENOMEM
+  } catch (const std::exception &ex) {
+    w2b_set_error("%s: %s", name, ex.what());
+    return 1;  // W2B_EINVAL
+  } catch (...) {
+    w2b_set_error("%s: unexpected exception", name);
+    return 1;
+  }
+}
 // InitUnigramTable (src/word2bits.cpp:112-128) in boundary form: start[i] = first table
 // slot owned by word i, start[V] = 1e8.  Same libm pow() and the same double arithmetic
 // as the reference loop, so expanding it reproduces the 1e8-entry table bit for bit.
