@@ -252,6 +252,8 @@ def test_null_arguments_are_errors_not_crashes():
     assert lib.w2b_corpus_shards(None, 2, None, None) == EINVAL
     assert lib.w2b_host_unigram_bounds(None, 5, None) == EINVAL
     assert lib.w2b_destroy(None) == 0  # like free(NULL)
+    assert lib.w2b_read_packed_header(None, None, None, None) == EINVAL
+    assert lib.w2b_read_packed(None, None, None, 0) == EINVAL
     with pytest.raises(w2b.W2BError) as e:
         w2b.Corpus(os.path.join(ROOT, "tests"), 1)  # a directory is not a training file
     assert e.value.code == 3

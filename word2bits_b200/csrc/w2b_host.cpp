@@ -790,6 +790,7 @@ static int w2b_write_packed_impl(const char *path, const w2b_corpus *c, const fl
 }
 
 extern "C" int w2b_read_packed_header(const char *path, int64_t *V, int64_t *D, int *bitlevel) {
+  if (!path || !V || !D || !bitlevel) { w2b_set_error("w2b_read_packed_header: null argument"); return W2B_EINVAL; }
   FILE *f = fopen(path, "rb");
   if (!f) {
     w2b_set_error("cannot open %s", path);
@@ -812,6 +813,7 @@ extern "C" int w2b_read_packed(const char *path, float *vec, char *words, int ma
   return w2b_guarded("w2b_read_packed", [&] { return w2b_read_packed_impl(path, vec, words, max_word); });
 }
 static int w2b_read_packed_impl(const char *path, float *vec, char *words, int max_word) {
+  if (!path || !vec || (words && max_word < 1)) { w2b_set_error("w2b_read_packed: bad argument"); return W2B_EINVAL; }
   int64_t V, D;
   int bits;
   int rc = w2b_read_packed_header(path, &V, &D, &bits);
