@@ -406,3 +406,20 @@ def test_evaluator_host_side_errors_and_empty_report(tmp_path):
     if os.path.exists(refbin):
         want = subprocess.run([refbin, vf, "0", "0"], stdin=open(qf), capture_output=True, text=True).stdout
         assert got == want
+
+
+def test_corpus_above_the_reduce_vocab_threshold_is_refused(tmp_path, monkeypatch):
+    """Above 0.7 * 30 M distinct words the reference prunes its vocabulary in the middle of the scan (ReduceVocab,
+    :245-263, called from :292) — an order-dependent cut the one-pass reader does not reproduce, so such a corpus
+    is an error, not a silently different vocabulary.  (The threshold is lowered through the test hook.)"""
+    import word2bits_b200 as w2b
+    p = tmp_path / "c.txt"
+    p.write_text(" ".join("w%d" % (i % 12) for i in range(200)) + "\n")  # 12 words + </s> = 13 vocabulary entries
+    monkeypatch.setenv("W2B_TOKENIZER_MAX_DISTINCT", "13")
+    c = w2b.Corpus(str(p), 1)
+    assert c.vocab_size == 13
+    c.close()
+    monkeypatch.setenv("W2B_TOKENIZER_MAX_DISTINCT", "12")
+    with pytest.raises(w2b.W2BError, match="ReduceVocab") as e:
+        w2b.Corpus(str(p), 1)
+    assert e.value.code == 1

@@ -509,6 +509,18 @@ static int w2b_corpus_load_impl(const char *path, int min_count, w2b_corpus **ou
   const uint64_t eos_hash = hash_bytes("</s>", 4);
   const int eos_part = part_of(eos_hash);
   const int64_t eos_entry = c->parts[eos_part].find("</s>", 4, eos_hash);
+  {  // the reference prunes its vocabulary in the middle of the scan once it holds more than 0.7 * 30 M words
+     // (ReduceVocab, :245-263, :292) — an order-dependent cut this one-pass reader does not reproduce: refuse
+    int64_t max_distinct = 21000000;
+    if (const char *e = getenv("W2B_TOKENIZER_MAX_DISTINCT")) max_distinct = atoll(e);  // (tests)
+    const int64_t distinct = (int64_t)part_base[kParts] + (eos_entry >= 0 ? 0 : 1);
+    if (distinct > max_distinct) {
+      w2b_corpus_free(c);
+      w2b_set_error("%lld distinct words: above 21 M the reference prunes its vocabulary mid-scan (ReduceVocab), "
+                    "which this reader does not reproduce", (long long)distinct);
+      return W2B_EINVAL;
+    }
+  }
   for (int p = 0; p < kParts; ++p)
     for (uint32_t e = 0; e < c->parts[p].size(); ++e) {
       if (p == eos_part && (int64_t)e == eos_entry) continue;
