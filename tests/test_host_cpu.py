@@ -423,3 +423,21 @@ def test_corpus_above_the_reduce_vocab_threshold_is_refused(tmp_path, monkeypatc
     with pytest.raises(w2b.W2BError, match="ReduceVocab") as e:
         w2b.Corpus(str(p), 1)
     assert e.value.code == 1
+
+
+def test_default_geometry_is_the_measured_one():
+    """The numbers under profiles/ were measured with these launch geometries of the default kernel (cfg.kernel 0;
+    C2: grid 148 x 288 threads, 229.3 KB of dynamic shared memory — profiles/r01_ring_v5_ncu_full.md).  The SASS is
+    pinned by test_default_kernels_are_the_measured_binary; this pins the run-time arguments next to it, so a planner
+    change made for a variant cannot move the default silently."""
+    import word2bits_b200 as w2b
+    want = {  # (D, window, negative, bitlevel): (u_rows, v_rows, group, threads, smem_bytes)
+        (800, 10, 24, 1): (24, 34, 13, 288, 229256),   # BASELINE configs[1]
+        (400, 10, 12, 2): (24, 33, 13, 192, 114056),   # configs[2]
+        (400, 10, 24, 0): (24, 33, 13, 192, 114056),   # configs[3]
+        (200, 8, 24, 1): (20, 52, 13, 192, 74920),     # configs[0] shape
+    }
+    for (D, W, neg, b), geo in want.items():
+        p = w2b.ring_plan(size=D, window=W, negative=neg, bitlevel=b, vocab_size=400001)
+        assert p["ring"] == 1 and p["rows_in_flight"] == 2 and p["units_per_warp"] == 1
+        assert (p["u_rows"], p["v_rows"], p["group"], p["threads"], p["smem_bytes"]) == geo, (D, p)
