@@ -17,6 +17,7 @@
 #include "w2b_internal.h"
 #include "w2b_kernels.cuh"
 #include "w2b_ring.cuh"
+#include "w2b_warp.cuh"
 
 using namespace w2b;
 
@@ -108,6 +109,10 @@ struct w2b_ctx {
   int ring_lpr = 32;       // lanes per target row (32 = a warp per row; 16 / 8: cfg.kernel 3 / 4)
   int ring_xw = 0;         // consumer warps beyond one per 128 columns (cfg.kernel 5: 2)
   size_t ring_smem = 0;
+  bool warp = false;       // warp-per-shard kernel (csrc/w2b_warp.cuh) usable for this configuration
+  int warp_k = 0, warp_qcap = 0, warp_minb = 0;  // ring slots per warp, job queue entries, warps per SM
+  size_t warp_smem = 0;
+  int *d_sen = nullptr;    // warp kernel: sentence buffers (kMaxS ints per local shard, + 1 for the parity hooks)
   int sm_count = 0;
   long long train_words = 0;
   float *d_u = nullptr, *d_v = nullptr, *d_keep = nullptr, *d_exptab = nullptr, *d_alpha = nullptr;
@@ -311,6 +316,54 @@ static void plan_ring(w2b_ctx *c) {
   c->ring_smem = ring_layout(D, nu, nv, ncw).total;
 }
 
+// ---- warp-per-shard kernel (csrc/w2b_warp.cuh)
+typedef void (*warp_fn)(TrainParams, int, int, ApplyArgs);
+// warps (= 1-warp CTAs) per SM the register allocation is sized for; multiples of 4 because the register file is
+// split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96
+static int warp_minb_of(int nj) { return nj >= 5 ? 12 : (nj >= 3 ? 16 : 20); }
+template <int BM>
+static warp_fn warp_by_nj(int nj) {
+  switch (nj) {
+    case 1: return train_warp_kernel<BM, 1, 20>;
+    case 2: return train_warp_kernel<BM, 2, 20>;
+    case 3: return train_warp_kernel<BM, 3, 16>;
+    case 4: return train_warp_kernel<BM, 4, 16>;
+    case 5: return train_warp_kernel<BM, 5, 12>;
+    case 6: return train_warp_kernel<BM, 6, 12>;
+    case 7: return train_warp_kernel<BM, 7, 12>;
+    case 8: return train_warp_kernel<BM, 8, 12>;
+  }
+  return nullptr;
+}
+static warp_fn pick_warp(const w2b_ctx *c) {
+  const int nj = (c->ncol + 31) / 32;
+  switch (bm_of(c->cfg.bitlevel)) {
+    case 0: return warp_by_nj<0>(nj);
+    case 1: return warp_by_nj<1>(nj);
+    case 2: return warp_by_nj<2>(nj);
+    default: return warp_by_nj<9>(nj);
+  }
+}
+// Geometry: as many ring slots as the warp's share of the SM's 228 KB holds (each resident CTA also costs 1 KB of
+// reserved shared memory); at least 3 (one row being worked on, one draining, one in flight).
+static void plan_warp(w2b_ctx *c) {
+  c->warp = false;
+  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel != 6) return;
+  const int nj = (c->ncol + 31) / 32;
+  if (nj > 8) return;  // kernels are instantiated for D <= 1024
+  const int minb = warp_minb_of(nj);
+  const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
+  const size_t budget = (size_t)(228 * 1024) / minb - 1024;
+  int K = c->cfg.ring_rows > 0 ? std::min(c->cfg.ring_rows, 32) : 16;
+  while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap).total > budget) --K;
+  if (K < 3) return;
+  c->warp = true;
+  c->warp_k = K;
+  c->warp_qcap = qcap;
+  c->warp_minb = minb;
+  c->warp_smem = warp_layout(c->cfg.layer1_size, K, qcap).total;
+}
+
 static size_t dyn_smem(const w2b_ctx *c) {
   return c->cfg.mode == W2B_MODE_STRICT ? (size_t)c->cfg.layer1_size * sizeof(float) : 0;
 }
@@ -350,6 +403,7 @@ static TrainParams base_params(const w2b_ctx *c) {
     p.sleep_ns = e ? (unsigned)atoi(e) : 128u;  // flat between 32 and 512 ns on B200 (measured)
   }
   p.wca_scale = c->nranks;
+  p.sen = c->d_sen;
   return p;
 }
 
@@ -399,7 +453,12 @@ extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   int per_sm = 0;
   plan_ring(&tmp);
-  if (tmp.ring) {
+  plan_warp(&tmp);
+  if (tmp.warp) {
+    warp_fn wf = pick_warp(&tmp);
+    CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp.warp_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf, 32, tmp.warp_smem));
+  } else if (tmp.ring) {
     ring_fn rf = pick_ring(&tmp);
     CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp.ring_smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rf, tmp.ring_threads, tmp.ring_smem));
@@ -504,6 +563,7 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   c->group = cfg->group ? cfg->group : (cfg->negative + 1 > 9 ? 13 : (cfg->negative + 1 > 5 ? 9 : 5));
   if (c->group != 5 && c->group != 9 && c->group != 13) c->group = 9;  // register kernel instantiations
   plan_ring(c);
+  plan_warp(c);
   CK(cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -533,8 +593,10 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
     float t[kExpN];
     w2b_exptable(t);
     CK(cudaMemcpy(c->d_exptab, t, sizeof t, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyToSymbol(c_exptab, t, sizeof t));
   }
   CK(cudaMalloc(&c->d_scratch, 64));
+  if (c->warp) CK(cudaMalloc(&c->d_sen, sizeof(int) * (size_t)kMaxS * (c->nlocal + 1)));
   return W2B_OK;
 }
 
@@ -546,6 +608,7 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
   cudaFree(c->d_shards);
   cudaFree(c->d_scratch);
+  cudaFree(c->d_sen);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -696,6 +759,26 @@ static int stage_slices(w2b_ctx *c, long long want, w2b_step_stats *acc) {
 }
 
 static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
+  if (c->warp) {  // production path: one warp (a 32-thread CTA) per shard
+    warp_fn wf = pick_warp(c);
+    CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    p.shard_base = 0;
+    ApplyArgs none;
+    memset(&none, 0, sizeof none);
+    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    acc->kernel_ms += ms;
+    acc->launches += 1;
+    acc->d2h_bytes += (long long)sizeof(ShardState) * c->nlocal;
+    return W2B_OK;
+  }
   if (c->ring) {  // production path: TMA ring kernel, one CTA per shard
     ring_fn rf = pick_ring(c);
     CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
@@ -887,7 +970,14 @@ static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_tra
   p.train = 0;
   p.max_iters = max_iterations;
   p.wca_scale = 1;
-  if (c->ring) {  // the production kernel's own sampler warp (prefetching draw path)
+  if (c->warp) {  // the production kernel's own sampling code (prefetching draw path)
+    warp_fn wf = pick_warp(c);
+    CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
+    p.sen = c->d_sen + (size_t)kMaxS * c->nlocal;  // the hooks' own sentence buffer
+    ApplyArgs none;
+    memset(&none, 0, sizeof none);
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
+  } else if (c->ring) {  // the production kernel's own sampler warp (prefetching draw path)
     ring_fn rf = pick_ring(c);
     CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
     rf<<<1, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv, c->ring_g);
@@ -952,6 +1042,28 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
   if (cw) CK(cudaMemcpy(d_ids, ctx_ids, cw * sizeof(int), cudaMemcpyHostToDevice));
   if (nt) CK(cudaMemcpy(d_ids + cw, targets, nt * sizeof(int), cudaMemcpyHostToDevice));
   TrainParams p = base_params(c);
+  if (c->warp) {  // L1 hook through the production kernel itself: one explicit position, one launch
+    if (cw > 2 * c->cfg.window || nt > c->cfg.negative + 1) {
+      w2b_set_error("w2b_apply_position: cw <= 2*window and ntargets <= negative+1 for this context");
+      return W2B_EINVAL;
+    }
+    if (cw == 0) return W2B_OK;  // nothing is trained without context (:450)
+    warp_fn wf = pick_warp(c);
+    CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
+    DevTmp t_s;
+    CK(t_s.alloc(sizeof(ShardState)));
+    CK(cudaMemset(t_s.p, 0, sizeof(ShardState)));
+    p.shards = t_s.as<ShardState>();
+    p.sen = c->d_sen + (size_t)kMaxS * c->nlocal;
+    p.serial = 1;
+    ApplyArgs ap;
+    ap.ctx = d_ids; ap.tg = d_ids + cw; ap.cw = cw; ap.nt = nt; ap.f_out = d_f;
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, ap);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    if (f_out && nt) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));
+    return W2B_OK;
+  }
   apply_fn fn = pick_apply(c);
   const size_t smem = dyn_smem(c);
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -77,6 +77,7 @@ struct TrainParams {
   int serial;                   // ring kernel debug: no prefetch across positions
   unsigned sleep_ns;            // ring kernel: back-off of the sampler/loader polling loops
   int wca_scale;                // multi-GPU: local words stand for wca_scale x as many globally
+  int *sen;                     // warp kernel: sentence buffers, kMaxS ints per local shard
   w2b_trace_rec *trace;
   long long trace_cap;
   unsigned long long *trace_n;
@@ -91,6 +92,13 @@ __device__ inline unsigned long long lcg_jump_big(unsigned long long r, unsigned
   for (int j = 0; k; ++j, k >>= 1)
     if (k & 1) r = r * c_PA[j] + c_PC[j];
   return r;
+}
+
+// r mod w for 1 <= w <= 64 with 32-bit arithmetic (the window draw, :429).
+__device__ __forceinline__ int mod_small(unsigned long long r, unsigned w) {
+  const unsigned hi = (unsigned)(r >> 32), lo = (unsigned)r;
+  const unsigned two32 = (0xffffffffu % w + 1u) % w;  // 2^32 mod w
+  return (int)(((hi % w) * two32 + lo % w) % w);
 }
 
 // :67-71 — reporting only.

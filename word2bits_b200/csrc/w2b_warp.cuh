@@ -1,0 +1,516 @@
+// Production kernel of the Word2Bits training path for sm_100a: one WARP per corpus shard.
+//
+// A shard is what one reference thread walks (TrainModelThread, src/word2bits.cpp:363-516).  Here it is one
+// warp in a CTA of its own (32 threads, grid = shards), so a B200 runs 148 x 12..32 shards side by side and
+// hides HBM latency with shards, not with a deep pipeline inside a shard.  The warp does everything the
+// reference thread does, in the reference's order:
+//   * sampling (:379-460): learning-rate schedule, sentence builder + sub-sampling, shard termination, window
+//     draw, negative draws — 32 draws at a time by LCG jump-ahead; the unigram-table lookups of position p+1
+//     are in flight while position p is trained;
+//   * every embedding row a position touches streams through a small ring of K shared-memory slots as a JOB:
+//     cw context rows of u, then 1+negative target rows of v, then one staging job.  Lane 0 moves rows with
+//     the bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier per slot) and keeps
+//     K-2 loads in flight while the warp works on a landed row;
+//   * context job (:431-449): lane l owns float4 columns l, l+32, ...; quantize and accumulate in registers;
+//   * target job (:450-492): quantize, dot against the context average (registers), 5-step butterfly, g from
+//     the expTable (constant memory, warp-uniform index), error accumulated in registers (:487), the row is
+//     overwritten in place with g*context_avg (:490) and handed back with ONE cp.reduce.async.bulk.add.f32
+//     (an atomic-add scatter of the whole row in L2);
+//   * staging job (:494-503): the error registers are written to the slot and bulk-reduced into every
+//     context row of u.
+// Flow control is private to the warp: job j lives in slot j mod K; every job commits exactly one bulk
+// async-group (empty for a context job), so after `wait_group.read 1` the slot of the job before the one just
+// finished is free and the next load is issued into it.  No CTA barrier, no inter-warp traffic, context_avg
+// and the error never leave registers.
+//
+// Ordering semantics: TrainParams::serial = 1 fetches the rows of position p+1 only after every update of
+// position p has completed (sequential semantics inside a shard, like one reference thread; the only
+// staleness left is Hogwild between shards, which the reference's threads have too).  serial = 0 lets the ring
+// run ahead across positions: a context row shared by neighbouring positions is then read one update stale
+// (no update is ever lost: all scatters are atomic adds).  Duplicate targets inside one position read the same
+// old row in both modes.
+#pragma once
+#include "w2b_kernels.cuh"
+#include "w2b_ptx.cuh"
+
+namespace w2b {
+
+__constant__ float c_exptab[kExpN];  // expTable (:614-618), uploaded by w2b_create
+
+constexpr int kJobTarget = 0x40000000;  // job queue entry: row id | kJobTarget = row of v; -1 = staging job
+constexpr int kJobIdMask = 0x3fffffff;
+
+// Shared-memory carve-up of one warp (host and device agree through this helper).
+struct WarpLayout {
+  int rowb, K, qcap;
+  size_t off_ring, off_jobq, off_bar, total;
+};
+__host__ __device__ inline WarpLayout warp_layout(long long D, int K, int qcap) {
+  WarpLayout L;
+  L.rowb = (int)(D * 4);
+  L.K = K;
+  L.qcap = qcap;
+  size_t o = 0;
+  L.off_ring = o; o += (size_t)K * L.rowb;
+  L.off_jobq = o; o += sizeof(int) * (size_t)qcap;
+  o = (o + 7) & ~(size_t)7;
+  L.off_bar = o;  o += 8 * (size_t)K;
+  L.total = (o + 15) & ~(size_t)15;
+  return L;
+}
+// job queue capacity: two positions (the one being trained and the one sampled ahead), power of two
+__host__ __device__ inline int warp_queue_capacity(int window, int negative) {
+  const int need = 2 * (2 * window + negative + 2);
+  int q = 32;
+  while (q < need) q <<= 1;
+  return q;
+}
+
+// ---------------------------------------------------------------------------- packed fp32 pairs (FFMA2)
+struct F2 { float x, y; };
+#ifdef W2B_EMULATE
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { return F2{__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)}; }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { return F2{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
+__device__ __forceinline__ float sign_level(float x, float level) {  // (x & 0x80000000) | level
+  unsigned xi, li;
+  memcpy(&xi, &x, 4); memcpy(&li, &level, 4);
+  xi = (xi & 0x80000000u) | li;
+  float r; memcpy(&r, &xi, 4);
+  return r;
+}
+__device__ __forceinline__ float ldc_exptab(int i) { return c_exptab[i]; }
+#else
+__device__ __forceinline__ unsigned long long f2_bits(F2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ F2 f2_from(unsigned long long r) {
+  F2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return f2_from(d);
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(d);
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(d);
+}
+__device__ __forceinline__ float sign_level(float x, float level) {  // (x & 0x80000000) | level: one LOP3
+  unsigned r;
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(r) : "r"(__float_as_uint(x)), "r"(__float_as_uint(level)));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float ldc_exptab(int i) { return c_exptab[i]; }
+#endif
+
+// quantize() (:73-108) as the training loop uses it.  bitlevel 1 and 2 copy the SIGN BIT onto the level instead
+// of testing x < 0: identical for every value except -0.0 (and NaNs with the sign bit set), which the reference
+// maps to the positive level; a master weight can only become -0.0 through a flushed negative denormal sum.
+// The exported vectors (export_kernel) and the strict kernel use the exact form (w2b_quant.cuh).
+template <int BM>
+__device__ __forceinline__ float quant_fast(float x, const QParams &q) {
+  if (BM == 0) return x;
+  if (BM == 1) return sign_level(x, 0.33333334f);
+  if (BM == 2) return sign_level(x, fabsf(x) <= 0.5f ? 0.25f : 0.75f);
+  return quant<9>(x, q);
+}
+
+// gradient scalar (:473-475) with the expTable in constant memory (f is warp-uniform after the butterfly).
+__device__ __forceinline__ float grad_scalar_c(float f, int label, float alpha) {
+  if (f > 6.f) return __fmul_rn((float)(label - 1), alpha);
+  if (f < -6.f) return __fmul_rn((float)label, alpha);
+  const int idx = __float2int_rz(__fmul_rn(__fadd_rn(f, 6.f), 83.f));
+  return __fmul_rn(__fsub_rn((float)label, ldc_exptab(idx)), alpha);
+}
+
+// Sampler state of a shard (warp-uniform unless noted).
+struct WarpSampler {
+  unsigned long long r;
+  long long cursor, wc, last, wc0, iters;
+  int len, sp, status, done;
+  bool have_pre;
+  unsigned long long r1_pre, rd_pre;  // rd_pre: per lane
+  int t_pre;                          // per lane
+  float alpha_c;
+  unsigned n_pos, n_ctx, n_tgt;       // per launch (a launch is bounded to 4 M words per shard)
+};
+
+// Explicit single position (L1 parity hook, w2b_apply_position): ids instead of draws.
+struct ApplyArgs {
+  const int *ctx, *tg;
+  int cw, nt;
+  float *f_out;
+};
+
+// Samples forward to the next trained position (cw > 0) of the shard and appends its jobs — cw context ids, nt
+// target ids | kJobTarget, -1 — to the job queue at index qtail.  Returns 1 with cw / nt / alpha of the position,
+// or 0 when the launch is over for this shard (word budget, shard end, slice exhausted, max_iters).
+// Control flow and draw order of :379-460; see train_ring_kernel's sampler warp in round 1 for the prefetch of
+// the next position's unigram-table lookups.
+__device__ inline int warp_next_position(const TrainParams &p, const ShardState &sh, WarpSampler &S, int lane, int *sen,
+                                         int *jobq, int qmask, unsigned qtail, const unsigned long long JA1,
+                                         const unsigned long long JC1, int &cw_out, int &nt_out, float &alpha_out) {
+  const int W = p.window, neg = p.negative;
+  const int negl = neg < 32 ? neg : 32;
+  const unsigned long long JAn = c_JA[neg], JCn = c_JC[neg];
+  for (;;) {
+    if (S.wc - S.last > 10000) {  // :379-393
+      const unsigned long long delta = (unsigned long long)(S.wc - S.last) * (unsigned long long)p.wca_scale;
+      long long wca = 0;
+      if (lane == 0) wca = (long long)(atomicAdd(p.wca, delta) + delta);
+      wca = __shfl_sync(kFull, wca, 0);
+      float a = __fmul_rn(p.starting_alpha, __fsub_rn(1.f, __fdiv_rn((float)wca, p.alpha_denom)));
+      if ((double)a < (double)p.starting_alpha * 0.0001) a = (float)((double)p.starting_alpha * 0.0001);
+      if (lane == 0) *(volatile float *)p.alpha = a;
+      S.alpha_c = a;
+      S.last = S.wc;
+    }
+    if (S.len == 0) {
+      if (p.word_budget > 0 && S.wc - S.wc0 >= p.word_budget) return 0;
+      unsigned long long r2 = S.r;
+      long long c2 = S.cursor, w2 = S.wc;
+      int l2 = 0;
+      S.status = build_sentence(p, sh, lane, sen, r2, c2, w2, l2);
+      __syncwarp();
+      if (S.status == 2) return 0;  // slice exhausted mid-sentence: nothing committed
+      S.r = r2; S.cursor = c2; S.wc = w2; S.len = l2; S.sp = 0;
+      S.have_pre = false;
+      // the shared learning rate (:53) is re-read once per sentence: other shards move it every 10k words each
+      S.alpha_c = *(volatile float *)p.alpha;
+    }
+    if (S.status == 1 || S.wc > p.shard_word_limit) {  // :414-423
+      if (lane == 0) atomicAdd(p.wca, (unsigned long long)(S.wc - S.last) * (unsigned long long)p.wca_scale);
+      S.last = S.wc;
+      S.done = 1;
+      return 0;
+    }
+    ++S.iters;
+    // ---- draws of this position (:428-460)
+    unsigned long long r1, rd;
+    int t = 0;
+    if (S.have_pre) {
+      r1 = S.r1_pre; rd = S.rd_pre; t = S.t_pre;
+    } else {
+      r1 = lcg(S.r);
+      rd = r1 * JA1 + JC1;
+      if (lane < negl) t = p.table[(rd >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+    }
+    S.have_pre = false;
+    const int b = mod_small(r1, (unsigned)W);
+    const int len = S.len, sp = S.sp;
+    const int center = len ? sen[sp] : -1;
+    int cw = 0;
+    if (len) {
+      for (int a0 = b; a0 < 2 * W + 1 - b; a0 += 32) {
+        const int a = a0 + lane;
+        const int qq = sp - W + a;
+        const bool ok = (a < 2 * W + 1 - b) && (a != W) && qq >= 0 && qq < len;
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) jobq[(qtail + cw + __popc(m & ((1u << lane) - 1))) & qmask] = sen[qq];
+        cw += __popc(m);
+      }
+    }
+    int nt = 0;
+    if (cw) {
+      const unsigned long long r_after = r1 * JAn + JCn;
+      if (sp + 1 < len) {  // next position of the sentence: its draws are already determined
+        S.r1_pre = lcg(r_after);
+        S.rd_pre = S.r1_pre * JA1 + JC1;
+        S.t_pre = 0;
+        if (lane < negl) S.t_pre = p.table[(S.rd_pre >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+        S.have_pre = true;
+      }
+      const unsigned tq = qtail + cw;
+      if (lane == 0) jobq[tq & qmask] = center | kJobTarget;
+      nt = 1;
+      {
+        bool ok = lane < negl;
+        int tt = t;
+        if (ok && tt == 0) tt = (int)(rd % (unsigned long long)(p.V - 1)) + 1;  // :457
+        ok = ok && (tt != center);                                                 // :458
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) jobq[(tq + nt + __popc(m & ((1u << lane) - 1))) & qmask] = tt | kJobTarget;
+        nt += __popc(m);
+      }
+      for (int d0 = 33; d0 <= neg; d0 += 32) {  // negative > 32: remaining draws, not prefetched
+        const int k = d0 + lane;
+        bool ok = k <= neg;
+        int tt = 0;
+        if (ok) {
+          const unsigned long long rd2 = lcg_jump(r1, k);
+          tt = p.table[(rd2 >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+          if (tt == 0) tt = (int)(rd2 % (unsigned long long)(p.V - 1)) + 1;
+          ok = (tt != center);
+        }
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) jobq[(tq + nt + __popc(m & ((1u << lane) - 1))) & qmask] = tt | kJobTarget;
+        nt += __popc(m);
+      }
+      if (lane == 0) jobq[(tq + nt) & qmask] = -1;  // staging job (:494-503)
+      S.r = r_after;
+    } else {
+      S.r = r1;
+    }
+    ++S.sp;
+    if (S.sp >= S.len) S.len = 0;  // :505-509
+    __syncwarp();                  // the queue entries are visible to every lane
+    if (p.trace) {  // parity hook: one record per window draw, exactly what the oracle's trace holds
+      if (lane == 0) {
+        const unsigned long long k = (*p.trace_n)++;
+        if ((long long)k < p.trace_cap) {
+          w2b_trace_rec *tr = p.trace + k;
+          tr->center = center; tr->b = b; tr->cw = cw; tr->ntargets = nt; tr->alpha = S.alpha_c;
+          for (int i = 0; i < nt; ++i) tr->targets[i] = jobq[(qtail + cw + i) & qmask] & kJobIdMask;
+        }
+      }
+      __syncwarp();
+    }
+    if (p.max_iters >= 0 && S.iters >= p.max_iters) {
+      if (cw) { S.n_pos += 1; S.n_ctx += cw; S.n_tgt += nt; }
+      return 0;
+    }
+    if (cw == 0) continue;  // single-word or empty sentence: one window draw, nothing trained
+    S.n_pos += 1; S.n_ctx += cw; S.n_tgt += nt;
+    if (!p.train) continue;  // draws only
+    cw_out = cw; nt_out = nt; alpha_out = S.alpha_c;
+    return 1;
+  }
+}
+
+// BM: compile-time bitlevel 0/1/2, 9 = run time.  NJ = float4 columns per lane = ceil(D / 128).  MINB = CTAs (warps)
+// per SM the register allocation is sized for.
+template <int BM, int NJ, int MINB>
+__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap, ApplyArgs ap) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x;
+  const WarpLayout L = warp_layout(p.D, K, qcap);
+  const unsigned s_base = smem_u32(smem);
+  const unsigned ring = s_base + (unsigned)L.off_ring;
+  const unsigned bars = s_base + (unsigned)L.off_bar;
+  int *jobq = reinterpret_cast<int *>(smem + L.off_jobq);
+  const int qmask = qcap - 1;
+  const unsigned rowb = (unsigned)L.rowb;
+  const int D4 = p.ncol;
+  const int shard = p.shard_base + blockIdx.x;
+  ShardState *shp = p.shards + shard;
+  if (!ap.ctx && shp->done) return;
+  int *sen = p.sen + (size_t)shard * kMaxS;
+
+  if (lane == 0) {
+    for (int i = 0; i < K; ++i) mbar_init(reinterpret_cast<unsigned long long *>(smem + L.off_bar) + i, 1);
+#ifndef W2B_EMULATE
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
+  __syncwarp();
+
+  QParams qp;
+  qp.bits = p.bitlevel;
+  qp.seg = (p.bitlevel >= 4) ? exp2f((float)(p.bitlevel - 1)) : 1.f;
+
+  // lane's float4 columns j*32+lane; every column group but the last is full (NJ == ceil(D4 / 32)); columns past
+  // the row end are clamped for loads and masked for stores (their context_avg is zero, so they add nothing)
+  const unsigned lane16 = (unsigned)lane * 16u;
+  const bool on_last = (NJ - 1) * 32 + lane < D4;
+  const unsigned coff_last = (unsigned)(on_last ? (NJ - 1) * 32 + lane : D4 - 1) * 16u;
+#define W2B_COFF(j) ((j) < NJ - 1 ? lane16 + (unsigned)(j) * 512u : coff_last)
+
+  const ShardState &sh = *shp;
+  WarpSampler S;
+  S.r = sh.rng; S.cursor = sh.cursor; S.wc = sh.word_count; S.last = sh.last_word_count; S.wc0 = S.wc;
+  S.iters = 0; S.len = 0; S.sp = 0; S.status = 0; S.done = 0; S.have_pre = false;
+  S.r1_pre = 0; S.rd_pre = 0; S.t_pre = 0; S.n_pos = S.n_ctx = S.n_tgt = 0;
+  S.alpha_c = *(volatile float *)p.alpha;
+  const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
+
+  // ---- job bookkeeping (all warp-uniform)
+  unsigned q_tail = 0;   // jobs appended to the queue
+  unsigned q_issue = 0;  // jobs whose load has been issued (or skipped: staging jobs)
+  unsigned q_cons = 0;   // jobs consumed (their bulk group committed)
+  unsigned q_limit = 0;  // jobs the issue side may look at (serial: end of the current position)
+  int islot = 0, cslot = 0;
+  unsigned phase = 0;    // per-slot mbarrier parity
+  double loss = 0.0;     // per lane: reported loss of the targets this lane looked after
+
+  // Issue loads while job j <= q_cons + K - 2 (slot of job j - K confirmed free by the last wait_group.read 1).
+  auto pump = [&]() {
+    while (q_issue < q_limit && q_issue + 2 <= q_cons + (unsigned)K) {
+      const int e = jobq[q_issue & qmask];
+      if (e >= 0 && lane == 0) {
+        const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
+        const unsigned bar = bars + 8u * (unsigned)islot;
+        mbar_expect_tx(bar, rowb);
+        bulk_load(ring + (unsigned)islot * rowb, src, rowb, bar);
+      }
+      ++q_issue;
+      if (++islot == K) islot = 0;
+    }
+  };
+  auto job_done = [&]() {  // the job's group is committed by lane 0; free the slot before it and refill
+    if (lane == 0) {
+      bulk_commit();
+      bulk_wait_read<1>();
+    }
+    __syncwarp();
+    ++q_cons;
+    if (++cslot == K) cslot = 0;
+    pump();
+  };
+
+  int n_cw = 0, n_nt = 0;
+  float n_alpha = 0.f;
+  int have_next;
+  if (ap.ctx) {  // one explicit position
+    for (int k = lane; k < ap.cw; k += 32) jobq[k & qmask] = ap.ctx[k];
+    for (int k = lane; k < ap.nt; k += 32) jobq[(ap.cw + k) & qmask] = ap.tg[k] | kJobTarget;
+    if (lane == 0) jobq[(ap.cw + ap.nt) & qmask] = -1;
+    __syncwarp();
+    n_cw = ap.cw; n_nt = ap.nt; n_alpha = S.alpha_c;
+    have_next = ap.cw > 0;
+  } else {
+    have_next = warp_next_position(p, sh, S, lane, sen, jobq, qmask, q_tail, JA1, JC1, n_cw, n_nt, n_alpha);
+  }
+  if (have_next) q_tail += (unsigned)(n_cw + n_nt + 1);
+
+  while (have_next) {
+    const int cw = n_cw, nt = n_nt;
+    const float alpha = n_alpha;
+    const unsigned q0 = q_cons;  // first job of this position
+    q_limit = q0 + (unsigned)(cw + nt + 1);
+    pump();
+    // sample one position ahead: its jobs extend the queue (and, without serial, what the ring may prefetch)
+    have_next = ap.ctx ? 0 : warp_next_position(p, sh, S, lane, sen, jobq, qmask, q_tail, JA1, JC1, n_cw, n_nt, n_alpha);
+    if (have_next) q_tail += (unsigned)(n_cw + n_nt + 1);
+    if (!p.serial) { q_limit = q_tail; pump(); }
+
+    // ---- context jobs: gather + quantize + average (:431-449)
+    F2 a[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) a[j][0] = a[j][1] = F2{0.f, 0.f};
+    for (int k = 0; k < cw; ++k) {
+      mbar_wait(bars + 8u * (unsigned)cslot, (phase >> cslot) & 1u);
+      phase ^= 1u << cslot;
+      const unsigned row = ring + (unsigned)cslot * rowb;
+      float4 x[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) x[j] = lds128(row + W2B_COFF(j));
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        a[j][0] = add2(a[j][0], F2{quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp)});
+        a[j][1] = add2(a[j][1], F2{quant_fast<BM>(x[j].z, qp), quant_fast<BM>(x[j].w, qp)});
+      }
+      job_done();
+    }
+    {
+      const float fcw = (float)cw;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const bool on = (j < NJ - 1) || on_last;
+        a[j][0] = on ? F2{__fdiv_rn(a[j][0].x, fcw), __fdiv_rn(a[j][0].y, fcw)} : F2{0.f, 0.f};
+        a[j][1] = on ? F2{__fdiv_rn(a[j][1].x, fcw), __fdiv_rn(a[j][1].y, fcw)} : F2{0.f, 0.f};
+      }
+    }
+
+    // ---- target jobs (:450-492)
+    F2 e[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) e[j][0] = e[j][1] = F2{0.f, 0.f};
+    float myf0 = 0.f, myf1 = 0.f;  // lane i keeps +-f of targets i and 32+i for the reported loss (:480-483)
+    for (int i = 0; i < nt; ++i) {
+      const int tid_row = jobq[q_cons & qmask] & kJobIdMask;
+      mbar_wait(bars + 8u * (unsigned)cslot, (phase >> cslot) & 1u);
+      phase ^= 1u << cslot;
+      const unsigned row = ring + (unsigned)cslot * rowb;
+      float4 x[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) x[j] = lds128(row + W2B_COFF(j));
+      F2 d0 = F2{0.f, 0.f}, d1 = F2{0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        x[j] = make_float4(quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp), quant_fast<BM>(x[j].z, qp),
+                           quant_fast<BM>(x[j].w, qp));
+        d0 = fma2(a[j][0], F2{x[j].x, x[j].y}, d0);
+        d1 = fma2(a[j][1], F2{x[j].z, x[j].w}, d1);
+      }
+      float f = (d0.x + d0.y) + (d1.x + d1.y);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(kFull, f, o);
+      const float g = grad_scalar_c(f, i == 0 ? 1 : 0, alpha);
+      {
+        const float sf = (i == 0) ? f : -f;
+        if (i < 32) { if (lane == i) myf0 = sf; }
+        else if (lane == i - 32) myf1 = sf;
+      }
+      const F2 g2 = F2{g, g};
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        e[j][0] = fma2(g2, F2{x[j].x, x[j].y}, e[j][0]);  // :487, quantized OLD v
+        e[j][1] = fma2(g2, F2{x[j].z, x[j].w}, e[j][1]);
+        const F2 u0 = mul2(g2, a[j][0]), u1 = mul2(g2, a[j][1]);  // :490: g*context_avg replaces the row in its slot
+        if ((j < NJ - 1) || on_last) sts128(row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_reduce_add(p.v + (long long)tid_row * p.D, row, rowb);
+      job_done();
+    }
+
+    // ---- staging job: the error goes to every context row of u (:494-503)
+    {
+      const unsigned row = ring + (unsigned)cslot * rowb;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if ((j < NJ - 1) || on_last) sts128(row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0)
+        for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, row, rowb);
+      if (lane < nt) loss += (double)logf(sigmoid_report(myf0));
+      if (lane + 32 < nt) loss += (double)logf(sigmoid_report(myf1));
+      if (ap.f_out) {
+        if (lane < nt) ap.f_out[lane] = lane == 0 ? myf0 : -myf0;
+        if (lane + 32 < nt) ap.f_out[lane + 32] = -myf1;
+      }
+      if (p.serial) {  // every update of this position has completed before the next position's rows are fetched
+        if (lane == 0) {
+          bulk_commit();
+          bulk_wait_all();
+        }
+        __syncwarp();
+        ++q_cons;
+        if (++cslot == K) cslot = 0;
+      } else {
+        job_done();
+      }
+    }
+  }
+#undef W2B_COFF
+  if (lane == 0) bulk_wait_all();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
+  if (lane == 0 && !ap.ctx) {
+    shp->rng = S.r;
+    shp->cursor = S.cursor;
+    shp->word_count = S.wc;
+    shp->last_word_count = S.last;
+    shp->done = S.done;
+    shp->loss = sh.loss + loss;
+    shp->n_iter = sh.n_iter + (unsigned long long)S.iters;
+    shp->n_pos = sh.n_pos + S.n_pos;
+    shp->n_ctx = sh.n_ctx + S.n_ctx;
+    shp->n_tgt = sh.n_tgt + S.n_tgt;
+  }
+}
+
+}  // namespace w2b
