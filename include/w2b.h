@@ -108,7 +108,8 @@ typedef struct {
   int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel,
                           experimental variants of the ring kernel: 2 = division-free index arithmetic,
                           3 / 4 = 2 + 16 / 8 lanes per target row (narrow rows, D <= 512 / 256),
-                          5 = 2 + two more consumer warps (wide rows, D > 512) */
+                          5 = 2 + two more consumer warps (wide rows, D > 512);
+                          6 = warp-per-shard kernel (one 32-thread CTA per shard) */
   int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
   int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed;
                           2 (kernel >= 2 only, experimental) = prefetching with early slot release */
@@ -159,6 +160,17 @@ int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out);
 /* Slot and landing-barrier index of target row i of a position whose first row sits in slot vs0, as the
  * kernel = 2 variant computes them (multiply-high by a precomputed reciprocal instead of % and /). */
 int w2b_host_ring_index(int vs0, int i, int nv, int G, int *slot, int *group);
+
+/* Geometry of the warp-per-shard kernel (csrc/w2b_warp.cuh; cfg.kernel = 6) for a configuration: pure host
+ * arithmetic.  warp = 0: the configuration runs another kernel (D % 4 != 0, D > 1024, reg != 0, strict mode). */
+typedef struct {
+  int32_t warp;           /* 1 = the warp kernel applies */
+  int32_t slots;          /* K: shared-memory row slots of a warp's ring (K-2 loads in flight) */
+  int32_t queue_entries;  /* job queue capacity (two positions) */
+  int32_t warps_per_sm;   /* resident 1-warp CTAs per SM the registers are sized for */
+  int64_t smem_bytes;     /* dynamic shared memory per warp */
+} w2b_warp_plan;
+int w2b_warp_plan_query(const w2b_config *cfg, w2b_warp_plan *out);
 
 /* Number of shards that keeps every SM busy for this configuration (SMs x resident CTAs);
  * the CLI's default for -threads (the reference's default of 12 is a CPU core count). */

@@ -37,6 +37,7 @@ def lib():
         _emu = C.CDLL(os.path.join(HERE, "libw2bemu.so"))
         _emu.emu_last_error.restype = C.c_char_p
         _emu.emu_run_ring.argtypes = [C.POINTER(EmuRun)]
+        _emu.emu_run_warp.argtypes = [C.POINTER(EmuRun)]
     return _emu
 
 
@@ -81,6 +82,48 @@ def train_epoch(corpus, table, u, v, *, size, window, negative, bitlevel, shards
                trace_n=p(trace_n) if trace_cap else None, only_shard=-1 if trace_shard is None else trace_shard,
                fault=fault)
     rc = lib().emu_run_ring(C.byref(r))
+    if rc:
+        raise EmuError(lib().emu_last_error().decode())
+    out["alpha"], out["wca"] = float(a[0]), int(wca[0])
+    out["plan"] = plan
+    if trace_cap:
+        n = int(trace_n[0])
+        out["trace"] = [(t.center, t.b, t.cw, list(t.targets[: t.ntargets]), t.alpha) for t in trace[: min(n, trace_cap)]]
+    return out
+
+
+def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, shards, serial=0, alpha=0.05,
+                     sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
+                     slots=0, fault=0):
+    """One pass of every shard (one 32-thread CTA after another) through the emulated warp-per-shard kernel
+    (csrc/w2b_warp.cuh).  Same conventions as train_epoch."""
+    plan = w2b.warp_plan(size=size, window=window, negative=negative, bitlevel=bitlevel, vocab_size=corpus.vocab_size,
+                         ring_rows=slots)
+    if not plan["warp"]:
+        raise EmuError("the warp kernel does not apply to this shape")
+    start, first = corpus.shards(shards)
+    keep = w2b.host_keep_thresholds(corpus.counts, corpus.train_words, sample)
+    exptab = w2b.host_exptable()
+    tokens = np.ascontiguousarray(corpus.tokens, np.int32)
+    a = np.array([alpha if state is None else state[0]], np.float32)
+    wca = np.array([0 if state is None else state[1]], np.uint64)
+    out = dict(loss=np.zeros(shards), words=np.zeros(shards, np.int64), n_pos=np.zeros(shards, np.int64),
+               n_ctx=np.zeros(shards, np.int64), n_tgt=np.zeros(shards, np.int64), done=np.zeros(shards, np.int32))
+    trace = (_lib.TraceRec * max(trace_cap, 1))()
+    trace_n = np.zeros(1, np.uint64)
+    p = _lib.ptr
+    r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
+               alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
+               opt=0, lpr=32, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32, serial=serial,
+               u=p(u), v=p(v), table=p(table), keep=p(keep), exptab=p(exptab), tokens=p(tokens), n_tokens=len(tokens),
+               shard_start=p(start), shard_first=p(first), alpha=p(a), wca=p(wca), word_budget=0, max_iters=max_iters,
+               seed=seed, async_mode=async_mode, train=0 if trace_cap else 1,
+               loss=p(out["loss"]), words=p(out["words"]), n_pos=p(out["n_pos"]), n_ctx=p(out["n_ctx"]),
+               n_tgt=p(out["n_tgt"]), done=p(out["done"]),
+               trace=C.cast(trace, C.c_void_p) if trace_cap else None, trace_cap=trace_cap,
+               trace_n=p(trace_n) if trace_cap else None, only_shard=-1 if trace_shard is None else trace_shard,
+               fault=fault)
+    rc = lib().emu_run_warp(C.byref(r))
     if rc:
         raise EmuError(lib().emu_last_error().decode())
     out["alpha"], out["wca"] = float(a[0]), int(wca[0])

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "w2b_ring.cuh"
+#include "w2b_warp.cuh"
 
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
@@ -347,6 +348,27 @@ entry_fn by_variant(int opt, int lpr, int xw, int nj) {
   return opt ? by_nj<BM, 1, 32, 0>(nj) : by_nj<BM, 0, 32, 0>(nj);
 }
 
+template <int BM, int NJ>
+void warp_entry() {
+  w2b::ApplyArgs none;
+  memset(&none, 0, sizeof none);
+  w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu, none);
+}
+template <int BM>
+entry_fn warp_by_nj(int nj) {
+  switch (nj) {
+    case 1: return warp_entry<BM, 1>;
+    case 2: return warp_entry<BM, 2>;
+    case 3: return warp_entry<BM, 3>;
+    case 4: return warp_entry<BM, 4>;
+    case 5: return warp_entry<BM, 5>;
+    case 6: return warp_entry<BM, 6>;
+    case 7: return warp_entry<BM, 7>;
+    case 8: return warp_entry<BM, 8>;
+  }
+  return nullptr;
+}
+
 }  // namespace
 
 extern "C" {
@@ -393,7 +415,7 @@ int emu_check_probe(unsigned off, unsigned bytes, uint64_t *total) {
   return bad;
 }
 
-int emu_run_ring(const EmuRun *r) {
+static void emu_setup(const EmuRun *r, std::vector<w2b::ShardState> &shards, w2b::TrainParams &p) {
   using namespace w2b;
   g_error = nullptr;
   g_rng.seed(r->seed);
@@ -404,17 +426,8 @@ int emu_run_ring(const EmuRun *r) {
   for (int k = 1; k <= 64; ++k) { c_JA[k] = c_JA[k - 1] * kLcgA; c_JC[k] = c_JC[k - 1] * kLcgA + kLcgC; }
   c_PA[0] = kLcgA; c_PC[0] = kLcgC;
   for (int j = 1; j < 64; ++j) { c_PA[j] = c_PA[j - 1] * c_PA[j - 1]; c_PC[j] = c_PA[j - 1] * c_PC[j - 1] + c_PC[j - 1]; }
-  if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
-  const int ncol = (int)(r->D / 4);
-  const int nj = (ncol + r->lpr - 1) / r->lpr;
-  entry_fn fn = nullptr;
-  switch (r->bitlevel) {
-    case 0: fn = by_variant<0>(r->opt, r->lpr, r->xw, nj); break;
-    case 1: fn = by_variant<1>(r->opt, r->lpr, r->xw, nj); break;
-    case 2: fn = by_variant<2>(r->opt, r->lpr, r->xw, nj); break;
-  }
-  if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
-  std::vector<ShardState> shards(r->num_shards);
+  memcpy(c_exptab, r->exptab, sizeof(float) * kExpN);
+  shards.assign(r->num_shards, ShardState());
   for (int i = 0; i < r->num_shards; ++i) {  // csrc/w2b_cuda.cu: w2b_epoch_begin
     ShardState &s = shards[i];
     memset(&s, 0, sizeof s);
@@ -426,17 +439,40 @@ int emu_run_ring(const EmuRun *r) {
     s.limit = r->n_tokens;
     s.limit_is_eof = 1;
   }
-  TrainParams p;
   memset(&p, 0, sizeof p);
   p.u = r->u; p.v = r->v; p.table = r->table; p.keep_thr = r->keep; p.exptab = r->exptab; p.tokens = r->tokens;
   p.shards = shards.data(); p.alpha = r->alpha; p.wca = (unsigned long long *)r->wca;
-  p.D = r->D; p.V = r->V; p.ncol = ncol; p.window = r->window; p.negative = r->negative; p.bitlevel = r->bitlevel;
+  p.D = r->D; p.V = r->V; p.ncol = (int)(r->D / 4); p.window = r->window; p.negative = r->negative; p.bitlevel = r->bitlevel;
   p.sample = r->sample; p.reg = 0.f; p.starting_alpha = r->alpha0;
   p.alpha_denom = (float)(r->iter * r->train_words + 1);
   p.shard_word_limit = r->train_words / r->num_shards;
   p.word_budget = r->word_budget; p.max_iters = r->max_iters; p.shard_base = 0; p.train = r->train;
   p.plain_store = 0; p.serial = r->serial; p.sleep_ns = 0; p.wca_scale = 1;
   p.trace = r->trace; p.trace_cap = r->trace_cap; p.trace_n = (unsigned long long *)r->trace_n;
+}
+
+static void emu_results(const EmuRun *r, const std::vector<w2b::ShardState> &shards) {
+  for (int i = 0; i < r->num_shards; ++i) {
+    r->loss[i] = shards[i].loss; r->words[i] = shards[i].word_count; r->n_pos[i] = (int64_t)shards[i].n_pos;
+    r->n_ctx[i] = (int64_t)shards[i].n_ctx; r->n_tgt[i] = (int64_t)shards[i].n_tgt; r->done[i] = shards[i].done;
+  }
+}
+
+int emu_run_ring(const EmuRun *r) {
+  using namespace w2b;
+  std::vector<ShardState> shards;
+  TrainParams p;
+  emu_setup(r, shards, p);
+  if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
+  const int ncol = (int)(r->D / 4);
+  const int nj = (ncol + r->lpr - 1) / r->lpr;
+  entry_fn fn = nullptr;
+  switch (r->bitlevel) {
+    case 0: fn = by_variant<0>(r->opt, r->lpr, r->xw, nj); break;
+    case 1: fn = by_variant<1>(r->opt, r->lpr, r->xw, nj); break;
+    case 2: fn = by_variant<2>(r->opt, r->lpr, r->xw, nj); break;
+  }
+  if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
   g_p = p; g_nu = r->nu; g_nv = r->nv; g_G = r->G;
   {
     const RingLayout L = ring_layout(r->D, r->nu, r->nv, r->threads / 32 - 2);
@@ -452,10 +488,45 @@ int emu_run_ring(const EmuRun *r) {
     blockIdx.x = b; blockIdx.y = blockIdx.z = 0;
     if (!run_block(r->threads, fn)) return 2;
   }
-  for (int i = 0; i < r->num_shards; ++i) {
-    r->loss[i] = shards[i].loss; r->words[i] = shards[i].word_count; r->n_pos[i] = (int64_t)shards[i].n_pos;
-    r->n_ctx[i] = (int64_t)shards[i].n_ctx; r->n_tgt[i] = (int64_t)shards[i].n_tgt; r->done[i] = shards[i].done;
+  emu_results(r, shards);
+  return 0;
+}
+
+// The warp-per-shard kernel (csrc/w2b_warp.cuh): r->nv = ring slots K, r->nu = job queue capacity; one 32-thread
+// CTA per shard, one after another.
+int emu_run_warp(const EmuRun *r) {
+  using namespace w2b;
+  std::vector<ShardState> shards;
+  TrainParams p;
+  emu_setup(r, shards, p);
+  if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
+  const int nj = ((int)(r->D / 4) + 31) / 32;
+  entry_fn fn = nullptr;
+  switch (r->bitlevel) {
+    case 0: fn = warp_by_nj<0>(nj); break;
+    case 1: fn = warp_by_nj<1>(nj); break;
+    case 2: fn = warp_by_nj<2>(nj); break;
+    default: fn = warp_by_nj<9>(nj); break;
   }
+  if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
+  std::vector<int> sen((size_t)kMaxS * (r->num_shards + 1));
+  p.sen = sen.data();
+  g_p = p; g_nv = r->nv; g_nu = r->nu;
+  {
+    const WarpLayout L = warp_layout(r->D, r->nv, r->nu);
+    if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }
+    g_smem_total = L.total;
+    g_rows_end = L.off_jobq;  // the ring: rows of 4*D bytes from offset 0
+    g_ring_end = L.off_jobq;
+    g_rowb = (unsigned)L.rowb;
+  }
+  gridDim.x = r->num_shards;
+  for (int b = 0; b < r->num_shards; ++b) {
+    if (r->only_shard >= 0 && b != r->only_shard) continue;
+    blockIdx.x = b; blockIdx.y = blockIdx.z = 0;
+    if (!run_block(32, fn)) return 2;
+  }
+  emu_results(r, shards);
   return 0;
 }
 }

@@ -38,7 +38,7 @@ __device__ __forceinline__ void bulk_reduce_add(void *dst, unsigned src, unsigne
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 // mode: 0 = load + reduce, 1 = load only, 2 = load + LDS/STS touch + reduce
-__global__ void __launch_bounds__(32) stream_kernel(float *tab, const int *ids, long long per_warp, int rowb, int K, int mode,
+__global__ void __launch_bounds__(32) stream_kernel(float *tab, float *tab2, const int *ids, long long per_warp, int rowb, int K, int mode,
                                                     unsigned long long *sink) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(32) stream_kernel(float *tab, const int *ids, 
   if (lane == 0)
     for (int j = 0; j < K - 1 && j < per_warp; ++j) {
       mbar_expect_tx(bars + 8 * j, rowb);
-      bulk_load(ring + j * rowb, tab + (long long)my[j] * D, rowb, bars + 8 * j);
+      bulk_load(ring + j * rowb, ((my[j] >> 30) ? tab2 : tab) + (long long)(my[j] & 0x3fffffff) * D, rowb, bars + 8 * j);
     }
   unsigned phase = 0;
   int slot = 0, islot = K - 1;
@@ -85,12 +85,12 @@ __global__ void __launch_bounds__(32) stream_kernel(float *tab, const int *ids, 
     }
     __syncwarp();
     if (lane == 0) {
-      if (mode != 1) bulk_reduce_add(tab + (long long)id_j * D, row, rowb);
+      if (mode != 1) bulk_reduce_add(((id_j >> 30) ? tab2 : tab) + (long long)(id_j & 0x3fffffff) * D, row, rowb);
       bulk_commit();
       asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       if (nj < per_warp) {
         mbar_expect_tx(bars + 8 * islot, rowb);
-        bulk_load(ring + islot * rowb, tab + (long long)id_n * D, rowb, bars + 8 * islot);
+        bulk_load(ring + islot * rowb, ((id_n >> 30) ? tab2 : tab) + (long long)(id_n & 0x3fffffff) * D, rowb, bars + 8 * islot);
       }
     }
     __syncwarp();
@@ -119,6 +119,26 @@ int main(int argc, char **argv) {
   for (long long i = 0; i < NIDS; ++i) h[i] = (int)(rnd() * V);
   CK(cudaMalloc(&d_unif, NIDS * 4));
   CK(cudaMemcpy(d_unif, h.data(), NIDS * 4, cudaMemcpyHostToDevice));
+  // training mix (C2 shape): per position 11 context rows of u drawn from the sub-sampled unigram distribution
+  // (sample = 1e-3: keep = (sqrt(f/s)+1)*s/f), then in v the center (same distribution) and 24 negatives ~ f^0.75
+  int *d_mix;
+  {
+    std::vector<double> csub(V), cneg(V);
+    double ss = 0, sn = 0;
+    for (int i = 0; i < V; ++i) {
+      const double f = (1.0 / (i + 1)) / s;
+      const double keep = std::min(1.0, (sqrt(f / 1e-3) + 1.0) * 1e-3 / f);
+      ss += f * keep; csub[i] = ss;
+      sn += pow(f, 0.75); cneg[i] = sn;
+    }
+    for (long long i = 0; i < NIDS; ++i) {
+      const int k = (int)(i % 36);
+      if (k < 12) h[i] = (int)(std::lower_bound(csub.begin(), csub.end(), rnd() * ss) - csub.begin()) | (k == 11 ? (1 << 30) : 0);
+      else h[i] = (int)(std::lower_bound(cneg.begin(), cneg.end(), rnd() * sn) - cneg.begin()) | (1 << 30);
+    }
+    CK(cudaMalloc(&d_mix, NIDS * 4));
+    CK(cudaMemcpy(d_mix, h.data(), NIDS * 4, cudaMemcpyHostToDevice));
+  }
   unsigned long long *sink;
   CK(cudaMalloc(&sink, 8));
   cudaEvent_t e0, e1;
@@ -126,15 +146,15 @@ int main(int argc, char **argv) {
   CK(cudaEventCreate(&e1));
   printf("| D | ids | mode | warps/SM | ring K | rows in flight/SM | M rows/s | GB/s (2 x row bytes) |\n|---|---|---|---|---|---|---|---|\n");
   struct Cfg { int D, wps, K; };
-  std::vector<Cfg> cfgs = {{800, 8, 8}, {800, 10, 6}, {800, 12, 5}, {800, 13, 4}, {800, 13, 5}, {800, 16, 4}, {800, 16, 3}, {800, 20, 3},
-                           {400, 16, 6}, {400, 24, 5}, {400, 32, 4}, {400, 32, 6},
-                           {200, 16, 8}, {200, 24, 8}, {200, 32, 6}, {200, 32, 10},
-                           {100, 32, 8}, {100, 32, 16}};
+  std::vector<Cfg> cfgs = {{800, 8, 8}, {800, 12, 5}, {800, 12, 4}, {800, 12, 3}, {800, 16, 4}, {800, 16, 3}, {800, 20, 3},
+                           {400, 16, 8}, {400, 16, 4}, {400, 24, 5}, {200, 20, 12}, {200, 20, 6}, {200, 28, 8}, {100, 28, 8}};
   for (const Cfg &c : cfgs) {
     const int rowb = c.D * 4;
-    float *tab;
+    float *tab, *tab2;
     CK(cudaMalloc(&tab, (size_t)V * rowb));
     CK(cudaMemset(tab, 0, (size_t)V * rowb));
+    CK(cudaMalloc(&tab2, (size_t)V * rowb));
+    CK(cudaMemset(tab2, 0, (size_t)V * rowb));
     const size_t smem = (size_t)c.K * rowb + 8 * c.K + 16;
     CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -142,13 +162,14 @@ int main(int argc, char **argv) {
     if (per_sm < c.wps) { printf("| %d | - | - | %d | %d | does not fit (%d CTAs/SM) | | |\n", c.D, c.wps, c.K, per_sm); cudaFree(tab); continue; }
     const int grid = sms * c.wps;
     long long per_warp = std::min<long long>(NIDS / grid, (long long)(12.0e9 / rowb / grid)) / 32 * 32;
-    for (int ids = 0; ids < 2; ++ids)
+    for (int ids = 0; ids < 3; ++ids)
       for (int mode = 0; mode < 3; ++mode) {
         if (ids == 1 && mode == 2) continue;
+        if (ids == 0 && mode != 0) continue;
         float best = 1e30f;
         for (int rep = 0; rep < 3; ++rep) {
           CK(cudaEventRecord(e0));
-          stream_kernel<<<grid, 32, smem>>>(tab, ids ? d_unif : d_zipf, per_warp, rowb, c.K, mode, sink);
+          stream_kernel<<<grid, 32, smem>>>(tab, tab2, ids == 2 ? d_mix : ids ? d_unif : d_zipf, per_warp, rowb, c.K, mode, sink);
           CK(cudaEventRecord(e1));
           CK(cudaEventSynchronize(e1));
           CK(cudaGetLastError());
@@ -157,12 +178,13 @@ int main(int argc, char **argv) {
           if (rep) best = std::min(best, ms);
         }
         const double rows = (double)per_warp * grid;
-        printf("| %d | %s | %s | %d | %d | %d | %.1f | %.0f |\n", c.D, ids ? "uniform" : "zipf",
+        printf("| %d | %s | %s | %d | %d | %d | %.1f | %.0f |\n", c.D, ids == 2 ? "train-mix" : ids ? "uniform" : "zipf",
                mode == 0 ? "load+reduce" : mode == 1 ? "load only" : "load+touch+reduce", c.wps, c.K, c.wps * (c.K - 2),
                rows / best / 1e3, rows * rowb * (mode == 1 ? 1 : 2) / best / 1e6);
         fflush(stdout);
       }
     cudaFree(tab);
+    cudaFree(tab2);
   }
   return 0;
 }

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import MODE_FAST, MODE_STRICT, TABLE_SIZE, W2BError, check, lib, ptr
 
 __all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id",
-           "compute_accuracy", "host_unigram_bounds", "host_exptable", "host_keep_thresholds", "host_lcg_tables", "ring_plan"]
+           "compute_accuracy", "host_unigram_bounds", "host_exptable", "host_keep_thresholds", "host_lcg_tables", "ring_plan", "warp_plan"]
 
 
 def device_count():
@@ -60,6 +60,16 @@ def ring_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, m
                       mode=mode, group=group, plain_store=0, kernel=kernel, ring_rows=ring_rows, ring_serial=0)
     out = _lib.RingPlan()
     check(lib.w2b_ring_plan_query(C.byref(cfg), C.byref(out)))
+    return out.as_dict()
+
+
+def warp_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, mode=MODE_FAST, kernel=6, ring_rows=0):
+    """Geometry of the warp-per-shard kernel for a configuration (pure host arithmetic)."""
+    cfg = _lib.Config(vocab_size=vocab_size, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
+                      alpha=0.05, sample=1e-3, reg=reg, iter=1, num_shards=1, shard_begin=0, shard_end=0, device=0,
+                      mode=mode, group=0, plain_store=0, kernel=kernel, ring_rows=ring_rows, ring_serial=0)
+    out = _lib.WarpPlan()
+    check(lib.w2b_warp_plan_query(C.byref(cfg), C.byref(out)))
     return out.as_dict()
 
 

@@ -55,6 +55,13 @@ class RingPlan(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class WarpPlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("warp", "slots", "queue_entries", "warps_per_sm")] + [("smem_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class TraceRec(C.Structure):
     _fields_ = [("center", C.c_int32), ("b", C.c_int32), ("cw", C.c_int32), ("ntargets", C.c_int32),
                 ("targets", C.c_int32 * 64), ("alpha", C.c_float)]
@@ -70,7 +77,7 @@ EXPORTS = [
     "w2b_upload_raw", "w2b_download_table", "w2b_download_exptable", "w2b_export", "w2b_quantize",
     "w2b_device_ptrs", "w2b_nccl_unique_id", "w2b_nccl_init", "w2b_sync", "w2b_scale_tables",
     "w2b_write_packed", "w2b_read_packed_header", "w2b_read_packed", "w2b_checkpoint_save", "w2b_checkpoint_load", "w2b_compute_accuracy",
-    "w2b_host_unigram_bounds", "w2b_host_exptable", "w2b_host_keep_thresholds", "w2b_host_lcg_tables", "w2b_ring_plan_query", "w2b_host_ring_index", "w2b_host_gather_slices",
+    "w2b_host_unigram_bounds", "w2b_host_exptable", "w2b_host_keep_thresholds", "w2b_host_lcg_tables", "w2b_ring_plan_query", "w2b_warp_plan_query", "w2b_host_ring_index", "w2b_host_gather_slices",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -108,6 +115,7 @@ lib.w2b_host_exptable.argtypes = [_vp]
 lib.w2b_host_keep_thresholds.argtypes = [_vp, _i64, _i64, _f, _vp]
 lib.w2b_host_lcg_tables.argtypes = [_vp, _vp, _vp, _vp]
 lib.w2b_ring_plan_query.argtypes = [_P(Config), _P(RingPlan)]
+lib.w2b_warp_plan_query.argtypes = [_P(Config), _P(WarpPlan)]
 lib.w2b_host_ring_index.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]
 lib.w2b_host_gather_slices.argtypes = [_vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]
 lib.w2b_device_count.argtypes = [_P(C.c_int)]

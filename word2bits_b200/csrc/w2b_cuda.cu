@@ -348,7 +348,12 @@ static warp_fn pick_warp(const w2b_ctx *c) {
 // reserved shared memory); at least 3 (one row being worked on, one draining, one in flight).
 static void plan_warp(w2b_ctx *c) {
   c->warp = false;
-  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel != 6) return;
+  int kernel = c->cfg.kernel;
+  if (kernel == 0) {  // A/B hook while both production kernels exist
+    const char *e = getenv("W2B_DEFAULT_KERNEL");
+    if (e) kernel = atoi(e);
+  }
+  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || kernel != 6) return;
   const int nj = (c->ncol + 31) / 32;
   if (nj > 8) return;  // kernels are instantiated for D <= 1024
   const int minb = warp_minb_of(nj);
@@ -492,6 +497,25 @@ extern "C" int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out) {
   out->desc_depth = kND;
   out->max_groups = kMaxGrp;
   out->smem_bytes = (int64_t)tmp.ring_smem;
+  return W2B_OK;
+}
+
+extern "C" int w2b_warp_plan_query(const w2b_config *cfg, w2b_warp_plan *out) {
+  if (!cfg || !out) { w2b_set_error("null argument"); return W2B_EINVAL; }
+  int rc = validate(cfg);
+  if (rc) return rc;
+  w2b_ctx tmp;
+  tmp.cfg = *cfg;
+  tmp.vec = (cfg->layer1_size % 4 == 0) ? 4 : 1;
+  tmp.ncol = (int)((cfg->layer1_size + tmp.vec - 1) / tmp.vec);
+  plan_warp(&tmp);
+  memset(out, 0, sizeof *out);
+  out->warp = tmp.warp ? 1 : 0;
+  if (!tmp.warp) return W2B_OK;
+  out->slots = tmp.warp_k;
+  out->queue_entries = tmp.warp_qcap;
+  out->warps_per_sm = tmp.warp_minb;
+  out->smem_bytes = (int64_t)tmp.warp_smem;
   return W2B_OK;
 }
 
