@@ -47,10 +47,10 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in src and "liboracle" not in src and "w2b_oracle" not in src, f
-                # the emulator (tests/emu) is reachable only through the W2B_EMULATE seam of w2b_ring.cuh,
+                # the emulator (tests/emu) is reachable only through the W2B_EMULATE seam of w2b_ptx.cuh,
                 # a macro no product build defines
                 if "w2b_emu" in src or "libw2bemu" in src:
-                    assert f == "w2b_ring.cuh" and src.count("w2b_emu_ptx.h") == 1 and "#ifdef W2B_EMULATE" in src, f
+                    assert f == "w2b_ptx.cuh" and src.count('#include "w2b_emu_ptx.h"') == 1 and "#ifdef W2B_EMULATE" in src, f
 
 
 @pytest.mark.parametrize("newline_every,min_count,vocab", [(0, 5, 3000), (15, 1, 30), (7, 2, 200)])
