@@ -94,9 +94,9 @@ def train_epoch(corpus, table, u, v, *, size, window, negative, bitlevel, shards
 
 def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, shards, serial=0, alpha=0.05,
                      sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                     slots=0, fault=0):
+                     slots=0, depth=1, fault=0):
     """One pass of every shard (one 32-thread CTA after another) through the emulated warp-per-shard kernel
-    (csrc/w2b_warp.cuh).  Same conventions as train_epoch."""
+    (csrc/w2b_warp.cuh).  Same conventions as train_epoch; depth = bulk-reduce groups left pending (RD)."""
     plan = w2b.warp_plan(size=size, window=window, negative=negative, bitlevel=bitlevel, vocab_size=corpus.vocab_size,
                          ring_rows=slots)
     if not plan["warp"]:
@@ -114,7 +114,8 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
     p = _lib.ptr
     r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
                alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
-               opt=0, lpr=32, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32, serial=serial,
+               opt=0, lpr=32, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=min(depth, plan["slots"] - 2), threads=32,
+               serial=serial,
                u=p(u), v=p(v), table=p(table), keep=p(keep), exptab=p(exptab), tokens=p(tokens), n_tokens=len(tokens),
                shard_start=p(start), shard_first=p(first), alpha=p(a), wca=p(wca), word_budget=0, max_iters=max_iters,
                seed=seed, async_mode=async_mode, train=0 if trace_cap else 1,

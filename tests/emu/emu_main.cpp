@@ -352,7 +352,7 @@ template <int BM, int NJ>
 void warp_entry() {
   w2b::ApplyArgs none;
   memset(&none, 0, sizeof none);
-  w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu, none);
+  w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu, g_G, none);
 }
 template <int BM>
 entry_fn warp_by_nj(int nj) {
@@ -509,15 +509,13 @@ int emu_run_warp(const EmuRun *r) {
     default: fn = warp_by_nj<9>(nj); break;
   }
   if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
-  std::vector<int> sen((size_t)kMaxS * (r->num_shards + 1));
-  p.sen = sen.data();
-  g_p = p; g_nv = r->nv; g_nu = r->nu;
+  g_p = p; g_nv = r->nv; g_nu = r->nu; g_G = r->G > 0 ? r->G : 1;  // G: reduce depth RD
   {
     const WarpLayout L = warp_layout(r->D, r->nv, r->nu);
     if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }
     g_smem_total = L.total;
-    g_rows_end = L.off_jobq;  // the ring: rows of 4*D bytes from offset 0
-    g_ring_end = L.off_jobq;
+    g_rows_end = L.off_sen;  // the ring: rows of 4*D bytes from offset 0
+    g_ring_end = L.off_sen;
     g_rowb = (unsigned)L.rowb;
   }
   gridDim.x = r->num_shards;

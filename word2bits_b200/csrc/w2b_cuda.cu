@@ -111,8 +111,8 @@ struct w2b_ctx {
   size_t ring_smem = 0;
   bool warp = false;       // warp-per-shard kernel (csrc/w2b_warp.cuh) usable for this configuration
   int warp_k = 0, warp_qcap = 0, warp_minb = 0;  // ring slots per warp, job queue entries, warps per SM
+  int warp_rd = 1;         // bulk-reduce groups left pending behind the arithmetic (1..3)
   size_t warp_smem = 0;
-  int *d_sen = nullptr;    // warp kernel: sentence buffers (kMaxS ints per local shard, + 1 for the parity hooks)
   int sm_count = 0;
   long long train_words = 0;
   float *d_u = nullptr, *d_v = nullptr, *d_keep = nullptr, *d_exptab = nullptr, *d_alpha = nullptr;
@@ -317,7 +317,7 @@ static void plan_ring(w2b_ctx *c) {
 }
 
 // ---- warp-per-shard kernel (csrc/w2b_warp.cuh)
-typedef void (*warp_fn)(TrainParams, int, int, ApplyArgs);
+typedef void (*warp_fn)(TrainParams, int, int, int, ApplyArgs);
 // warps (= 1-warp CTAs) per SM the register allocation is sized for; multiples of 4 because the register file is
 // split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96
 static int warp_minb_of(int nj) { return nj >= 5 ? 12 : (nj >= 3 ? 16 : 20); }
@@ -362,6 +362,8 @@ static void plan_warp(w2b_ctx *c) {
   int K = c->cfg.ring_rows > 0 ? std::min(c->cfg.ring_rows, 32) : 16;
   while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap).total > budget) --K;
   if (K < 3) return;
+  // cfg.group doubles as the reduce depth for this kernel (tuning knob; 0 = default)
+  c->warp_rd = std::max(1, std::min(3, std::min(c->cfg.group > 0 ? c->cfg.group : 1, K - 2)));
   c->warp = true;
   c->warp_k = K;
   c->warp_qcap = qcap;
@@ -408,7 +410,6 @@ static TrainParams base_params(const w2b_ctx *c) {
     p.sleep_ns = e ? (unsigned)atoi(e) : 128u;  // flat between 32 and 512 ns on B200 (measured)
   }
   p.wca_scale = c->nranks;
-  p.sen = c->d_sen;
   return p;
 }
 
@@ -620,7 +621,6 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
     CK(cudaMemcpyToSymbol(c_exptab, t, sizeof t));
   }
   CK(cudaMalloc(&c->d_scratch, 64));
-  if (c->warp) CK(cudaMalloc(&c->d_sen, sizeof(int) * (size_t)kMaxS * (c->nlocal + 1)));
   return W2B_OK;
 }
 
@@ -632,7 +632,6 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
   cudaFree(c->d_shards);
   cudaFree(c->d_scratch);
-  cudaFree(c->d_sen);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -790,7 +789,7 @@ static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
     p.shard_base = 0;
     ApplyArgs none;
     memset(&none, 0, sizeof none);
-    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
+    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, none);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
@@ -997,10 +996,9 @@ static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_tra
   if (c->warp) {  // the production kernel's own sampling code (prefetching draw path)
     warp_fn wf = pick_warp(c);
     CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
-    p.sen = c->d_sen + (size_t)kMaxS * c->nlocal;  // the hooks' own sentence buffer
     ApplyArgs none;
     memset(&none, 0, sizeof none);
-    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, none);
   } else if (c->ring) {  // the production kernel's own sampler warp (prefetching draw path)
     ring_fn rf = pick_ring(c);
     CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
@@ -1078,11 +1076,10 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
     CK(t_s.alloc(sizeof(ShardState)));
     CK(cudaMemset(t_s.p, 0, sizeof(ShardState)));
     p.shards = t_s.as<ShardState>();
-    p.sen = c->d_sen + (size_t)kMaxS * c->nlocal;
     p.serial = 1;
     ApplyArgs ap;
     ap.ctx = d_ids; ap.tg = d_ids + cw; ap.cw = cw; ap.nt = nt; ap.f_out = d_f;
-    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, ap);
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, ap);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     if (f_out && nt) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));

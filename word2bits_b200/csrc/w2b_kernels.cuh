@@ -77,7 +77,6 @@ struct TrainParams {
   int serial;                   // ring kernel debug: no prefetch across positions
   unsigned sleep_ns;            // ring kernel: back-off of the sampler/loader polling loops
   int wca_scale;                // multi-GPU: local words stand for wca_scale x as many globally
-  int *sen;                     // warp kernel: sentence buffers, kMaxS ints per local shard
   w2b_trace_rec *trace;
   long long trace_cap;
   unsigned long long *trace_n;

@@ -43,7 +43,7 @@ constexpr int kJobIdMask = 0x3fffffff;
 // Shared-memory carve-up of one warp (host and device agree through this helper).
 struct WarpLayout {
   int rowb, K, qcap;
-  size_t off_ring, off_jobq, off_bar, total;
+  size_t off_ring, off_sen, off_jobq, off_bar, total;
 };
 __host__ __device__ inline WarpLayout warp_layout(long long D, int K, int qcap) {
   WarpLayout L;
@@ -52,6 +52,7 @@ __host__ __device__ inline WarpLayout warp_layout(long long D, int K, int qcap) 
   L.qcap = qcap;
   size_t o = 0;
   L.off_ring = o; o += (size_t)K * L.rowb;
+  L.off_sen = o;  o += sizeof(int) * (size_t)kMaxS;  // the shard's current sentence (:394-413)
   L.off_jobq = o; o += sizeof(int) * (size_t)qcap;
   o = (o + 7) & ~(size_t)7;
   L.off_bar = o;  o += 8 * (size_t)K;
@@ -290,8 +291,10 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
 
 // BM: compile-time bitlevel 0/1/2, 9 = run time.  NJ = float4 columns per lane = ceil(D / 128).  MINB = CTAs (warps)
 // per SM the register allocation is sized for.
+// RD = bulk-reduce groups a warp leaves pending behind the job it just finished (1..3): after job c, jobs <= c - RD
+// have been read out of their slots, so loads run K - 1 - RD jobs ahead of the arithmetic.
 template <int BM, int NJ, int MINB>
-__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap, ApplyArgs ap) {
+__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap, int RD, ApplyArgs ap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
   const WarpLayout L = warp_layout(p.D, K, qcap);
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   const int shard = p.shard_base + blockIdx.x;
   ShardState *shp = p.shards + shard;
   if (!ap.ctx && shp->done) return;
-  int *sen = p.sen + (size_t)shard * kMaxS;
+  int *sen = reinterpret_cast<int *>(smem + L.off_sen);
 
   if (lane == 0) {
     for (int i = 0; i < K; ++i) mbar_init(reinterpret_cast<unsigned long long *>(smem + L.off_bar) + i, 1);
@@ -343,9 +346,9 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   unsigned phase = 0;    // per-slot mbarrier parity
   double loss = 0.0;     // per lane: reported loss of the targets this lane looked after
 
-  // Issue loads while job j <= q_cons + K - 2 (slot of job j - K confirmed free by the last wait_group.read 1).
+  // Issue loads while job j <= q_cons + K - 1 - RD (slot of job j - K confirmed free by the last wait_group.read RD).
   auto pump = [&]() {
-    while (q_issue < q_limit && q_issue + 2 <= q_cons + (unsigned)K) {
+    while (q_issue < q_limit && q_issue + 1 + (unsigned)RD <= q_cons + (unsigned)K) {
       const int e = jobq[q_issue & qmask];
       if (e >= 0 && lane == 0) {
         const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
@@ -360,7 +363,9 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   auto job_done = [&]() {  // the job's group is committed by lane 0; free the slot before it and refill
     if (lane == 0) {
       bulk_commit();
-      bulk_wait_read<1>();
+      if (RD == 1) bulk_wait_read<1>();
+      else if (RD == 2) bulk_wait_read<2>();
+      else bulk_wait_read<3>();
     }
     __syncwarp();
     ++q_cons;
