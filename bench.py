@@ -146,10 +146,52 @@ def _write_text(ids, path_prefix):
     return tmp.name
 
 
-def _ref_runner(po, path, threads, iters):
+def host_core_budget():
+    """Cores this process may use: the affinity mask, capped by a cgroup CPU quota when one is set."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:  # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:  # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n, quota
+
+
+def ref_flavour(po):
+    """The reference's Makefile builds with -march=native (Makefile:2).  oracle/_ref holds such a build
+    (libw2b_ref_native.so, made where the repo was built) beside the portable x86-64-v3 one; the native one is
+    used when it runs on this host (probed in a child process: an illegal instruction must not take the bench down)."""
+    if os.environ.get("W2B_REF_FLAVOUR"):
+        return os.environ["W2B_REF_FLAVOUR"]
+    if po.ref_available("native"):
+        probe = ("import sys; sys.path.insert(0, %r); from oracle import pyoracle as po; r = po.Ref('native'); "
+                 "import numpy as np; print(r.L.ref_quantize(0.3, 1))" % ROOT)
+        try:
+            r = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, timeout=120)
+            if r.returncode == 0:
+                return "native"
+        except Exception:
+            pass
+    return "o3" if po.ref_available("o3") else None
+
+
+def _ref_runner(po, path, threads, iters, flavour):
     """(run_one_pass, words_per_pass, kind) for the reference on `path` with `threads` threads."""
-    if po.ref_available("o3"):
-        ref = po.Ref("o3")
+    if flavour:
+        ref = po.Ref(flavour)
         ref.configure(path, D, WINDOW, NEG, BITS, threads=threads, iters=iters, min_count=1, alpha=ALPHA, sample=SAMPLE)
         ref.learn_vocab(); ref.init_net(); ref.init_unigram()
         return ref.train_epoch, ref.train_words, "reference"
@@ -159,27 +201,28 @@ def _ref_runner(po, path, threads, iters):
 
 
 def run_reference(args, rank, budget_s=100.0):
-    """The reference's own CPU implementation of the path (oracle/_ref = the unmodified source
-    compiled as a library, else the C port) on a bounded sample of the same workload; one step =
-    one pass over the sample (the reference's per-epoch thread launch).  The thread count is the
-    best of {all, 1/2, 1/4, 1/8 of the host threads} on a calibration sample — Hogwild on two
-    sockets can get slower with more threads — and the sample is sized so that W+K passes fit the
-    time budget."""
+    """The reference's own CPU implementation of the path (oracle/_ref = the unmodified source compiled as a
+    library, -march=native like its Makefile when that build runs here, else x86-64-v3; else the C port) on a
+    bounded sample of the same workload; one step = one pass over the sample (the reference's per-epoch thread
+    launch).  Threads: best of {all, 1/2, 1/4 of the cores this process may use} on a >= 2 M-token calibration pass
+    (Hogwild on two sockets can get slower with more threads; a short pass would measure thread start-up instead);
+    the sample is sized so that W+K passes fit the time budget."""
     if rank != 0:
         return None
     from oracle import pyoracle as po
-    cores = os.cpu_count() or 1
+    cores, quota = host_core_budget()
+    flavour = ref_flavour(po)
     cdf, _ = zipf_cdf(V)
-    ids = synth_ids(int(os.environ.get("W2B_REF_MAX_TOKENS", 12_000_000)), 4242, cdf)
+    ids = synth_ids(int(os.environ.get("W2B_REF_MAX_TOKENS", 16_000_000)), 4242, cdf)
     cands = [int(os.environ["W2B_REF_THREADS"])] if "W2B_REF_THREADS" in os.environ else \
-        sorted({max(1, cores // k) for k in (1, 2, 4, 8)}, reverse=True)
-    cal_n = int(os.environ.get("W2B_REF_CAL_TOKENS", 400_000))  # (tests shrink it)
+        sorted({max(1, cores // k) for k in (1, 2, 4)}, reverse=True)
+    cal_n = min(len(ids), int(os.environ.get("W2B_REF_CAL_TOKENS", 2_000_000)))  # (tests shrink it)
     cal = _write_text(ids[:cal_n], "w2b_cal_")
     best = (0.0, cands[-1])
     tried = []
     try:
         for th in cands:
-            run, wpp, kind = _ref_runner(po, cal, th, 1)
+            run, wpp, kind = _ref_runner(po, cal, th, 1, flavour)
             t0 = time.time()
             run()
             rate = wpp / (time.time() - t0)
@@ -190,10 +233,11 @@ def run_reference(args, rank, budget_s=100.0):
         os.unlink(cal)
     rate, threads = best
     passes = args.steps + args.warmup
-    n = int(min(len(ids), max(int(os.environ.get("W2B_REF_MIN_TOKENS", 300_000)), rate * min(15.0, budget_s / passes))))
+    n = int(min(len(ids), max(int(os.environ.get("W2B_REF_MIN_TOKENS", 1_000_000)), rate * min(15.0, budget_s / passes))))
     path = _write_text(ids[:n], "w2b_ref_")
+    distinct = int(len(np.unique(ids[:n])))
     try:
-        run, words_per_pass, kind = _ref_runner(po, path, threads, passes)
+        run, words_per_pass, kind = _ref_runner(po, path, threads, passes, flavour)
         for _ in range(args.warmup):
             run()
         t0 = time.time()
@@ -203,14 +247,20 @@ def run_reference(args, rank, budget_s=100.0):
     finally:
         os.unlink(path)
     value = words_per_pass * args.steps / dt
-    sample = "%d-token Zipf(1.0) V=%d text sample, %d timed passes, %s; threads chosen from %s (words/s on a %d-token calibration sample)" % (
-        n, V, args.steps, "oracle/_ref (unmodified reference, -O3 x86-64-v3)" if kind == "reference" else "oracle C port",
-        tried, cal_n)
+    build = {"native": "oracle/_ref (unmodified reference, -O3 -march=native as its Makefile:2)",
+             "o3": "oracle/_ref (unmodified reference, -O3 -march=x86-64-v3: the native build does not run on this host)",
+             None: "oracle C port"}.get(flavour, "oracle/_ref (%s)" % flavour)
+    sample = ("%d-token Zipf(1.0) V=%d text sample (%d distinct words occur, so fewer table rows than the GPU arm's %d: "
+              "favours the CPU), %d timed passes, %s; threads chosen from %s (words/s on a %d-token calibration pass); "
+              "cores usable by this process: %d%s" % (
+                  n, V, distinct, V, args.steps, build, tried, cal_n, cores,
+                  " (cgroup quota %.1f)" % quota if quota else ""))
     return {"metric": METRIC, "value": value, "unit": "words/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD_TEXT + " (CPU, bounded sample)",
-                       "threads": threads, "host_threads": cores},
+                       "threads": threads, "host_threads": cores, "host_cpu_count": os.cpu_count(),
+                       "distinct_words_in_sample": distinct, "sample_tokens": n},
             "cpu_baseline": {"value": value, "unit": "words/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "words/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

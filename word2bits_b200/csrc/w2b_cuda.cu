@@ -125,10 +125,23 @@ struct w2b_ctx {
   const int32_t *h_ids = nullptr;  // streaming mode: caller-owned
   long long n_tokens = 0;
   bool resident = true, have_counts = false, have_corpus = false, have_tables = false;
-  int *h_stage = nullptr;  // pinned, streaming mode
-  long long stage_cap = 0, stage_len = 0, stage_margin = 4096;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // streaming mode: two staging buffers (pinned host + device).  While a launch reads one, the next launch's
+  // slices are gathered and copied into the other on copy_stream (speculatively: a shard advances by at least
+  // the word budget and at most budget + one sentence, so its next slice is known to within `stage_margin`).
+  int *h_stage[2] = {nullptr, nullptr};
+  int *d_stage[2] = {nullptr, nullptr};
+  long long stage_cap[2] = {0, 0};
+  long long stage_margin = 4096;
+  int stage_cur = 0;  // buffer the next launch reads
+  struct Prefetch {
+    bool valid = false;
+    int buf = 0;
+    long long L = 0, chunk = 0;
+    std::vector<long long> begin, limit;  // per local shard: global index of the slice's first token / its end
+    std::vector<int> eof;
+  } pf;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
   unsigned long long *d_scratch = nullptr;  // 64 B: word-count all-reduce
   nccl_comm comm = nullptr;
   int rank = 0, nranks = 1;
@@ -594,8 +607,10 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
   unsigned long long JA[65], JC[65], PA[64], PC[64];
   lcg_tables(JA, JC, PA, PC);
   CK(cudaMemcpyToSymbol(c_JA, JA, sizeof JA));
@@ -632,10 +647,16 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
   cudaFree(c->d_shards);
   cudaFree(c->d_scratch);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int b = 0; b < 2; ++b) {
+    if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
+    cudaFree(c->d_stage[b]);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
   return W2B_OK;
 }
@@ -696,12 +717,29 @@ static int w2b_set_corpus_impl(w2b_ctx *c, const int32_t *ids, int64_t n, const 
   NEED(shard_start);
   NEED(shard_first);
   if (n < 0 || (n > 0 && !ids)) { w2b_set_error("w2b_set_corpus: bad token stream"); return W2B_EINVAL; }
+  // the kernels use token ids as row indices of u / v and shard starts as stream offsets: check them once
+  for (int i = c->cfg.shard_begin; i < c->cfg.shard_end; ++i) {
+    const int64_t lo = shard_first[i] >= 0 ? 1 : 0;
+    if (shard_start[i] < lo || shard_start[i] > n || shard_first[i] >= c->cfg.vocab_size) {
+      w2b_set_error("w2b_set_corpus: shard %d starts at %lld (first token %d) outside the stream of %lld tokens", i,
+                    (long long)shard_start[i], (int)shard_first[i], (long long)n);
+      return W2B_EINVAL;
+    }
+  }
+  {
+    const uint32_t V = (uint32_t)c->cfg.vocab_size;
+    uint32_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) bad |= (uint32_t)((uint32_t)ids[i] >= V);
+    if (bad) { w2b_set_error("w2b_set_corpus: token id outside [0, %u)", V); return W2B_EINVAL; }
+  }
   CK(cudaSetDevice(c->cfg.device));
   c->n_tokens = n;
   c->resident = resident != 0;
   c->shard_start.assign(shard_start + c->cfg.shard_begin, shard_start + c->cfg.shard_end);
   c->shard_first.assign(shard_first + c->cfg.shard_begin, shard_first + c->cfg.shard_end);
   if (c->d_tokens) { cudaFree(c->d_tokens); c->d_tokens = nullptr; }
+  if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+  c->pf.valid = false;  // slices prefetched from the previous stream are void
   if (c->resident) {
     CK(cudaMalloc(&c->d_tokens, std::max<int64_t>(n, 1) * sizeof(int)));
     CK(cudaMemcpy(c->d_tokens, ids, n * sizeof(int), cudaMemcpyHostToDevice));
@@ -746,108 +784,156 @@ static void sum_shards(const std::vector<ShardState> &s, w2b_step_stats *o) {
   }
 }
 
-// Streaming mode: copy every unfinished shard's next slice into the pinned staging
-// buffer, upload, and point the shard states at it.
-static int stage_slices(w2b_ctx *c, long long want, w2b_step_stats *acc) {
-  const long long L = want + c->stage_margin;
-  const long long need = L * c->nlocal;
-  if (need > c->stage_cap) {
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->d_tokens) cudaFree(c->d_tokens);
-    c->h_stage = nullptr;
-    c->d_tokens = nullptr;
-    CK(cudaMallocHost(&c->h_stage, need * sizeof(int)));
-    CK(cudaMalloc(&c->d_tokens, need * sizeof(int)));
-    c->stage_cap = need;
-  }
-  c->stage_len = L;
-  {  // gather every unfinished shard's next L tokens (host threads: w2b_gather_slices, tested on the CPU)
-    std::vector<long long> cursor(c->nlocal), xlate(c->nlocal), limit(c->nlocal);
-    std::vector<int> done(c->nlocal), eof(c->nlocal);
-    for (int i = 0; i < c->nlocal; ++i) { cursor[i] = c->h_shards[i].cursor; done[i] = c->h_shards[i].done; }
-    w2b_gather_slices(c->h_ids, c->n_tokens, L, c->nlocal, cursor.data(), done.data(), c->h_stage, xlate.data(),
-                      limit.data(), eof.data(), 0);
-    for (int i = 0; i < c->nlocal; ++i) {
-      if (done[i]) continue;
-      c->h_shards[i].xlate = xlate[i];
-      c->h_shards[i].limit = limit[i];
-      c->h_shards[i].limit_is_eof = eof[i];
-    }
-  }
-  CK(cudaMemcpyAsync(c->d_tokens, c->h_stage, need * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice,
-                     c->stream));
-  acc->h2d_bytes += need * (long long)sizeof(int) + (long long)sizeof(ShardState) * c->nlocal;
+// ---- streaming mode (host token buffers)
+static int stage_reserve(w2b_ctx *c, int b, long long need) {
+  if (need <= c->stage_cap[b]) return W2B_OK;
+  c->stage_cap[b] = 0;
+  if (c->h_stage[b]) { cudaFreeHost(c->h_stage[b]); c->h_stage[b] = nullptr; }
+  if (c->d_stage[b]) { cudaFree(c->d_stage[b]); c->d_stage[b] = nullptr; }
+  CK(cudaMallocHost(&c->h_stage[b], need * sizeof(int)));
+  CK(cudaMalloc(&c->d_stage[b], need * sizeof(int)));
+  c->stage_cap[b] = need;
   return W2B_OK;
 }
 
-static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
+// Gathers, for every unfinished shard, the L tokens from `begin[i]` into staging buffer b (slice i at i*L) and
+// starts the H2D copy on `stream`.  Host threads: w2b_gather_slices (tested on the CPU).
+static int stage_gather(w2b_ctx *c, int b, long long L, const std::vector<long long> &begin, cudaStream_t stream,
+                        std::vector<long long> &limit, std::vector<int> &eof, w2b_step_stats *acc) {
+  const long long need = L * c->nlocal;
+  int rc = stage_reserve(c, b, need);
+  if (rc) return rc;
+  std::vector<long long> xlate(c->nlocal);
+  std::vector<int> done(c->nlocal);
+  limit.assign(c->nlocal, 0);
+  eof.assign(c->nlocal, 0);
+  for (int i = 0; i < c->nlocal; ++i) done[i] = c->h_shards[i].done;
+  w2b_gather_slices(c->h_ids, c->n_tokens, L, c->nlocal, begin.data(), done.data(), c->h_stage[b], xlate.data(),
+                    limit.data(), eof.data(), 0);
+  CK(cudaMemcpyAsync(c->d_stage[b], c->h_stage[b], need * sizeof(int), cudaMemcpyHostToDevice, stream));
+  acc->h2d_bytes += need * (long long)sizeof(int);
+  return W2B_OK;
+}
+
+// Points the shard states at the slices of this launch: the prefetched buffer when it covers every unfinished
+// shard's next `chunk + margin` tokens, else a synchronous gather from the cursors.
+static int stage_acquire(w2b_ctx *c, long long chunk, w2b_step_stats *acc) {
+  w2b_ctx::Prefetch &pf = c->pf;
+  bool use = pf.valid && pf.chunk == chunk;
+  if (use)
+    for (int i = 0; i < c->nlocal && use; ++i) {
+      const ShardState &sh = c->h_shards[i];
+      if (sh.done) continue;
+      const long long cur = std::max<long long>(sh.cursor, 0);
+      const long long want_end = std::min<long long>(cur + chunk + c->stage_margin, c->n_tokens);
+      if (cur < pf.begin[i] || want_end > pf.limit[i]) use = false;
+    }
+  if (use) {
+    CK(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    c->stage_cur = pf.buf;
+    for (int i = 0; i < c->nlocal; ++i) {
+      ShardState &sh = c->h_shards[i];
+      if (sh.done) continue;
+      sh.xlate = pf.begin[i] - (long long)i * pf.L;
+      sh.limit = pf.limit[i];
+      sh.limit_is_eof = pf.eof[i];
+    }
+  } else {
+    if (pf.valid) CK(cudaStreamSynchronize(c->copy_stream));  // its buffer may be the one re-used below
+    const long long L = chunk + c->stage_margin;
+    std::vector<long long> begin(c->nlocal), limit;
+    std::vector<int> eof;
+    for (int i = 0; i < c->nlocal; ++i) begin[i] = std::max<long long>(c->h_shards[i].cursor, 0);
+    int rc = stage_gather(c, c->stage_cur, L, begin, c->stream, limit, eof, acc);
+    if (rc) return rc;
+    for (int i = 0; i < c->nlocal; ++i) {
+      ShardState &sh = c->h_shards[i];
+      if (sh.done) continue;
+      sh.xlate = begin[i] - (long long)i * L;
+      sh.limit = limit[i];
+      sh.limit_is_eof = eof[i];
+    }
+  }
+  pf.valid = false;
+  CK(cudaMemcpyAsync(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice,
+                     c->stream));
+  acc->h2d_bytes += (long long)sizeof(ShardState) * c->nlocal;
+  return W2B_OK;
+}
+
+// While the launch that was just enqueued runs: gather and upload what the NEXT launch of the same budget will
+// read.  A shard that starts at cursor c ends this launch in [c + chunk, c + chunk + one sentence], so the slice
+// [c + chunk, c + 2*chunk + 2*margin) covers the next launch's cursor .. cursor + chunk + margin.
+static int stage_prefetch(w2b_ctx *c, long long chunk, w2b_step_stats *acc) {
+  w2b_ctx::Prefetch &pf = c->pf;
+  pf.valid = false;
+  pf.buf = c->stage_cur ^ 1;
+  pf.chunk = chunk;
+  pf.L = chunk + 2 * c->stage_margin;
+  pf.begin.assign(c->nlocal, 0);
+  for (int i = 0; i < c->nlocal; ++i) pf.begin[i] = std::max<long long>(c->h_shards[i].cursor, 0) + chunk;
+  int rc = stage_gather(c, pf.buf, pf.L, pf.begin, c->copy_stream, pf.limit, pf.eof, acc);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev_copy, c->copy_stream));
+  pf.valid = true;
+  return W2B_OK;
+}
+
+// Enqueues the training kernel(s) of one launch on the context's stream (between ev0 and ev1).
+static int launch_enqueue(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int launches = 1;
   if (c->warp) {  // production path: one warp (a 32-thread CTA) per shard
     warp_fn wf = pick_warp(c);
     CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
-    CK(cudaEventRecord(c->ev0, c->stream));
     p.shard_base = 0;
     ApplyArgs none;
     memset(&none, 0, sizeof none);
     wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, none);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
-    CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
-                       c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    acc->kernel_ms += ms;
-    acc->launches += 1;
-    acc->d2h_bytes += (long long)sizeof(ShardState) * c->nlocal;
-    return W2B_OK;
-  }
-  if (c->ring) {  // production path: TMA ring kernel, one CTA per shard
+  } else if (c->ring) {  // round-1 production path: TMA ring kernel, one CTA per shard
     ring_fn rf = pick_ring(c);
     CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
-    CK(cudaEventRecord(c->ev0, c->stream));
     p.shard_base = 0;
     rf<<<c->nlocal, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv, c->ring_g);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
-    CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
-                       c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    acc->kernel_ms += ms;
-    acc->launches += 1;
-    acc->d2h_bytes += (long long)sizeof(ShardState) * c->nlocal;
-    return W2B_OK;
-  }
-  train_fn fn = pick_train(c);
-  if (!fn) { w2b_set_error("no kernel for this configuration"); return W2B_EINVAL; }
-  const size_t smem = dyn_smem(c);
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaEventRecord(c->ev0, c->stream));
-  int launches = 0;
-  if (c->cfg.mode == W2B_MODE_STRICT) {
-    for (int i = 0; i < c->nlocal; ++i) {  // shards one after another, like joined threads
-      p.shard_base = i;
-      fn<<<1, c->threads, smem, c->stream>>>(p);
-      ++launches;
-    }
   } else {
-    p.shard_base = 0;
-    fn<<<c->nlocal, c->threads, smem, c->stream>>>(p);
-    ++launches;
+    train_fn fn = pick_train(c);
+    if (!fn) { w2b_set_error("no kernel for this configuration"); return W2B_EINVAL; }
+    const size_t smem = dyn_smem(c);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->cfg.mode == W2B_MODE_STRICT) {
+      launches = 0;
+      for (int i = 0; i < c->nlocal; ++i) {  // shards one after another, like joined threads
+        p.shard_base = i;
+        fn<<<1, c->threads, smem, c->stream>>>(p);
+        ++launches;
+      }
+    } else {
+      p.shard_base = 0;
+      fn<<<c->nlocal, c->threads, smem, c->stream>>>(p);
+    }
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->stream));
+  acc->launches += launches;
+  return W2B_OK;
+}
+
+// Waits for the launch and reads the shard states back.
+static int launch_finish(w2b_ctx *c, w2b_step_stats *acc) {
   CK(cudaMemcpyAsync(c->h_shards.data(), c->d_shards, sizeof(ShardState) * c->nlocal, cudaMemcpyDeviceToHost,
                      c->stream));
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   acc->kernel_ms += ms;
-  acc->launches += launches;
   acc->d2h_bytes += (long long)sizeof(ShardState) * c->nlocal;
   return W2B_OK;
+}
+
+static int launch_train(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
+  int rc = launch_enqueue(c, p, acc);
+  if (rc) return rc;
+  return launch_finish(c, acc);
 }
 
 static int w2b_train_step_impl(w2b_ctx *c, int64_t words_per_shard, w2b_step_stats *stats);
@@ -887,17 +973,22 @@ static int w2b_train_step_impl(w2b_ctx *c, int64_t words_per_shard, w2b_step_sta
       }
     }
   } else {
-    // streaming: slices of (budget + margin) tokens; run-to-end loops over slices
+    // streaming: slices of (budget + margin) tokens; run-to-end loops over slices.  The slices of the launch after
+    // this one are gathered and uploaded while this one runs (stage_prefetch).
     long long left = words_per_shard;
     for (;;) {
       const long long chunk = words_per_shard > 0 ? std::min(left, kSliceWords) : 65536;
-      int rc = stage_slices(c, chunk, &acc);
+      int rc = stage_acquire(c, chunk, &acc);
       if (rc) return rc;
-      p.tokens = c->d_tokens;
+      p.tokens = c->d_stage[c->stage_cur];
       p.word_budget = chunk;
       std::vector<long long> wc_before(c->nlocal);
       for (int i = 0; i < c->nlocal; ++i) wc_before[i] = c->h_shards[i].word_count;
-      rc = launch_train(c, p, &acc);
+      rc = launch_enqueue(c, p, &acc);
+      if (rc) return rc;
+      rc = stage_prefetch(c, chunk, &acc);  // overlaps the kernel; cursors are still the pre-launch ones
+      if (rc) return rc;
+      rc = launch_finish(c, &acc);
       if (rc) return rc;
       w2b_step_stats a2;
       sum_shards(c->h_shards, &a2);
