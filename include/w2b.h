@@ -30,7 +30,7 @@ extern "C" {
 #define W2B_MAX_WINDOW 64
 #define W2B_MAX_NEGATIVE 63
 
-#define W2B_MODE_FAST 0   /* production: one CTA per shard, all shards concurrent (Hogwild) */
+#define W2B_MODE_FAST 0   /* production: one warp per shard, all shards concurrent (Hogwild) */
 #define W2B_MODE_STRICT 1 /* parity: shards one after another, sequential IEEE op order */
 
 /* ------------------------------------------------------------------ host glue (no GPU)
@@ -103,16 +103,14 @@ typedef struct {
   int32_t shard_end;   /*   (0,0 = all; used to split S across GPUs) */
   int32_t device;      /* CUDA device ordinal */
   int32_t mode;        /* W2B_MODE_FAST | W2B_MODE_STRICT */
-  int32_t group;       /* fast mode: target rows in flight per CTA step (0 = default) */
+  int32_t group;       /* register kernel: target rows in flight per CTA step (0 = default) */
   int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
-  int32_t kernel;      /* fast mode: 0 = TMA ring kernel when applicable (default), 1 = register kernel,
-                          experimental variants of the ring kernel: 2 = division-free index arithmetic,
-                          3 / 4 = 2 + 16 / 8 lanes per target row (narrow rows, D <= 512 / 256),
-                          5 = 2 + two more consumer warps (wide rows, D > 512);
-                          6 = warp-per-shard kernel (one 32-thread CTA per shard) */
-  int32_t ring_rows;   /* ring kernel: v-ring depth in rows (0 = as many as fit) */
-  int32_t ring_serial; /* ring kernel parity aid: 1 = fetch position p+1 only after p's updates landed;
-                          2 (kernel >= 2 only, experimental) = prefetching with early slot release */
+  int32_t kernel;      /* fast mode: 0 = warp-per-shard kernel when applicable (default; csrc/w2b_warp.cuh),
+                          1 = register kernel (one CTA per shard; also serves strict mode, D % 4 != 0, D > 1024) */
+  int32_t slots;       /* warp kernel: shared-memory row slots per warp (0 = as many as fit, at most 16) */
+  int32_t prefetch;    /* warp kernel: 0 = the positions of a shard strictly one after another, like a reference
+                          thread (default; measured free on B200); 1 = rows of position p+1 are fetched before p's
+                          updates have landed (a context row shared by neighbours is read one update stale) */
 } w2b_config;
 
 typedef struct {
@@ -140,29 +138,9 @@ typedef struct {
 const char *w2b_last_error(void);
 int w2b_device_count(int *n);
 
-/* Geometry the production (TMA ring) kernel would run with for a configuration: pure host arithmetic
- * (no CUDA call).  ring = 0 means the configuration runs the register kernel instead (D % 4 != 0,
- * D > 1024, reg != 0, strict mode, kernel = 1, or no ring fits 227 KB of shared memory). */
-typedef struct {
-  int32_t ring;            /* 1 = ring kernel applies */
-  int32_t group;           /* target rows per landing barrier (G) */
-  int32_t consumer_warps;  /* warps doing the arithmetic; + 1 loader warp + 1 sampler warp */
-  int32_t rows_in_flight;  /* target rows a consumer warp holds at once (R) */
-  int32_t u_rows, v_rows;  /* ring depths in rows of 4*D bytes */
-  int32_t threads;         /* CTA size */
-  int32_t desc_depth;      /* positions in flight (descriptor ring) */
-  int32_t max_groups;      /* landing barriers per descriptor slot */
-  int32_t units_per_warp;  /* target rows a consumer warp works on side by side (1; 2 / 4 for cfg.kernel 3 / 4) */
-  int32_t reserved;
-  int64_t smem_bytes;      /* dynamic shared memory per CTA */
-} w2b_ring_plan;
-int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out);
-/* Slot and landing-barrier index of target row i of a position whose first row sits in slot vs0, as the
- * kernel = 2 variant computes them (multiply-high by a precomputed reciprocal instead of % and /). */
-int w2b_host_ring_index(int vs0, int i, int nv, int G, int *slot, int *group);
-
-/* Geometry of the warp-per-shard kernel (csrc/w2b_warp.cuh; cfg.kernel = 6) for a configuration: pure host
- * arithmetic.  warp = 0: the configuration runs another kernel (D % 4 != 0, D > 1024, reg != 0, strict mode). */
+/* Geometry the production (warp-per-shard) kernel would run with for a configuration: pure host arithmetic (no
+ * CUDA call).  warp = 0: the configuration runs the register kernel instead (D % 4 != 0, D > 1024, reg != 0,
+ * strict mode, kernel = 1). */
 typedef struct {
   int32_t warp;           /* 1 = the warp kernel applies */
   int32_t slots;          /* K: shared-memory row slots of a warp's ring (K-2 loads in flight) */
@@ -172,7 +150,7 @@ typedef struct {
 } w2b_warp_plan;
 int w2b_warp_plan_query(const w2b_config *cfg, w2b_warp_plan *out);
 
-/* Number of shards that keeps every SM busy for this configuration (SMs x resident CTAs);
+/* Number of shards that keeps every SM busy for this configuration (SMs x resident warps of the production kernel);
  * the CLI's default for -threads (the reference's default of 12 is a CPU core count). */
 int w2b_suggest_shards(const w2b_config *cfg, int *out);
 int w2b_create(const w2b_config *cfg, w2b_ctx **out); /* globals :45-61 -> context */

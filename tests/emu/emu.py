@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — ctypes front end of tests/emu/libw2bemu.so: the production kernel's source compiled for
-the host and run on fibers (tests/emu/emu_main.cpp).  Used by tests/test_ring_emulation.py to check kernel
-variants functionally when no GPU is at hand."""
+the host and run on fibers (tests/emu/emu_main.cpp).  Used by tests/test_warp_emulation.py to check the kernel
+functionally when no GPU is at hand."""
 import ctypes as C
 import os
 import subprocess
@@ -36,7 +36,6 @@ def lib():
         subprocess.check_call(["make", "-s", "-C", HERE], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         _emu = C.CDLL(os.path.join(HERE, "libw2bemu.so"))
         _emu.emu_last_error.restype = C.c_char_p
-        _emu.emu_run_ring.argtypes = [C.POINTER(EmuRun)]
         _emu.emu_run_warp.argtypes = [C.POINTER(EmuRun)]
     return _emu
 
@@ -45,60 +44,14 @@ class EmuError(RuntimeError):
     pass
 
 
-def train_epoch(corpus, table, u, v, *, size, window, negative, bitlevel, shards, kernel=0, serial=0, alpha=0.05,
-                sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                plan_override=None, group=0, ring_rows=0, fault=0):
-    """One pass of every shard (one CTA after another) through the emulated ring kernel variant `kernel`
-    (cfg.kernel numbering).  u, v are updated in place.  Returns a dict of per-shard statistics; `state` carries
-    (alpha, word_count_actual) across epochs."""
-    plan = w2b.ring_plan(size=size, window=window, negative=negative, bitlevel=bitlevel, kernel=kernel,
-                         vocab_size=corpus.vocab_size, group=group, ring_rows=ring_rows)
-    if not plan["ring"]:
-        raise EmuError("the ring kernel does not apply to this shape")
-    plan.update(plan_override or {})
-    upw = plan["units_per_warp"]
-    base_ncw = max((size // 4 + 31) // 32, 4)
-    start, first = corpus.shards(shards)
-    keep = w2b.host_keep_thresholds(corpus.counts, corpus.train_words, sample)
-    exptab = w2b.host_exptable()
-    tokens = np.ascontiguousarray(corpus.tokens, np.int32)
-    a = np.array([alpha if state is None else state[0]], np.float32)
-    wca = np.array([0 if state is None else state[1]], np.uint64)
-    out = dict(loss=np.zeros(shards), words=np.zeros(shards, np.int64), n_pos=np.zeros(shards, np.int64),
-               n_ctx=np.zeros(shards, np.int64), n_tgt=np.zeros(shards, np.int64), done=np.zeros(shards, np.int32))
-    trace = (_lib.TraceRec * max(trace_cap, 1))()
-    trace_n = np.zeros(1, np.uint64)
-    p = _lib.ptr
-    r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
-               alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
-               opt=1 if kernel >= 2 else 0, lpr=32 // upw, xw=plan["consumer_warps"] - base_ncw, nu=plan["u_rows"],
-               nv=plan["v_rows"], G=plan["group"], threads=plan["threads"], serial=serial,
-               u=p(u), v=p(v), table=p(table), keep=p(keep), exptab=p(exptab), tokens=p(tokens), n_tokens=len(tokens),
-               shard_start=p(start), shard_first=p(first), alpha=p(a), wca=p(wca), word_budget=0, max_iters=max_iters,
-               seed=seed, async_mode=async_mode, train=0 if trace_cap else 1,
-               loss=p(out["loss"]), words=p(out["words"]), n_pos=p(out["n_pos"]), n_ctx=p(out["n_ctx"]),
-               n_tgt=p(out["n_tgt"]), done=p(out["done"]),
-               trace=C.cast(trace, C.c_void_p) if trace_cap else None, trace_cap=trace_cap,
-               trace_n=p(trace_n) if trace_cap else None, only_shard=-1 if trace_shard is None else trace_shard,
-               fault=fault)
-    rc = lib().emu_run_ring(C.byref(r))
-    if rc:
-        raise EmuError(lib().emu_last_error().decode())
-    out["alpha"], out["wca"] = float(a[0]), int(wca[0])
-    out["plan"] = plan
-    if trace_cap:
-        n = int(trace_n[0])
-        out["trace"] = [(t.center, t.b, t.cw, list(t.targets[: t.ntargets]), t.alpha) for t in trace[: min(n, trace_cap)]]
-    return out
-
-
 def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, shards, serial=0, alpha=0.05,
                      sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                     slots=0, depth=1, fault=0):
+                     slots=0, red=0, fault=0):
     """One pass of every shard (one 32-thread CTA after another) through the emulated warp-per-shard kernel
-    (csrc/w2b_warp.cuh).  Same conventions as train_epoch; depth = bulk-reduce groups left pending (RD)."""
+    (csrc/w2b_warp.cuh).  u, v are updated in place.  Returns a dict of per-shard statistics; `state` carries
+    (alpha, word_count_actual) across epochs."""
     plan = w2b.warp_plan(size=size, window=window, negative=negative, bitlevel=bitlevel, vocab_size=corpus.vocab_size,
-                         ring_rows=slots)
+                         slots=slots)
     if not plan["warp"]:
         raise EmuError("the warp kernel does not apply to this shape")
     start, first = corpus.shards(shards)
@@ -114,7 +67,7 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
     p = _lib.ptr
     r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
                alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
-               opt=0, lpr=32, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=min(depth, plan["slots"] - 2), threads=32,
+               opt=red, lpr=32, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32,
                serial=serial,
                u=p(u), v=p(v), table=p(table), keep=p(keep), exptab=p(exptab), tokens=p(tokens), n_tokens=len(tokens),
                shard_start=p(start), shard_first=p(first), alpha=p(a), wca=p(wca), word_budget=0, max_iters=max_iters,

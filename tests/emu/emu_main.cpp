@@ -1,6 +1,6 @@
-// TEST INFRASTRUCTURE — runs the product's production kernel (train_ring_kernel and its variants, compiled from
-// word2bits_b200/csrc/w2b_ring.cuh with -DW2B_EMULATE) on the CPU: one fiber per CUDA thread, one CTA (= one
-// corpus shard) after another.  Purpose: functional verification of kernel variants without a GPU — same
+// TEST INFRASTRUCTURE — runs the product's production kernel (train_warp_kernel, compiled from
+// word2bits_b200/csrc/w2b_warp.cuh with -DW2B_EMULATE) on the CPU: one fiber per CUDA thread, one CTA (= one
+// corpus shard) after another.  Purpose: functional verification of the kernel without a GPU — same
 // source, same control flow, same index arithmetic and protocol; only the PTX wrappers and the intrinsics are
 // host code.  It is not a timing model and not a fallback: nothing under word2bits_b200/ references it.
 #include <stdio.h>
@@ -11,7 +11,6 @@
 #include <random>
 #include <vector>
 
-#include "w2b_ring.cuh"
 #include "w2b_warp.cuh"
 
 uint3 threadIdx, blockIdx;
@@ -321,50 +320,25 @@ bool run_block(int nthreads, void (*entry)()) {
 }
 
 w2b::TrainParams g_p;
-int g_nu, g_nv, g_G;
-template <int BM, int NJ, int OPT, int LPR, int XW>
-void entry() { w2b::train_ring_kernel<BM, NJ, 2, OPT, LPR, XW>(g_p, g_nu, g_nv, g_G); }
-
+int g_nu, g_nv;
 typedef void (*entry_fn)();
-template <int BM, int OPT, int LPR, int XW>
-entry_fn by_nj(int nj) {
-  switch (nj) {
-    case 1: return entry<BM, 1, OPT, LPR, XW>;
-    case 2: return entry<BM, 2, OPT, LPR, XW>;
-    case 3: return entry<BM, 3, OPT, LPR, XW>;
-    case 4: return entry<BM, 4, OPT, LPR, XW>;
-    case 5: return entry<BM, 5, OPT, LPR, XW>;
-    case 6: return entry<BM, 6, OPT, LPR, XW>;
-    case 7: return entry<BM, 7, OPT, LPR, XW>;
-    case 8: return entry<BM, 8, OPT, LPR, XW>;
-  }
-  return nullptr;
-}
-template <int BM>
-entry_fn by_variant(int opt, int lpr, int xw, int nj) {
-  if (xw == 2) return by_nj<BM, 1, 32, 2>(nj);
-  if (lpr == 16) return by_nj<BM, 1, 16, 0>(nj);
-  if (lpr == 8) return by_nj<BM, 1, 8, 0>(nj);
-  return opt ? by_nj<BM, 1, 32, 0>(nj) : by_nj<BM, 0, 32, 0>(nj);
-}
-
-template <int BM, int NJ>
+template <int BM, int NJ, int RG>
 void warp_entry() {
   w2b::ApplyArgs none;
   memset(&none, 0, sizeof none);
-  w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu, g_G, none);
+  w2b::train_warp_kernel<BM, NJ, 12, RG>(g_p, g_nv, g_nu, none);
 }
-template <int BM>
+template <int BM, int RG>
 entry_fn warp_by_nj(int nj) {
   switch (nj) {
-    case 1: return warp_entry<BM, 1>;
-    case 2: return warp_entry<BM, 2>;
-    case 3: return warp_entry<BM, 3>;
-    case 4: return warp_entry<BM, 4>;
-    case 5: return warp_entry<BM, 5>;
-    case 6: return warp_entry<BM, 6>;
-    case 7: return warp_entry<BM, 7>;
-    case 8: return warp_entry<BM, 8>;
+    case 1: return warp_entry<BM, 1, RG>;
+    case 2: return warp_entry<BM, 2, RG>;
+    case 3: return warp_entry<BM, 3, RG>;
+    case 4: return warp_entry<BM, 4, RG>;
+    case 5: return warp_entry<BM, 5, RG>;
+    case 6: return warp_entry<BM, 6, RG>;
+    case 7: return warp_entry<BM, 7, RG>;
+    case 8: return warp_entry<BM, 8, RG>;
   }
   return nullptr;
 }
@@ -447,7 +421,7 @@ static void emu_setup(const EmuRun *r, std::vector<w2b::ShardState> &shards, w2b
   p.alpha_denom = (float)(r->iter * r->train_words + 1);
   p.shard_word_limit = r->train_words / r->num_shards;
   p.word_budget = r->word_budget; p.max_iters = r->max_iters; p.shard_base = 0; p.train = r->train;
-  p.plain_store = 0; p.serial = r->serial; p.sleep_ns = 0; p.wca_scale = 1;
+  p.plain_store = 0; p.serial = r->serial; p.wca_scale = 1;
   p.trace = r->trace; p.trace_cap = r->trace_cap; p.trace_n = (unsigned long long *)r->trace_n;
 }
 
@@ -456,40 +430,6 @@ static void emu_results(const EmuRun *r, const std::vector<w2b::ShardState> &sha
     r->loss[i] = shards[i].loss; r->words[i] = shards[i].word_count; r->n_pos[i] = (int64_t)shards[i].n_pos;
     r->n_ctx[i] = (int64_t)shards[i].n_ctx; r->n_tgt[i] = (int64_t)shards[i].n_tgt; r->done[i] = shards[i].done;
   }
-}
-
-int emu_run_ring(const EmuRun *r) {
-  using namespace w2b;
-  std::vector<ShardState> shards;
-  TrainParams p;
-  emu_setup(r, shards, p);
-  if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
-  const int ncol = (int)(r->D / 4);
-  const int nj = (ncol + r->lpr - 1) / r->lpr;
-  entry_fn fn = nullptr;
-  switch (r->bitlevel) {
-    case 0: fn = by_variant<0>(r->opt, r->lpr, r->xw, nj); break;
-    case 1: fn = by_variant<1>(r->opt, r->lpr, r->xw, nj); break;
-    case 2: fn = by_variant<2>(r->opt, r->lpr, r->xw, nj); break;
-  }
-  if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
-  g_p = p; g_nu = r->nu; g_nv = r->nv; g_G = r->G;
-  {
-    const RingLayout L = ring_layout(r->D, r->nu, r->nv, r->threads / 32 - 2);
-    if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }
-    g_smem_total = L.total;
-    g_rows_end = L.off_rc;    // rows of 4*D bytes from offset 0: u-ring, v-ring, staging, context_avg, partials
-    g_ring_end = L.off_err;   // ... of which the two rings take bulk loads
-    g_rowb = (unsigned)L.rowb;
-  }
-  gridDim.x = r->num_shards;
-  for (int b = 0; b < r->num_shards; ++b) {
-    if (r->only_shard >= 0 && b != r->only_shard) continue;
-    blockIdx.x = b; blockIdx.y = blockIdx.z = 0;
-    if (!run_block(r->threads, fn)) return 2;
-  }
-  emu_results(r, shards);
-  return 0;
 }
 
 // The warp-per-shard kernel (csrc/w2b_warp.cuh): r->nv = ring slots K, r->nu = job queue capacity; one 32-thread
@@ -502,14 +442,14 @@ int emu_run_warp(const EmuRun *r) {
   if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
   const int nj = ((int)(r->D / 4) + 31) / 32;
   entry_fn fn = nullptr;
-  switch (r->bitlevel) {
-    case 0: fn = warp_by_nj<0>(nj); break;
-    case 1: fn = warp_by_nj<1>(nj); break;
-    case 2: fn = warp_by_nj<2>(nj); break;
-    default: fn = warp_by_nj<9>(nj); break;
+  switch (r->bitlevel) {  // r->opt: scatter-adds through red.global (RG = 1) instead of the bulk-copy engine
+    case 0: fn = r->opt ? warp_by_nj<0, 1>(nj) : warp_by_nj<0, 0>(nj); break;
+    case 1: fn = r->opt ? warp_by_nj<1, 1>(nj) : warp_by_nj<1, 0>(nj); break;
+    case 2: fn = r->opt ? warp_by_nj<2, 1>(nj) : warp_by_nj<2, 0>(nj); break;
+    default: fn = r->opt ? warp_by_nj<9, 1>(nj) : warp_by_nj<9, 0>(nj); break;
   }
   if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
-  g_p = p; g_nv = r->nv; g_nu = r->nu; g_G = r->G > 0 ? r->G : 1;  // G: reduce depth RD
+  g_p = p; g_nv = r->nv; g_nu = r->nu;
   {
     const WarpLayout L = warp_layout(r->D, r->nv, r->nu);
     if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }

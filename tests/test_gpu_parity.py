@@ -69,7 +69,7 @@ def test_tables_bit_exact(medium):
 ])
 @pytest.mark.parametrize("kernel", [0, 1])
 def test_draw_trace_bit_exact(cfg, kernel, small, medium):
-    """kernel=0: the ring kernel's sampler warp (jump-ahead + prefetched table lookups);
+    """kernel=0: the production (warp-per-shard) kernel's sampling code (jump-ahead + prefetched table lookups);
     kernel=1: the register kernel's inline sampler.  Both must replay the oracle's draws exactly."""
     name, mc, W, neg, sample, shards = cfg
     path = {"small": small, "medium": medium}[name]
@@ -88,8 +88,12 @@ def test_draw_trace_bit_exact(cfg, kernel, small, medium):
 
 # ------------------------------------------------------------------------------------ L1
 @pytest.mark.parametrize("b,D,reg", [(1, 200, 0.0), (2, 400, 0.0), (0, 400, 0.0), (5, 100, 0.0), (1, 800, 0.0),
-                                      (1, 50, 0.0), (2, 64, 0.01)])
+                                      (0, 800, 0.0), (2, 800, 0.0), (0, 200, 0.0), (2, 200, 0.0), (1, 400, 0.0),
+                                      (1, 1024, 0.0), (1, 4, 0.0), (1, 50, 0.0), (2, 64, 0.01)])
 def test_single_step(b, D, reg, medium):
+    """L1: one explicit position through the kernel that trains this configuration — w2b_apply_position launches the
+    production (warp-per-shard) kernel itself for every D % 4 == 0, reg == 0 case (the BASELINE shapes D = 800 / 400 /
+    200 at bitlevel 0 / 1 / 2 among them), the register kernel for D = 50 and reg != 0."""
     c = w2b.Corpus(medium, 5)
     o = po.Corpus(medium, 5)
     V = c.vocab_size
@@ -210,23 +214,22 @@ def test_stepwise_equals_epoch(medium):
 
 
 # ------------------------------------------------------------------------------------ L3
-# kernel 0 = TMA ring kernel (production), 1 = register kernel; serial=1 = ring kernel with the
-# cross-position prefetch off.  All run S shards concurrently (Hogwild), so the comparator is the
+# kernel 0 = warp-per-shard kernel (production), 1 = register kernel; prefetch=1 = production kernel with rows
+# fetched across position boundaries.  All run S shards concurrently (Hogwild), so the comparator is the
 # oracle with S concurrent pthreads (the reference's own execution model), not sequential shards.
-# Bars: epoch loss within 1 % (3 % at D=800 on this 5k-word vocabulary, where 16
-# concurrent shards collide on rows far more often than at V=400k); sign agreement at b=1 at least
-# the reference's own run-to-run agreement minus 5 points (0.852 -> 0.80 at equal concurrency;
-# 0.70 floor); master weights strongly correlated.
-@pytest.mark.parametrize("b,D,neg,group,kernel,serial", [
+# Bars: epoch loss within 1 % (2 % with prefetch at D=800 on this 5k-word vocabulary, where a
+# stale context row weighs most); sign agreement at b=1 at least the reference's own run-to-run agreement minus
+# 5 points (0.852 -> 0.80 at equal concurrency; 0.70 floor); master weights strongly correlated.
+@pytest.mark.parametrize("b,D,neg,group,kernel,prefetch", [
     (1, 200, 24, 0, 0, 0), (2, 100, 12, 0, 0, 0), (0, 100, 24, 0, 0, 0), (1, 800, 24, 0, 0, 0), (5, 64, 5, 0, 0, 0),
-    (1, 200, 24, 0, 0, 1), (0, 400, 24, 0, 0, 0), (2, 400, 12, 0, 0, 0), (1, 100, 5, 4, 0, 0),
+    (1, 200, 24, 0, 0, 1), (0, 400, 24, 0, 0, 0), (2, 400, 12, 0, 0, 0), (1, 100, 5, 0, 0, 0), (1, 800, 24, 0, 0, 1),
     (1, 200, 24, 0, 1, 0), (0, 100, 24, 9, 1, 0), (1, 800, 24, 5, 1, 0), (2, 50, 12, 0, 0, 0)])
-def test_fast_statistical(b, D, neg, group, kernel, serial, large):
+def test_fast_statistical(b, D, neg, group, kernel, prefetch, large):
     shards = 16
     c = w2b.Corpus(large, 5)
     o = po.Corpus(large, 5)
     t = w2b.Trainer(c, size=D, window=8, negative=neg, bitlevel=b, threads=shards, iter=2, group=group,
-                    kernel=kernel, ring_serial=serial)
+                    kernel=kernel, prefetch=prefetch)
     m = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=2)
     words_total = 0
     for ep in range(2):
@@ -234,7 +237,7 @@ def test_fast_statistical(b, D, neg, group, kernel, serial, large):
         lg, st = t.train_epoch()
         words_total += st["words"]
         assert st["shards_done"] == shards
-        assert abs(lg - lo) <= (0.03 if D >= 800 else 0.01) * abs(lo), (ep, lg, lo)
+        assert abs(lg - lo) <= (0.02 if (D >= 800 and prefetch) else 0.01) * abs(lo), (ep, lg, lo)
     a, wca = t.get_state()
     # the device counter is an atomic: exact.  The oracle's 16 threads race on word_count_actual
     # like the reference's do (:380,:415) and may lose increments, never gain any.
@@ -248,8 +251,8 @@ def test_fast_statistical(b, D, neg, group, kernel, serial, large):
     cu = np.corrcoef(u.ravel(), m.u.ravel())[0, 1]
     cv = np.corrcoef(v.ravel(), m.v.ravel())[0, 1]
     agree = np.mean(bits(out) == bits(m.export())) if b == 1 else 1.0
-    print("fast-vs-oracle b=%d D=%d kernel=%d serial=%d: corr(u)=%.4f corr(v)=%.4f sign agreement=%.4f loss %.1f vs %.1f"
-          % (b, D, kernel, serial, cu, cv, agree, lg, lo))
+    print("fast-vs-oracle b=%d D=%d kernel=%d prefetch=%d: corr(u)=%.4f corr(v)=%.4f sign agreement=%.4f loss %.1f vs %.1f"
+          % (b, D, kernel, prefetch, cu, cv, agree, lg, lo))
     assert cu > 0.75 and cv > 0.90, (cu, cv)
     if b == 1:
         assert agree > 0.70, agree
@@ -275,16 +278,17 @@ def test_fast_counters_match_oracle(kernel, large):
 
 
 def test_fast_streaming_and_steps(large):
-    """Ring kernel driven step by step from host slices (the e2e path): every shard ends,
-    counters equal the resident run's."""
+    """Production kernel driven step by step from host slices (the e2e path, double-buffered: the next
+    step's slices are gathered and uploaded while the current one runs): every shard ends, counters equal the
+    resident run's — also when the step size changes between calls (prefetched slices no longer fit)."""
     c = w2b.Corpus(large, 5)
     tot = []
     for resident in (True, False):
         t = w2b.Trainer(c, size=128, window=5, negative=12, bitlevel=1, threads=12, iter=1, resident=resident)
         t.epoch_begin()
         words = pos = 0
-        for _ in range(10000):
-            st = t.train_step(5000)
+        for k in range(10000):
+            st = t.train_step(5000 if k % 7 else 1200)
             words += st["words"]; pos += st["positions"]
             if st["shards_done"] == 12:
                 break
@@ -293,10 +297,10 @@ def test_fast_streaming_and_steps(large):
     assert tot[0] == tot[1]
 
 
-@pytest.mark.parametrize("kernel,serial", [(1, 0), (0, 1), (0, 0)])
-@pytest.mark.parametrize("b,D", [(0, 64), (0, 200), (2, 64)])
-def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
-    """One shard, positions in order (register kernel; ring kernel with prefetch off): the
+@pytest.mark.parametrize("kernel,prefetch", [(1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("b,D", [(0, 64), (0, 200), (2, 64), (0, 800)])
+def test_fast_single_shard_tracks_oracle(kernel, prefetch, b, D, medium):
+    """One shard, positions in order (register kernel; production kernel in its default mode): the
     production arithmetic (FMA, shuffle-tree dot, atomic-add scatter) must stay close to the
     sequential oracle over a whole epoch.  Calibration: the reference's own
     -O3 vs strict-fp builds differ on this corpus by d0 = 8.7e-5 (D=64) / 3.5e-4 (D=200) at b=0
@@ -305,7 +309,7 @@ def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
     c = w2b.Corpus(medium, 5)
     o = po.Corpus(medium, 5)
     t = w2b.Trainer(c, size=D, window=5, negative=6, bitlevel=b, threads=1, iter=1, kernel=kernel,
-                    ring_serial=serial)
+                    prefetch=prefetch)
     m = po.OracleModel(o, D, 5, 6, b, shards=1, iters=1)
     lo = m.train_shard(0)
     lg, st = t.train_epoch()
@@ -314,7 +318,7 @@ def test_fast_single_shard_tracks_oracle(kernel, serial, b, D, medium):
     fu, fv = np.mean(np.abs(u - m.u) < 1e-3), np.mean(np.abs(v - m.v) < 1e-3)
     print("single-shard kernel=%d b=%d D=%d: max|du|=%.3g max|dv|=%.3g within1e-3: %.4f %.4f loss %.3f vs %.3f"
           % (kernel, b, D, du, dv, fu, fv, lg, lo))
-    ordered = kernel == 1 or serial  # prefetch on: context rows are read 1-2 updates stale
+    ordered = not prefetch  # prefetch on: context rows are read one update stale
     assert abs(lg - lo) <= (1e-3 if ordered else 5e-3) * abs(lo)
     if b == 0:
         lim = 5e-3 if ordered else 1e-1
@@ -361,7 +365,7 @@ def test_cli_end_to_end(tmp_path):
 def test_planted_topic_quality(tmp_path):
     """L3 statistical end-to-end: on a corpus with planted topics the trained
     1-bit vectors must recover the topics as well as the reference's own (kNN purity within 0.04,
-    final epoch loss within 1 %), for the production ring kernel with its prefetch on."""
+    final epoch loss within 1 %), for the production kernel in its default mode and with its prefetch on."""
     from tests.util import planted_topic_corpus, topic_purity
     topics = 25
     path = planted_topic_corpus(str(tmp_path / "topics.txt"), vocab=5000, topics=topics, sentences=60000, length=20)
@@ -381,7 +385,7 @@ def test_planted_topic_quality(tmp_path):
     m = po.OracleModel(o, D, W, neg, 1, shards=shards, iters=iters)
     losses = [m.train_epoch_threads() for _ in range(iters)]
     res["oracle"] = (losses[-1], topic_purity(words, m.export(), topics))
-    for name, kw in (("ring", dict(kernel=0)), ("ring_serial", dict(kernel=0, ring_serial=1)), ("register", dict(kernel=1))):
+    for name, kw in (("warp", dict(kernel=0)), ("warp_prefetch", dict(kernel=0, prefetch=1)), ("register", dict(kernel=1))):
         t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=1, threads=shards, iter=iters, **kw)
         losses = [t.train_epoch()[0] for _ in range(iters)]
         res[name] = (losses[-1], topic_purity(words, t.export(), topics))
@@ -389,16 +393,16 @@ def test_planted_topic_quality(tmp_path):
     print("planted-topic quality (final-epoch loss, kNN purity):", {k: (round(v[0], 1), round(v[1], 4)) for k, v in res.items()})
     base = res.get("reference", res["oracle"])
     assert base[1] > 0.5, "corpus too weak to measure anything"
-    for name in ("ring", "ring_serial", "register"):
+    for name in ("warp", "warp_prefetch", "register"):
         assert abs(res[name][1] - base[1]) <= 0.04, (name, res)   # reference vs oracle differ by 0.011 themselves
         assert abs(res[name][0] - base[0]) <= 0.01 * abs(base[0]), (name, res)
 
 
 @pytest.mark.parametrize("D,W,neg,b", [(4, 1, 0, 1), (8, 2, 1, 2), (100, 5, 5, 1), (256, 20, 40, 0), (1024, 3, 7, 1),
                                          (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (12, 5, 3, 4), (800, 10, 63, 1),
-                                         (100, 5, 63, 1)])
-def test_ring_kernel_odd_shapes(D, W, neg, b, medium):
-    """Production kernel on edge geometries (negative=0, window 1..30, D 4..1024, > 32 negatives):
+                                         (100, 5, 63, 1), (132, 64, 63, 1)])
+def test_production_kernel_odd_shapes(D, W, neg, b, medium):
+    """Production kernel on edge geometries (negative=0, window 1..64, D 4..1024, > 32 negatives):
     terminates, trains every position the oracle's trace holds, loss within 2 % of the oracle."""
     shards = 6
     c = w2b.Corpus(medium, 5)

@@ -248,7 +248,7 @@ def test_null_arguments_are_errors_not_crashes():
         assert getattr(lib, fn)(None) == EINVAL
     assert lib.w2b_export(None, None) == EINVAL
     assert lib.w2b_create(None, C.byref(C.c_void_p())) == EINVAL
-    assert lib.w2b_ring_plan_query(None, None) == EINVAL
+    assert lib.w2b_warp_plan_query(None, None) == EINVAL
     assert lib.w2b_corpus_shards(None, 2, None, None) == EINVAL
     assert lib.w2b_host_unigram_bounds(None, 5, None) == EINVAL
     assert lib.w2b_destroy(None) == 0  # like free(NULL)
@@ -354,22 +354,6 @@ def test_text_writer_parallel_and_cached_formatting(tmp_path, monkeypatch):
         assert lines[1 + a] == want, a
 
 
-def test_default_kernels_are_the_measured_binary():
-    """profiles/r01_sass_fingerprints_measured_build.json holds a fingerprint (instruction text, labels renumbered)
-    of every kernel of the build whose numbers are in profiles/ (commit 3b82bf5).  Variants were added to the
-    production kernel's template afterwards; the OPT = 0, LPR = 32, XW = 0 instantiations — what cfg.kernel = 0 runs —
-    must still be that machine code, instruction for instruction, until a new default has been measured."""
-    import shutil
-    import sys
-    if not shutil.which("cuobjdump"):
-        pytest.skip("CUDA toolkit not on PATH")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_fingerprint.py"), LIB, "--compare",
-                        os.path.join(ROOT, "profiles", "r01_sass_fingerprints_measured_build.json"), "--map",
-                        "ELi2EEEvNS_11TrainParamsEiii=ELi2ELi0ELi32ELi0EEEvNS_11TrainParamsEiii"],
-                       capture_output=True, text=True)
-    assert r.returncode == 0 and "72 kernels compared, 0 differ" in r.stdout, r.stdout[-2000:] + r.stderr[-500:]
-
-
 def _vector_file(path, words, D, seed=0):
     rng = np.random.default_rng(seed)
     with open(path, "wb") as f:
@@ -426,18 +410,17 @@ def test_corpus_above_the_reduce_vocab_threshold_is_refused(tmp_path, monkeypatc
 
 
 def test_default_geometry_is_the_measured_one():
-    """The numbers under profiles/ were measured with these launch geometries of the default kernel (cfg.kernel 0;
-    C2: grid 148 x 288 threads, 229.3 KB of dynamic shared memory — profiles/r01_ring_v5_ncu_full.md).  The SASS is
-    pinned by test_default_kernels_are_the_measured_binary; this pins the run-time arguments next to it, so a planner
-    change made for a variant cannot move the default silently."""
+    """The numbers under profiles/ (round 2) were measured with these launch geometries of the production kernel: one
+    32-thread CTA per shard, `warps_per_sm` of them resident per SM.  Pinned so that a planner change cannot move the
+    benchmarked configuration silently."""
     import word2bits_b200 as w2b
-    want = {  # (D, window, negative, bitlevel): (u_rows, v_rows, group, threads, smem_bytes)
-        (800, 10, 24, 1): (24, 34, 13, 288, 229256),   # BASELINE configs[1]
-        (400, 10, 12, 2): (24, 33, 13, 192, 114056),   # configs[2]
-        (400, 10, 24, 0): (24, 33, 13, 192, 114056),   # configs[3]
-        (200, 8, 24, 1): (20, 52, 13, 192, 74920),     # configs[0] shape
+    want = {  # (D, window, negative, bitlevel): (slots, queue_entries, warps_per_sm, smem_bytes)
+        (800, 10, 24, 1): (4, 128, 12, 17344),   # BASELINE configs[1]
+        (400, 10, 12, 2): (5, 128, 16, 12560),   # configs[2]
+        (400, 10, 24, 0): (5, 128, 16, 12560),   # configs[3]
+        (200, 8, 24, 1): (7, 128, 20, 10176),    # configs[0] shape
     }
     for (D, W, neg, b), geo in want.items():
-        p = w2b.ring_plan(size=D, window=W, negative=neg, bitlevel=b, vocab_size=400001)
-        assert p["ring"] == 1 and p["rows_in_flight"] == 2 and p["units_per_warp"] == 1
-        assert (p["u_rows"], p["v_rows"], p["group"], p["threads"], p["smem_bytes"]) == geo, (D, p)
+        p = w2b.warp_plan(size=D, window=W, negative=neg, bitlevel=b, vocab_size=400001)
+        assert p["warp"] == 1
+        assert (p["slots"], p["queue_entries"], p["warps_per_sm"], p["smem_bytes"]) == geo, (D, p)

@@ -75,12 +75,12 @@ def test_every_geometry_trains_what_the_oracle_trains(D, W, neg, b, S, tiny):
         trained = [t for t in tr if t[2] > 0]
         want["n_pos"].append(len(trained)); want["n_ctx"].append(sum(t[2] for t in trained))
         want["n_tgt"].append(sum(len(t[3]) for t in trained))
-    for slots, depth in ((0, 1), (3, 1), (0, 3), (5, 2)):  # planner's ring / the minimum; reduce depths 1..3
-        u, v, out = _run(c, table, D, W, neg, b, S, serial=0, async_mode=2, seed=11, slots=slots, depth=depth)
+    for slots in (0, 3):  # the planner's ring, and the minimum the protocol allows
+        u, v, out = _run(c, table, D, W, neg, b, S, serial=0, async_mode=2, seed=11, slots=slots)
         for k in want:
-            assert out[k].tolist() == want[k], (k, slots, depth)
+            assert out[k].tolist() == want[k], (k, slots)
         assert out["wca"] == m.word_count_actual
-        assert abs(out["loss"].sum() - lo) <= 0.06 * abs(lo), (slots, depth, out["loss"].sum(), lo)
+        assert abs(out["loss"].sum() - lo) <= 0.06 * abs(lo), (slots, out["loss"].sum(), lo)
 
 
 def test_sampler_trace_equals_oracle(tiny):

@@ -37,7 +37,8 @@ __device__ __forceinline__ void bulk_reduce_add(void *dst, unsigned src, unsigne
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
-// mode: 0 = load + reduce, 1 = load only, 2 = load + LDS/STS touch + reduce
+// mode: 0 = load + bulk reduce, 1 = load only, 2 = load + LDS/STS touch + bulk reduce,
+//       3 = load + LDS + red.global.add.v4.f32 from registers (the load/store unit carries the scatter-add)
 __global__ void __launch_bounds__(32) stream_kernel(float *tab, float *tab2, const int *ids, long long per_warp, int rowb, int K, int mode,
                                                     unsigned long long *sink) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -83,9 +84,17 @@ __global__ void __launch_bounds__(32) stream_kernel(float *tab, float *tab2, con
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (mode == 3) {
+      float *dst = ((id_j >> 30) ? tab2 : tab) + (long long)(id_j & 0x3fffffff) * D;
+      for (int c = lane * 16; c < rowb; c += 512) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(row + c) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c / 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      }
+    }
     __syncwarp();
     if (lane == 0) {
-      if (mode != 1) bulk_reduce_add(((id_j >> 30) ? tab2 : tab) + (long long)(id_j & 0x3fffffff) * D, row, rowb);
+      if (mode != 1 && mode != 3) bulk_reduce_add(((id_j >> 30) ? tab2 : tab) + (long long)(id_j & 0x3fffffff) * D, row, rowb);
       bulk_commit();
       asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       if (nj < per_warp) {
@@ -146,8 +155,7 @@ int main(int argc, char **argv) {
   CK(cudaEventCreate(&e1));
   printf("| D | ids | mode | warps/SM | ring K | rows in flight/SM | M rows/s | GB/s (2 x row bytes) |\n|---|---|---|---|---|---|---|---|\n");
   struct Cfg { int D, wps, K; };
-  std::vector<Cfg> cfgs = {{800, 8, 8}, {800, 12, 5}, {800, 12, 4}, {800, 12, 3}, {800, 16, 4}, {800, 16, 3}, {800, 20, 3},
-                           {400, 16, 8}, {400, 16, 4}, {400, 24, 5}, {200, 20, 12}, {200, 20, 6}, {200, 28, 8}, {100, 28, 8}};
+  std::vector<Cfg> cfgs = {{800, 12, 4}, {800, 16, 4}, {800, 20, 3}, {400, 16, 5}, {400, 24, 5}, {200, 20, 7}, {200, 28, 8}, {100, 28, 8}};
   for (const Cfg &c : cfgs) {
     const int rowb = c.D * 4;
     float *tab, *tab2;
@@ -163,7 +171,7 @@ int main(int argc, char **argv) {
     const int grid = sms * c.wps;
     long long per_warp = std::min<long long>(NIDS / grid, (long long)(12.0e9 / rowb / grid)) / 32 * 32;
     for (int ids = 0; ids < 3; ++ids)
-      for (int mode = 0; mode < 3; ++mode) {
+      for (int mode = 0; mode < 4; ++mode) {
         if (ids == 1 && mode == 2) continue;
         if (ids == 0 && mode != 0) continue;
         float best = 1e30f;
@@ -179,7 +187,7 @@ int main(int argc, char **argv) {
         }
         const double rows = (double)per_warp * grid;
         printf("| %d | %s | %s | %d | %d | %d | %.1f | %.0f |\n", c.D, ids == 2 ? "train-mix" : ids ? "uniform" : "zipf",
-               mode == 0 ? "load+reduce" : mode == 1 ? "load only" : "load+touch+reduce", c.wps, c.K, c.wps * (c.K - 2),
+               mode == 0 ? "load+reduce" : mode == 1 ? "load only" : mode == 2 ? "load+touch+reduce" : "load+red.v4", c.wps, c.K, c.wps * (c.K - 2),
                rows / best / 1e3, rows * rowb * (mode == 1 ? 1 : 2) / best / 1e6);
         fflush(stdout);
       }

@@ -10,7 +10,7 @@ neg = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 b = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 kernel = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 words = int(sys.argv[5]) if len(sys.argv) > 5 else 1500
-V, N = 400000, 8_000_000
+V, N = 400000, 24_000_000
 ids, cn = synth(V, N)
 t = w2b.Trainer(None, vocab_size=V + 1, size=D, window=10, negative=neg, bitlevel=b, iter=1, kernel=kernel)
 S = t.threads

@@ -28,12 +28,12 @@ def main():
     threads_list = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [0]
     plain = int(sys.argv[8]) if len(sys.argv) > 8 else 0
     kernel = int(sys.argv[9]) if len(sys.argv) > 9 else 0
-    ring_rows = int(sys.argv[10]) if len(sys.argv) > 10 else 0
+    slots = int(sys.argv[10]) if len(sys.argv) > 10 else 0
     ids, cn = synth(V, N)
     for group in groups:
       for threads in threads_list:
         t = w2b.Trainer(None, vocab_size=V + 1, size=D, window=10, negative=neg, bitlevel=b, iter=1,
-                        threads=threads or None, group=group, plain_store=plain, kernel=kernel, ring_rows=ring_rows)
+                        threads=threads or None, group=group, plain_store=plain, kernel=kernel, slots=slots)
         S = t.threads
         t.set_vocab_counts(cn, int(N))
         start = (np.arange(S, dtype=np.int64) * (N // S))
@@ -47,7 +47,7 @@ def main():
         wall = time.time() - t0
         gb = rows * D * 4 * 2 / 1e9
         print("kernel=%d rows=%d V=%d D=%d neg=%d b=%d group=%d plain=%d shards=%d: %.2f M words/s, %.2f M pos/s (kernel), alg %.0f GB/s, wall %.2fs kernel %.1f ms loss/pos ~ alpha=%.4f" % (
-            kernel, ring_rows, V, D, neg, b, group, plain, S, tot_w / ms / 1e3, tot_p / ms / 1e3, gb / (ms / 1e3), wall, ms, st["alpha"]), flush=True)
+            kernel, slots, V, D, neg, b, group, plain, S, tot_w / ms / 1e3, tot_p / ms / 1e3, gb / (ms / 1e3), wall, ms, st["alpha"]), flush=True)
         t.close()
 
 

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import MODE_FAST, MODE_STRICT, TABLE_SIZE, W2BError, check, lib, ptr
 
 __all__ = ["Corpus", "Trainer", "W2BError", "MODE_FAST", "MODE_STRICT", "device_count", "read_packed", "nccl_unique_id",
-           "compute_accuracy", "host_unigram_bounds", "host_exptable", "host_keep_thresholds", "host_lcg_tables", "ring_plan", "warp_plan"]
+           "compute_accuracy", "host_unigram_bounds", "host_exptable", "host_keep_thresholds", "host_lcg_tables", "warp_plan"]
 
 
 def device_count():
@@ -52,22 +52,11 @@ def host_lcg_tables():
     return ja, jc, pa, pc
 
 
-def ring_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, mode=MODE_FAST, group=0, kernel=0,
-              ring_rows=0):
-    """Geometry of the production (TMA ring) kernel for a configuration (pure host arithmetic)."""
+def warp_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, mode=MODE_FAST, kernel=0, slots=0):
+    """Geometry of the production (warp-per-shard) kernel for a configuration (pure host arithmetic)."""
     cfg = _lib.Config(vocab_size=vocab_size, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
                       alpha=0.05, sample=1e-3, reg=reg, iter=1, num_shards=1, shard_begin=0, shard_end=0, device=0,
-                      mode=mode, group=group, plain_store=0, kernel=kernel, ring_rows=ring_rows, ring_serial=0)
-    out = _lib.RingPlan()
-    check(lib.w2b_ring_plan_query(C.byref(cfg), C.byref(out)))
-    return out.as_dict()
-
-
-def warp_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, mode=MODE_FAST, kernel=6, ring_rows=0):
-    """Geometry of the warp-per-shard kernel for a configuration (pure host arithmetic)."""
-    cfg = _lib.Config(vocab_size=vocab_size, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
-                      alpha=0.05, sample=1e-3, reg=reg, iter=1, num_shards=1, shard_begin=0, shard_end=0, device=0,
-                      mode=mode, group=0, plain_store=0, kernel=kernel, ring_rows=ring_rows, ring_serial=0)
+                      mode=mode, group=0, plain_store=0, kernel=kernel, slots=slots, prefetch=0)
     out = _lib.WarpPlan()
     check(lib.w2b_warp_plan_query(C.byref(cfg), C.byref(out)))
     return out.as_dict()
@@ -134,12 +123,12 @@ class Trainer:
 
     def __init__(self, corpus=None, *, size=100, window=5, negative=5, bitlevel=1, alpha=0.05, sample=1e-3,
                  reg=0.0, iter=5, threads=None, device=0, mode=MODE_FAST, shard_range=None, group=0,
-                 plain_store=0, resident=True, vocab_size=None, init=True, kernel=0, ring_rows=0, ring_serial=0):
+                 plain_store=0, resident=True, vocab_size=None, init=True, kernel=0, slots=0, prefetch=0):
         V = corpus.vocab_size if corpus is not None else vocab_size
         cfg = _lib.Config(vocab_size=V, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
                           alpha=alpha, sample=sample, reg=reg, iter=iter, num_shards=threads or 1,
                           shard_begin=0, shard_end=0, device=device, mode=mode, group=group,
-                          plain_store=plain_store, kernel=kernel, ring_rows=ring_rows, ring_serial=ring_serial)
+                          plain_store=plain_store, kernel=kernel, slots=slots, prefetch=prefetch)
         if threads is None:
             n = C.c_int(0)
             check(lib.w2b_suggest_shards(C.byref(cfg), C.byref(n)))

@@ -27,7 +27,7 @@ class Config(C.Structure):
                 ("iter", C.c_int64),
                 ("num_shards", C.c_int32), ("shard_begin", C.c_int32), ("shard_end", C.c_int32),
                 ("device", C.c_int32), ("mode", C.c_int32), ("group", C.c_int32), ("plain_store", C.c_int32),
-                ("kernel", C.c_int32), ("ring_rows", C.c_int32), ("ring_serial", C.c_int32)]
+                ("kernel", C.c_int32), ("slots", C.c_int32), ("prefetch", C.c_int32)]
 
 
 class StepStats(C.Structure):
@@ -44,15 +44,6 @@ class Accuracy(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("questions_total", "questions_seen", "correct", "semantic_correct",
                                          "semantic_seen", "syntactic_correct", "syntactic_seen", "vocab", "size")] + \
                [("gpu_ms", C.c_float)]
-
-
-class RingPlan(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("ring", "group", "consumer_warps", "rows_in_flight", "u_rows", "v_rows",
-                                         "threads", "desc_depth", "max_groups", "units_per_warp", "reserved")] + \
-               [("smem_bytes", C.c_int64)]
-
-    def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class WarpPlan(C.Structure):
@@ -77,7 +68,7 @@ EXPORTS = [
     "w2b_upload_raw", "w2b_download_table", "w2b_download_exptable", "w2b_export", "w2b_quantize",
     "w2b_device_ptrs", "w2b_nccl_unique_id", "w2b_nccl_init", "w2b_sync", "w2b_scale_tables",
     "w2b_write_packed", "w2b_read_packed_header", "w2b_read_packed", "w2b_checkpoint_save", "w2b_checkpoint_load", "w2b_compute_accuracy",
-    "w2b_host_unigram_bounds", "w2b_host_exptable", "w2b_host_keep_thresholds", "w2b_host_lcg_tables", "w2b_ring_plan_query", "w2b_warp_plan_query", "w2b_host_ring_index", "w2b_host_gather_slices",
+    "w2b_host_unigram_bounds", "w2b_host_exptable", "w2b_host_keep_thresholds", "w2b_host_lcg_tables", "w2b_warp_plan_query", "w2b_host_gather_slices",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -114,9 +105,7 @@ lib.w2b_host_unigram_bounds.argtypes = [_vp, _i64, _vp]
 lib.w2b_host_exptable.argtypes = [_vp]
 lib.w2b_host_keep_thresholds.argtypes = [_vp, _i64, _i64, _f, _vp]
 lib.w2b_host_lcg_tables.argtypes = [_vp, _vp, _vp, _vp]
-lib.w2b_ring_plan_query.argtypes = [_P(Config), _P(RingPlan)]
 lib.w2b_warp_plan_query.argtypes = [_P(Config), _P(WarpPlan)]
-lib.w2b_host_ring_index.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]
 lib.w2b_host_gather_slices.argtypes = [_vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]
 lib.w2b_device_count.argtypes = [_P(C.c_int)]
 lib.w2b_suggest_shards.argtypes = [_P(Config), _P(C.c_int)]

@@ -16,7 +16,6 @@
 #include "w2b.h"
 #include "w2b_internal.h"
 #include "w2b_kernels.cuh"
-#include "w2b_ring.cuh"
 #include "w2b_warp.cuh"
 
 using namespace w2b;
@@ -104,14 +103,8 @@ struct w2b_ctx {
   w2b_config cfg;
   int nlocal = 0;  // shards owned by this context
   int vec = 4, ncol = 0, threads = 0, group = 9;
-  bool ring = false;       // production TMA-ring kernel usable for this configuration
-  int ring_nu = 0, ring_nv = 0, ring_g = 13, ring_threads = 0;
-  int ring_lpr = 32;       // lanes per target row (32 = a warp per row; 16 / 8: cfg.kernel 3 / 4)
-  int ring_xw = 0;         // consumer warps beyond one per 128 columns (cfg.kernel 5: 2)
-  size_t ring_smem = 0;
-  bool warp = false;       // warp-per-shard kernel (csrc/w2b_warp.cuh) usable for this configuration
+  bool warp = false;       // production warp-per-shard kernel (csrc/w2b_warp.cuh) usable for this configuration
   int warp_k = 0, warp_qcap = 0, warp_minb = 0;  // ring slots per warp, job queue entries, warps per SM
-  int warp_rd = 1;         // bulk-reduce groups left pending behind the arithmetic (1..3)
   size_t warp_smem = 0;
   int sm_count = 0;
   long long train_words = 0;
@@ -204,179 +197,55 @@ static apply_fn pick_apply(const w2b_ctx *c) {
   return nullptr;
 }
 
-typedef void (*ring_fn)(TrainParams, int, int, int);
-// Target rows in flight per consumer warp.  Measured on B200 (tools/quick_perf.py): R=2 wins
-// everywhere — R=3 at D=800 spills (a CTA with 9+ warps gets at most 168 registers per thread:
-// three warps share one SM sub-partition's 16K registers) and drops 5782 -> 4440 GB/s; R=4 at
-// D=400 costs the second CTA per SM (204 registers) and halves throughput.
-template <int BM, int OPT, int LPR>
-static ring_fn ring_by_nj(int nj) {
-  switch (nj) {
-    case 1: return train_ring_kernel<BM, 1, 2, OPT, LPR>;
-    case 2: return train_ring_kernel<BM, 2, 2, OPT, LPR>;
-    case 3: return train_ring_kernel<BM, 3, 2, OPT, LPR>;
-    case 4: return train_ring_kernel<BM, 4, 2, OPT, LPR>;
-    case 5: return train_ring_kernel<BM, 5, 2, OPT, LPR>;
-    case 6: return train_ring_kernel<BM, 6, 2, OPT, LPR>;
-    case 7: return train_ring_kernel<BM, 7, 2, OPT, LPR>;
-    case 8: return train_ring_kernel<BM, 8, 2, OPT, LPR>;
-  }
-  return nullptr;
-}
-static int ring_rows_in_flight(int) { return 2; }
-// cfg.kernel: 0 = the ring kernel measured in round 1; 1 = register kernel; experimental variants of the
-// ring kernel (same protocol and arithmetic; bitlevel 0/1/2 only — other bit levels stay on kernel 0):
-// 2 = division-free index arithmetic (OPT), 3 / 4 = OPT + 16 / 8 lanes per target row for narrow rows,
-// 5 = OPT + two more consumer warps for wide rows (D > 512).
-static int ring_lpr_of(const w2b_config &cfg, int ncol) {
-  const int bm = bm_of(cfg.bitlevel);
-  if (bm == 9) return 32;
-  if (cfg.kernel == 3 && (ncol + 15) / 16 <= 8) return 16;
-  if (cfg.kernel == 4 && (ncol + 7) / 8 <= 8) return 8;
-  return 32;
-}
-template <int BM>
-static ring_fn ring_xw2(int nj) {  // wide rows only (narrow rows have the lanes-per-row variants)
-  switch (nj) {
-    case 5: return train_ring_kernel<BM, 5, 2, 1, 32, 2>;
-    case 6: return train_ring_kernel<BM, 6, 2, 1, 32, 2>;
-    case 7: return train_ring_kernel<BM, 7, 2, 1, 32, 2>;
-    case 8: return train_ring_kernel<BM, 8, 2, 1, 32, 2>;
-  }
-  return nullptr;
-}
-static int ring_xw_of(const w2b_config &cfg, int ncol) {
-  return (cfg.kernel == 5 && bm_of(cfg.bitlevel) != 9 && (ncol + 31) / 32 >= 5) ? 2 : 0;
-}
-template <int BM>
-static ring_fn pick_ring_bm(int kernel, int lpr, int ncol) {
-  if (kernel == 5 && (ncol + 31) / 32 >= 5) return ring_xw2<BM>((ncol + 31) / 32);
-  if (lpr == 16) return ring_by_nj<BM, 1, 16>((ncol + 15) / 16);
-  if (lpr == 8) return ring_by_nj<BM, 1, 8>((ncol + 7) / 8);
-  if (kernel >= 2) return ring_by_nj<BM, 1, 32>((ncol + 31) / 32);
-  return ring_by_nj<BM, 0, 32>((ncol + 31) / 32);
-}
-static ring_fn pick_ring(const w2b_ctx *c) {
-  switch (bm_of(c->cfg.bitlevel)) {
-    case 0: return pick_ring_bm<0>(c->cfg.kernel, c->ring_lpr, c->ncol);
-    case 1: return pick_ring_bm<1>(c->cfg.kernel, c->ring_lpr, c->ncol);
-    case 2: return pick_ring_bm<2>(c->cfg.kernel, c->ring_lpr, c->ncol);
-    default: return ring_by_nj<9, 0, 32>((c->ncol + 31) / 32);
-  }
-}
-
-// Ring kernel geometry: the u-ring holds one full window plus slack, the v-ring as many
-// rows as 227 KB of shared memory allow (up to 4 groups).  Lower bounds: 2 groups, and
-// ncw + G + 1 rows so that a slot awaiting its read confirmation can never be needed by
-// the group that contains the confirming warp's next row.
-static void plan_ring(w2b_ctx *c) {
-  c->ring = false;
-  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
-  const int nt = c->cfg.negative + 1;
-  int G = (c->cfg.group > 0 && c->cfg.group <= 16) ? c->cfg.group : 13;
-  if ((nt + G - 1) / G > kMaxGrp) G = (nt + kMaxGrp - 1) / kMaxGrp;
-  const int nj = (c->ncol + 31) / 32;
-  if (nj > 8) return;  // kernels are instantiated for D <= 1024
-  // consumer warps: one per 128 columns, but at least 4 — the target phase deals whole rows to
-  // warps, so narrow rows (D < 512) still get enough warps to walk 1+negative rows quickly
-  c->ring_xw = ring_xw_of(c->cfg, c->ncol);
-  const int ncw = std::max(nj, 4) + c->ring_xw;
-  // row units: a warp per target row, or (experimental narrow-row variants) 2 / 4 units per warp
-  c->ring_lpr = ring_lpr_of(c->cfg, c->ncol);
-  const int upw = 32 / c->ring_lpr, nunits = ncw * upw;
-  const long long D = c->cfg.layer1_size;
-  // Small rows: aim for several CTAs per SM (more warps hide the per-row dependency chains);
-  // k CTAs share the 227 KB (minus 1 KB reserved per CTA).  Take the largest k <= 4 whose
-  // share still holds >= 2.5 groups of v rows; big rows (D=800) end up with k = 1.
-  // a warp confirms a batch of R slots when it commits its next batch, whose rows lie up to
-  // (2*R-1)*ncw rows further on: the group holding them must never need an unconfirmed slot
-  const int R = ring_rows_in_flight(ncw);
-  // ... unless the ring holds a whole position (nv >= 1+negative): then no row of a position can
-  // wait for a slot of the same position, and everything older was confirmed at its position's end
-  // (with several units per warp the batch a unit waits for also holds its warp-mates' rows: + upw - 1)
-  const int nv_min = std::max(2 * G, std::min((2 * R - 1) * nunits + G + upw, nt));
-  const int nv_good = std::max(nv_min, (5 * G + 1) / 2);
-  // u-ring: one full window plus slack in the measured kernel.  The variants keep exactly one window (the
-  // largest cw): the rows of position p+1 that do not fit are requested at p's barrier A, a whole target phase
-  // before they are needed, and the four rows go to the v-ring, whose depth is what hides latency
-  int nu = c->cfg.kernel >= 2 ? 2 * c->cfg.window : 2 * c->cfg.window + 4;
-  int nv = 0;
-  for (int k = 4; k >= 1 && !nv; --k) {
-    const size_t cap = (size_t)(227 * 1024) / k - 1024;
-    int cand = c->cfg.ring_rows > 0 ? std::max(c->cfg.ring_rows, nv_min) : 4 * G;
-    if (upw > 1) cand = std::max(cand, nv_min);  // many row units: the bound can exceed four groups
-    // variants: the ring depth is what hides the latency of the next position's rows (profiles/
-    // r01_static_sass_variants.md); do not tie it to the group size — take what the share of shared memory holds
-    if (c->cfg.kernel >= 2 && c->cfg.ring_rows <= 0) cand = std::max(cand, std::min(96, 2 * nt + G));
-    while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
-    if (cand >= (k > 1 ? nv_good : nv_min)) nv = cand;
-  }
-  if (!nv) {
-    nu = 2 * c->cfg.window;
-    const size_t cap = (size_t)(227 * 1024) - 1024;
-    int cand = 4 * G;
-    if (upw > 1) cand = std::max(cand, nv_min);
-    if (c->cfg.kernel >= 2) cand = std::max(cand, std::min(96, 2 * nt + G));
-    while (cand >= nv_min && ring_layout(D, nu, cand, ncw).total > cap) --cand;
-    if (cand < nv_min) return;
-    nv = cand;
-  }
-  c->ring = true;
-  c->ring_g = G;
-  c->ring_nu = nu;
-  c->ring_nv = nv;
-  c->ring_threads = (ncw + 2) * 32;  // consumers + loader warp + sampler warp
-  c->ring_smem = ring_layout(D, nu, nv, ncw).total;
-}
-
 // ---- warp-per-shard kernel (csrc/w2b_warp.cuh)
-typedef void (*warp_fn)(TrainParams, int, int, int, ApplyArgs);
+typedef void (*warp_fn)(TrainParams, int, int, ApplyArgs);
 // warps (= 1-warp CTAs) per SM the register allocation is sized for; multiples of 4 because the register file is
 // split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96
 static int warp_minb_of(int nj) { return nj >= 5 ? 12 : (nj >= 3 ? 16 : 20); }
-template <int BM>
+template <int BM, int RG>
 static warp_fn warp_by_nj(int nj) {
   switch (nj) {
-    case 1: return train_warp_kernel<BM, 1, 20>;
-    case 2: return train_warp_kernel<BM, 2, 20>;
-    case 3: return train_warp_kernel<BM, 3, 16>;
-    case 4: return train_warp_kernel<BM, 4, 16>;
-    case 5: return train_warp_kernel<BM, 5, 12>;
-    case 6: return train_warp_kernel<BM, 6, 12>;
-    case 7: return train_warp_kernel<BM, 7, 12>;
-    case 8: return train_warp_kernel<BM, 8, 12>;
+    case 1: return train_warp_kernel<BM, 1, 20, RG>;
+    case 2: return train_warp_kernel<BM, 2, 20, RG>;
+    case 3: return train_warp_kernel<BM, 3, 16, RG>;
+    case 4: return train_warp_kernel<BM, 4, 16, RG>;
+    case 5: return train_warp_kernel<BM, 5, 12, RG>;
+    case 6: return train_warp_kernel<BM, 6, 12, RG>;
+    case 7: return train_warp_kernel<BM, 7, 12, RG>;
+    case 8: return train_warp_kernel<BM, 8, 12, RG>;
   }
   return nullptr;
 }
 static warp_fn pick_warp(const w2b_ctx *c) {
   const int nj = (c->ncol + 31) / 32;
+  static const bool rg = getenv("W2B_WARP_RED") && atoi(getenv("W2B_WARP_RED")) != 0;  // A/B hook (scatter path)
+  if (rg)
+    switch (bm_of(c->cfg.bitlevel)) {
+      case 0: return warp_by_nj<0, 1>(nj);
+      case 1: return warp_by_nj<1, 1>(nj);
+      case 2: return warp_by_nj<2, 1>(nj);
+      default: return warp_by_nj<9, 1>(nj);
+    }
   switch (bm_of(c->cfg.bitlevel)) {
-    case 0: return warp_by_nj<0>(nj);
-    case 1: return warp_by_nj<1>(nj);
-    case 2: return warp_by_nj<2>(nj);
-    default: return warp_by_nj<9>(nj);
+    case 0: return warp_by_nj<0, 0>(nj);
+    case 1: return warp_by_nj<1, 0>(nj);
+    case 2: return warp_by_nj<2, 0>(nj);
+    default: return warp_by_nj<9, 0>(nj);
   }
 }
 // Geometry: as many ring slots as the warp's share of the SM's 228 KB holds (each resident CTA also costs 1 KB of
 // reserved shared memory); at least 3 (one row being worked on, one draining, one in flight).
 static void plan_warp(w2b_ctx *c) {
   c->warp = false;
-  int kernel = c->cfg.kernel;
-  if (kernel == 0) {  // A/B hook while both production kernels exist
-    const char *e = getenv("W2B_DEFAULT_KERNEL");
-    if (e) kernel = atoi(e);
-  }
-  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || kernel != 6) return;
+  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
   const int nj = (c->ncol + 31) / 32;
   if (nj > 8) return;  // kernels are instantiated for D <= 1024
   const int minb = warp_minb_of(nj);
   const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
   const size_t budget = (size_t)(228 * 1024) / minb - 1024;
-  int K = c->cfg.ring_rows > 0 ? std::min(c->cfg.ring_rows, 32) : 16;
+  int K = c->cfg.slots > 0 ? std::min(c->cfg.slots, 32) : 16;
   while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap).total > budget) --K;
   if (K < 3) return;
-  // cfg.group doubles as the reduce depth for this kernel (tuning knob; 0 = default)
-  c->warp_rd = std::max(1, std::min(3, std::min(c->cfg.group > 0 ? c->cfg.group : 1, K - 2)));
   c->warp = true;
   c->warp_k = K;
   c->warp_qcap = qcap;
@@ -416,12 +285,7 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.shard_base = 0;
   p.train = 1;
   p.plain_store = c->cfg.plain_store;
-  // ring_serial 2 ("early release", experimental) exists in the variant kernels only
-  p.serial = (c->cfg.ring_serial == 2 && c->cfg.kernel < 2) ? 0 : c->cfg.ring_serial;
-  {
-    const char *e = getenv("W2B_SLEEP_NS");  // tuning hook
-    p.sleep_ns = e ? (unsigned)atoi(e) : 128u;  // flat between 32 and 512 ns on B200 (measured)
-  }
+  p.serial = c->cfg.prefetch ? 0 : 1;  // default: the positions of a shard strictly one after another
   p.wca_scale = c->nranks;
   return p;
 }
@@ -471,16 +335,11 @@ extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   int per_sm = 0;
-  plan_ring(&tmp);
   plan_warp(&tmp);
   if (tmp.warp) {
     warp_fn wf = pick_warp(&tmp);
     CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp.warp_smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf, 32, tmp.warp_smem));
-  } else if (tmp.ring) {
-    ring_fn rf = pick_ring(&tmp);
-    CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp.ring_smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rf, tmp.ring_threads, tmp.ring_smem));
   } else {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_train(&tmp), tmp.threads, dyn_smem(&tmp)));
   }
@@ -489,31 +348,6 @@ extern "C" int w2b_suggest_shards(const w2b_config *cfg, int *out) {
 }
 
 // ---- host-only views of the path's host logic (no CUDA call: usable, and tested, without a GPU)
-extern "C" int w2b_ring_plan_query(const w2b_config *cfg, w2b_ring_plan *out) {
-  if (!cfg || !out) { w2b_set_error("null argument"); return W2B_EINVAL; }
-  int rc = validate(cfg);
-  if (rc) return rc;
-  w2b_ctx tmp;
-  tmp.cfg = *cfg;
-  tmp.vec = (cfg->layer1_size % 4 == 0) ? 4 : 1;
-  tmp.ncol = (int)((cfg->layer1_size + tmp.vec - 1) / tmp.vec);
-  plan_ring(&tmp);
-  memset(out, 0, sizeof *out);
-  out->ring = tmp.ring ? 1 : 0;
-  if (!tmp.ring) return W2B_OK;
-  out->group = tmp.ring_g;
-  out->u_rows = tmp.ring_nu;
-  out->v_rows = tmp.ring_nv;
-  out->threads = tmp.ring_threads;
-  out->consumer_warps = tmp.ring_threads / 32 - 2;
-  out->rows_in_flight = ring_rows_in_flight(out->consumer_warps);
-  out->units_per_warp = 32 / tmp.ring_lpr;
-  out->desc_depth = kND;
-  out->max_groups = kMaxGrp;
-  out->smem_bytes = (int64_t)tmp.ring_smem;
-  return W2B_OK;
-}
-
 extern "C" int w2b_warp_plan_query(const w2b_config *cfg, w2b_warp_plan *out) {
   if (!cfg || !out) { w2b_set_error("null argument"); return W2B_EINVAL; }
   int rc = validate(cfg);
@@ -539,19 +373,6 @@ extern "C" int w2b_host_lcg_tables(uint64_t *ja, uint64_t *jc, uint64_t *pa, uin
   lcg_tables(JA, JC, PA, PC);
   for (int i = 0; i < 65; ++i) { ja[i] = JA[i]; jc[i] = JC[i]; }
   for (int i = 0; i < 64; ++i) { pa[i] = PA[i]; pc[i] = PC[i]; }
-  return W2B_OK;
-}
-
-// The division-free row index of the kernel = 2 variant, evaluated by the very same inline helpers on the
-// host (tests compare it with % and / over the kernel's whole operand range).
-extern "C" int w2b_host_ring_index(int vs0, int i, int nv, int G, int *slot, int *group) {
-  NEED(slot);
-  NEED(group);
-  if (nv < 1 || G < 1 || vs0 < 0 || vs0 >= nv || i < 0) { w2b_set_error("w2b_host_ring_index: bad argument"); return W2B_EINVAL; }
-  unsigned us = 0, ug = 0;
-  ring_row_index((unsigned)vs0, (unsigned)i, (unsigned)nv, ring_magic((unsigned)nv), ring_magic((unsigned)G), &us, &ug);
-  *slot = (int)us;
-  *group = (int)ug;
   return W2B_OK;
 }
 
@@ -600,7 +421,6 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   c->threads = std::max(32, (c->ncol + 31) / 32 * 32);
   c->group = cfg->group ? cfg->group : (cfg->negative + 1 > 9 ? 13 : (cfg->negative + 1 > 5 ? 9 : 5));
   if (c->group != 5 && c->group != 9 && c->group != 13) c->group = 9;  // register kernel instantiations
-  plan_ring(c);
   plan_warp(c);
   CK(cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
@@ -889,12 +709,7 @@ static int launch_enqueue(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
     p.shard_base = 0;
     ApplyArgs none;
     memset(&none, 0, sizeof none);
-    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, none);
-  } else if (c->ring) {  // round-1 production path: TMA ring kernel, one CTA per shard
-    ring_fn rf = pick_ring(c);
-    CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
-    p.shard_base = 0;
-    rf<<<c->nlocal, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv, c->ring_g);
+    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
   } else {
     train_fn fn = pick_train(c);
     if (!fn) { w2b_set_error("no kernel for this configuration"); return W2B_EINVAL; }
@@ -951,8 +766,8 @@ static int w2b_train_step_impl(w2b_ctx *c, int64_t words_per_shard, w2b_step_sta
   memset(&acc, 0, sizeof acc);
   sum_shards(c->h_shards, &before);
   TrainParams p = base_params(c);
-  // The ring kernel keeps 32-bit row counters per launch and the streaming path stages one slice per
-  // shard in pinned memory, so a step is cut into bounded launches: 4 M words per shard per launch
+  // The production kernel keeps 32-bit job and row counters per launch and the streaming path stages one slice
+  // per shard in pinned memory, so a step is cut into bounded launches: 4 M words per shard per launch
   // (resident) / 1 M words per slice (streaming).  Steps up to those sizes are exactly one launch.
   const long long kLaunchWords = 4 << 20, kSliceWords = 1 << 20;
   if (c->resident) {
@@ -1089,11 +904,7 @@ static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_tra
     CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
     ApplyArgs none;
     memset(&none, 0, sizeof none);
-    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, none);
-  } else if (c->ring) {  // the production kernel's own sampler warp (prefetching draw path)
-    ring_fn rf = pick_ring(c);
-    CK(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ring_smem));
-    rf<<<1, c->ring_threads, c->ring_smem, c->stream>>>(p, c->ring_nu, c->ring_nv, c->ring_g);
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
   } else {
     train_fn fn = pick_train(c);
     const size_t smem = dyn_smem(c);
@@ -1170,7 +981,7 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
     p.serial = 1;
     ApplyArgs ap;
     ap.ctx = d_ids; ap.tg = d_ids + cw; ap.cw = cw; ap.nt = nt; ap.f_out = d_f;
-    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, c->warp_rd, ap);
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, ap);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     if (f_out && nt) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));

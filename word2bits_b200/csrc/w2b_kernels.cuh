@@ -74,8 +74,7 @@ struct TrainParams {
   int shard_base;               // first local shard handled by blockIdx 0
   int train;                    // 0: draws only (trace)
   int plain_store;
-  int serial;                   // ring kernel debug: no prefetch across positions
-  unsigned sleep_ns;            // ring kernel: back-off of the sampler/loader polling loops
+  int serial;                   // warp kernel: 1 = position p+1 is fetched after every update of p completed
   int wca_scale;                // multi-GPU: local words stand for wca_scale x as many globally
   w2b_trace_rec *trace;
   long long trace_cap;

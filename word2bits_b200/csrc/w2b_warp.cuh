@@ -291,10 +291,24 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
 
 // BM: compile-time bitlevel 0/1/2, 9 = run time.  NJ = float4 columns per lane = ceil(D / 128).  MINB = CTAs (warps)
 // per SM the register allocation is sized for.
-// RD = bulk-reduce groups a warp leaves pending behind the job it just finished (1..3): after job c, jobs <= c - RD
-// have been read out of their slots, so loads run K - 1 - RD jobs ahead of the arithmetic.
-template <int BM, int NJ, int MINB>
-__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap, int RD, ApplyArgs ap) {
+#ifdef W2B_EMULATE
+__device__ __forceinline__ void red_add_v4(float *dst, float4 v) { dst[0] += v.x; dst[1] += v.y; dst[2] += v.z; dst[3] += v.w; }
+__device__ __forceinline__ void fence_generic_to_async_global() {}
+#else
+__device__ __forceinline__ void red_add_v4(float *dst, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// every earlier red of this thread is performed, and ordered before later bulk copies (async proxy) from global
+__device__ __forceinline__ void fence_generic_to_async_global() {
+  __threadfence();
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+#endif
+
+// RG = 1: the scatter-adds leave through the load/store unit (red.global.add.v4.f32 from registers) instead of the
+// bulk-copy engine (row written back to its slot, one cp.reduce.async.bulk): the engine then only carries the loads.
+template <int BM, int NJ, int MINB, int RG = 0>
+__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap, ApplyArgs ap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
   const WarpLayout L = warp_layout(p.D, K, qcap);
@@ -346,9 +360,10 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   unsigned phase = 0;    // per-slot mbarrier parity
   double loss = 0.0;     // per lane: reported loss of the targets this lane looked after
 
-  // Issue loads while job j <= q_cons + K - 1 - RD (slot of job j - K confirmed free by the last wait_group.read RD).
+  // Issue loads while job j <= q_cons + K - 2 (slot of job j - K confirmed free by the last wait_group.read 1;
+  // leaving 2 or 3 groups pending instead made no difference on B200: profiles/r02_warp_kernel_sweeps.md).
   auto pump = [&]() {
-    while (q_issue < q_limit && q_issue + 1 + (unsigned)RD <= q_cons + (unsigned)K) {
+    while (q_issue < q_limit && q_issue + (RG ? 1u : 2u) <= q_cons + (unsigned)K) {
       const int e = jobq[q_issue & qmask];
       if (e >= 0 && lane == 0) {
         const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
@@ -361,13 +376,11 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     }
   };
   auto job_done = [&]() {  // the job's group is committed by lane 0; free the slot before it and refill
-    if (lane == 0) {
+    if (!RG && lane == 0) {
       bulk_commit();
-      if (RD == 1) bulk_wait_read<1>();
-      else if (RD == 2) bulk_wait_read<2>();
-      else bulk_wait_read<3>();
+      bulk_wait_read<1>();
     }
-    __syncwarp();
+    __syncwarp();  // (RG: every lane has read the row out of its slot)
     ++q_cons;
     if (++cslot == K) cslot = 0;
     pump();
@@ -463,24 +476,39 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
         e[j][0] = fma2(g2, F2{x[j].x, x[j].y}, e[j][0]);  // :487, quantized OLD v
         e[j][1] = fma2(g2, F2{x[j].z, x[j].w}, e[j][1]);
         const F2 u0 = mul2(g2, a[j][0]), u1 = mul2(g2, a[j][1]);  // :490: g*context_avg replaces the row in its slot
-        if ((j < NJ - 1) || on_last) sts128(row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
+        if ((j < NJ - 1) || on_last) {
+          if (RG) red_add_v4(p.v + (long long)tid_row * p.D + (W2B_COFF(j) >> 2), make_float4(u0.x, u0.y, u1.x, u1.y));
+          else sts128(row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
+        }
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) bulk_reduce_add(p.v + (long long)tid_row * p.D, row, rowb);
+      if (!RG) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_reduce_add(p.v + (long long)tid_row * p.D, row, rowb);
+      }
       job_done();
     }
 
     // ---- staging job: the error goes to every context row of u (:494-503)
     {
       const unsigned row = ring + (unsigned)cslot * rowb;
+      if (RG) {
+        for (int k = 0; k < cw; ++k) {
+          float *dst = p.u + (long long)jobq[(q0 + k) & qmask] * p.D;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if ((j < NJ - 1) || on_last) sts128(row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0)
-        for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, row, rowb);
+          for (int j = 0; j < NJ; ++j)
+            if ((j < NJ - 1) || on_last)
+              red_add_v4(dst + (W2B_COFF(j) >> 2), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if ((j < NJ - 1) || on_last) sts128(row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0)
+          for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, row, rowb);
+      }
       if (lane < nt) loss += (double)logf(sigmoid_report(myf0));
       if (lane + 32 < nt) loss += (double)logf(sigmoid_report(myf1));
       if (ap.f_out) {
@@ -488,7 +516,9 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
         if (lane + 32 < nt) ap.f_out[lane + 32] = -myf1;
       }
       if (p.serial) {  // every update of this position has completed before the next position's rows are fetched
-        if (lane == 0) {
+        if (RG) {
+          fence_generic_to_async_global();
+        } else if (lane == 0) {
           bulk_commit();
           bulk_wait_all();
         }
