@@ -126,11 +126,12 @@ def measured_peak():
 
 
 def ncu_traffic_per_position():
-    if WORKLOAD != "c2":  # the committed ncu capture is of the headline shape
-        return None
+    """DRAM bytes per trained position of the training kernel, from the committed ncu capture of this workload at
+    the bench's own step size (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch of
+    `bench.py` under ncu, divided by the positions that launch trained; tools/measure_traffic.sh)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_position"])
+            return float(json.load(f)[WORKLOAD]["dram_bytes_per_position"])
     except Exception:
         return None
 
@@ -363,6 +364,7 @@ def main():
             acc["words"] += st["words"]; acc["positions"] += st["positions"]
             acc["rows"] += st["context_rows"] + st["target_rows"]
             acc["kernel_ms"] += st["kernel_ms"]; acc["launches"] += st["launches"]
+            acc.setdefault("per_step", []).append((st["positions"], st["kernel_ms"], st["launches"]))
             acc["h2d"] += st["h2d_bytes"]; acc["d2h"] += st["d2h_bytes"]; acc["loss"] += st["loss"]
         torch.cuda.synchronize()
         if dist:
@@ -392,6 +394,11 @@ def main():
     t = make(resident=True)
     a = run(t, args.steps, args.warmup, sampler_index=local if rank == 0 else None)
     t.close()
+    if os.environ.get("W2B_BENCH_STEP_LOG") and rank == 0:  # tools/measure_traffic.sh pairs this with ncu's launch list
+        with open(os.environ["W2B_BENCH_STEP_LOG"], "w") as f:
+            json.dump({"workload": WORKLOAD, "warmup": args.warmup, "per_step": a["per_step"]}, f)
+    if os.environ.get("W2B_BENCH_RESIDENT_ONLY"):
+        return 0
     # device time of the timed region = kernel events + sync; whole-job rate = all ranks' words / max time
     dev_s = reduce_max(a["kernel_ms"] / 1e3 + a["sync_ms"] / 1e3)
     wall_s = reduce_max(a["wall_s"])
@@ -406,7 +413,8 @@ def main():
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": (tpp * a["positions"] / max(a["launches"], 1)) if tpp else None,
             "peak_source": peak_src,
-            "kernel": "train_ring_kernel<%d,%d,2> (one launch per step)" % (BITS if BITS in (0, 1, 2) else 9, (D // 4 + 31) // 32),
+            "kernel": "train_warp_kernel<%d,%d> (one launch per step, one 32-thread CTA per shard)" % (
+                BITS if BITS in (0, 1, 2) else 9, (D // 4 + 31) // 32),
             "algorithmic_bytes_per_launch": alg_bytes / max(a["launches"], 1),
             "kernel_ms_per_launch": a["kernel_ms"] / max(a["launches"], 1),
             "bytes_per_position": alg_bytes / max(a["positions"], 1)}
@@ -429,7 +437,7 @@ def main():
                       "vocab": V, "size": D, "window": WINDOW, "negative": NEG, "bitlevel": BITS, "sample": SAMPLE,
                       "shards_per_gpu": S_local, "words_per_shard_per_step": B,
                       "l2": "inputs larger than L2: 2 x %.2f GB embedding tables + 400 MB unigram table per GPU, rows drawn at random" % ((V + 1) * D * 4 / 1e9),
-                      "parallelism": "dp%d, replica all-reduce-average of u and v every %d steps (NCCL)" % (world, args.sync_every) if world > 1 else "single GPU, %d concurrent shards (one CTA each)" % S_local},
+                      "parallelism": "dp%d, replica all-reduce-average of u and v every %d steps (NCCL)" % (world, args.sync_every) if world > 1 else "single GPU, %d concurrent shards (one warp each)" % S_local},
            "positions_per_s": positions / dev_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
            "sync_ms_per_step": a["sync_ms"] / args.steps,
            "roofline": roof, "e2e": e2e, "clocks": a["clocks"], "gpu_launches": int(a["launches"]),

@@ -256,6 +256,19 @@ def test_fast_statistical(b, D, neg, group, kernel, prefetch, large):
     assert cu > 0.75 and cv > 0.90, (cu, cv)
     if b == 1:
         assert agree > 0.70, agree
+    if b == 0 and kernel == 0:
+        # fp32 tolerance (north_star: "within a stated fp tolerance for bitlevel=0"): relative L2 distance of the master
+        # tables to the oracle's, in units of the oracle's own run-to-run distance at the same concurrency (two
+        # runs of its 16 Hogwild threads) — the GPU may be at most twice as far from the oracle as the oracle is
+        # from itself
+        m2 = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=2)
+        for ep in range(2):
+            m2.train_epoch_threads()
+        rel = lambda x, y: float(np.linalg.norm(x - y) / np.linalg.norm(y))
+        base_u, base_v = rel(m2.u, m.u), rel(m2.v, m.v)
+        gu, gv = rel(u, m.u), rel(v, m.v)
+        print("b=0 D=%d prefetch=%d rel-L2 vs oracle: u %.4f v %.4f; oracle vs oracle: u %.4f v %.4f" % (D, prefetch, gu, gv, base_u, base_v))
+        assert gu <= 2.0 * base_u + 1e-3 and gv <= 2.0 * base_v + 1e-3, (gu, gv, base_u, base_v)
 
 
 @pytest.mark.parametrize("kernel", [0, 1])
@@ -321,7 +334,7 @@ def test_fast_single_shard_tracks_oracle(kernel, prefetch, b, D, medium):
     ordered = not prefetch  # prefetch on: context rows are read one update stale
     assert abs(lg - lo) <= (1e-3 if ordered else 5e-3) * abs(lo)
     if b == 0:
-        lim = 5e-3 if ordered else 1e-1
+        lim = (5e-3 if D <= 200 else 2e-2) if ordered else 1e-1  # D=800: 4x the terms per dot product and update
         assert du < lim and dv < lim, (du, dv)
     else:  # b=2 is chaotic (level flips feed back): the reference's own two builds agree within
         # 1e-3 on only 26 % of the elements here, so hold the trajectories to correlation instead
@@ -550,5 +563,44 @@ def test_full_size_shape_properties(tmp_path):
         assert np.array_equal(bits(t.quantize(out, 1)), bits(out))       # idempotent
         u2, v2 = t.download_raw()
         assert np.isfinite(u2).all() and np.isfinite(v2).all() and not np.array_equal(bits(v2), bits(v))
+    finally:
+        os.unlink(path)
+
+
+@pytest.mark.parametrize("S", [148, 1776])
+def test_full_size_shape_loss_tracks_the_reference(S, tmp_path):
+    """L3 at the benchmarked shape: a 400k-class Zipf vocabulary, D=800, window 10,
+    negative 24, bitlevel 1 — with 148 shards and with the 1776 shards the bench runs (148 SMs x 12 warps).  Comparator:
+    the unmodified reference (oracle/_ref, -O3) with as many pthreads as there are shards, else the oracle port with
+    the same threads.  Bar: epoch loss within 1 % of the reference's, and not further from it than 1 % plus the
+    reference's own run-to-run spread (two runs of its Hogwild threads differ by 1e-4 .. 4e-4 here)."""
+    import bench
+    cdf, _ = bench.zipf_cdf(400000)
+    ids = bench.synth_ids(3_000_000, 99, cdf)
+    path = bench._write_text(ids, str(tmp_path / "big_"))
+    D, W, neg, b = 800, 10, 24, 1
+    try:
+        if po.ref_available("o3"):
+            ref = po.Ref("o3")
+            losses = []
+            for _ in range(2):
+                ref.configure(path, D, W, neg, b, threads=S, iters=1, min_count=1)
+                ref.learn_vocab(); ref.init_net(); ref.init_unigram()
+                losses.append(ref.train_epoch())
+            V = ref.V
+        else:
+            o = po.Corpus(path, 1)
+            losses = [po.OracleModel(o, D, W, neg, b, shards=S, iters=1).train_epoch_threads() for _ in range(2)]
+            V = o.vocab_size
+        lo, spread = 0.5 * (losses[0] + losses[1]), abs(losses[0] - losses[1])
+        c = w2b.Corpus(path, 1)
+        assert c.vocab_size == V
+        t = w2b.Trainer(c, size=D, window=W, negative=neg, bitlevel=b, threads=S, iter=1)
+        lg, st = t.train_epoch()
+        t.close()
+        print("full-size L3, %d shards: GPU epoch loss %.1f, reference %.1f / %.1f (rel. gap %.5f, reference spread %.5f)"
+              % (S, lg, losses[0], losses[1], abs(lg - lo) / abs(lo), spread / abs(lo)))
+        assert st["shards_done"] == S
+        assert abs(lg - lo) <= 0.01 * abs(lo) + spread, (lg, losses)
     finally:
         os.unlink(path)

@@ -351,39 +351,74 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   S.alpha_c = *(volatile float *)p.alpha;
   const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
 
-  // ---- job bookkeeping (all warp-uniform)
+  // ---- job bookkeeping (all warp-uniform).  Job j lives in slot j mod K; the issue side and the arithmetic each
+  // keep their slot's shared-memory address and mbarrier incrementally.  Every job arms its slot's mbarrier exactly
+  // once (a staging job with 0 bytes), so all slots advance one phase per trip round the ring and one parity bit,
+  // flipped at the wrap, serves every wait.
   unsigned q_tail = 0;   // jobs appended to the queue
-  unsigned q_issue = 0;  // jobs whose load has been issued (or skipped: staging jobs)
-  unsigned q_cons = 0;   // jobs consumed (their bulk group committed)
+  unsigned q_issue = 0;  // jobs whose load has been issued (staging jobs: barrier armed)
+  unsigned q_cons = 0;   // jobs consumed
   unsigned q_limit = 0;  // jobs the issue side may look at (serial: end of the current position)
-  int islot = 0, cslot = 0;
-  unsigned phase = 0;    // per-slot mbarrier parity
+  const unsigned ring_end = ring + (unsigned)K * rowb;
+  unsigned i_row = ring, i_bar = bars;  // issue slot
+  unsigned c_row = ring, c_bar = bars;  // slot of the job being worked on
+  unsigned c_par = 0;
   double loss = 0.0;     // per lane: reported loss of the targets this lane looked after
+  // a job may be issued once the job K before it has left its slot: with the bulk-reduce scatter that is known
+  // after the `wait_group.read 1` that follows the NEXT job (ahead = K - 2 loads in flight); with the red.global
+  // scatter (RG) a slot is free as soon as the warp has read it (ahead = K - 1)
+  const unsigned ahead = (unsigned)K - (RG ? 1u : 2u);
 
-  // Issue loads while job j <= q_cons + K - 2 (slot of job j - K confirmed free by the last wait_group.read 1;
-  // leaving 2 or 3 groups pending instead made no difference on B200: profiles/r02_warp_kernel_sweeps.md).
-  auto pump = [&]() {
-    while (q_issue < q_limit && q_issue + (RG ? 1u : 2u) <= q_cons + (unsigned)K) {
-      const int e = jobq[q_issue & qmask];
-      if (e >= 0 && lane == 0) {
+  auto issue_one = [&]() {  // all lanes; lane 0 acts.  Precondition: q_issue < q_limit, slot free.
+    const int e = jobq[q_issue & qmask];
+    if (lane == 0) {
+      if (e >= 0) {
         const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
-        const unsigned bar = bars + 8u * (unsigned)islot;
-        mbar_expect_tx(bar, rowb);
-        bulk_load(ring + (unsigned)islot * rowb, src, rowb, bar);
+        mbar_expect_tx(i_bar, rowb);
+        bulk_load(i_row, src, rowb, i_bar);
+      } else {
+        mbar_expect_tx(i_bar, 0);
       }
-      ++q_issue;
-      if (++islot == K) islot = 0;
     }
+    ++q_issue;
+    i_row += rowb; i_bar += 8u;
+    if (i_row == ring_end) { i_row = ring; i_bar = bars; }
   };
-  auto job_done = [&]() {  // the job's group is committed by lane 0; free the slot before it and refill
-    if (!RG && lane == 0) {
-      bulk_commit();
-      bulk_wait_read<1>();
-    }
-    __syncwarp();  // (RG: every lane has read the row out of its slot)
+  auto pump = [&]() {
+    while (q_issue < q_limit && q_issue <= q_cons + ahead) issue_one();
+  };
+  // End of a job, after every lane is done with the slot (__syncwarp by the caller): lane 0 hands the slot's row to
+  // the bulk-copy engine as an atomic-add scatter — to `dst` (target job), or to the position's n_dst context rows
+  // of u (staging job; none for a context job or with RG) — confirms the previous job's slot and refills it: one
+  // divergent region per job.
+  auto finish_job = [&](float *dst, int n_dst, unsigned q0) {
     ++q_cons;
-    if (++cslot == K) cslot = 0;
-    pump();
+    const bool can = q_issue < q_limit && q_issue <= q_cons + ahead;
+    const int e = can ? jobq[q_issue & qmask] : -1;
+    if (lane == 0) {
+      if (!RG) {
+        if (dst) bulk_reduce_add(dst, c_row, rowb);
+        else for (int k = 0; k < n_dst; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, c_row, rowb);
+        bulk_commit();
+        bulk_wait_read<1>();
+      }
+      if (can) {
+        if (e >= 0) {
+          const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
+          mbar_expect_tx(i_bar, rowb);
+          bulk_load(i_row, src, rowb, i_bar);
+        } else {
+          mbar_expect_tx(i_bar, 0);
+        }
+      }
+    }
+    if (can) {
+      ++q_issue;
+      i_row += rowb; i_bar += 8u;
+      if (i_row == ring_end) { i_row = ring; i_bar = bars; }
+    }
+    c_row += rowb; c_bar += 8u;
+    if (c_row == ring_end) { c_row = ring; c_bar = bars; c_par ^= 1u; }
   };
 
   int n_cw = 0, n_nt = 0;
@@ -417,26 +452,34 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
 #pragma unroll
     for (int j = 0; j < NJ; ++j) a[j][0] = a[j][1] = F2{0.f, 0.f};
     for (int k = 0; k < cw; ++k) {
-      mbar_wait(bars + 8u * (unsigned)cslot, (phase >> cslot) & 1u);
-      phase ^= 1u << cslot;
-      const unsigned row = ring + (unsigned)cslot * rowb;
+      mbar_wait(c_bar, c_par);
       float4 x[NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) x[j] = lds128(row + W2B_COFF(j));
+      for (int j = 0; j < NJ; ++j) x[j] = lds128(c_row + W2B_COFF(j));
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         a[j][0] = add2(a[j][0], F2{quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp)});
         a[j][1] = add2(a[j][1], F2{quant_fast<BM>(x[j].z, qp), quant_fast<BM>(x[j].w, qp)});
       }
-      job_done();
+      __syncwarp();
+      finish_job(nullptr, 0, q0);
     }
-    {
+    {  // context_avg = sum / cw (:449), correctly rounded without the division subroutine: q = a*r, then one
+       // Newton step on the exact remainder (r = RN(1/cw); equals IEEE division for every cw <= 128 and every
+       // numerator in range — tests/test_host_cpu.py checks the identity on the host)
       const float fcw = (float)cw;
+      const float rc = __frcp_rn(fcw);
+      const F2 r2 = F2{rc, rc}, nc2 = F2{-fcw, -fcw};
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const bool on = (j < NJ - 1) || on_last;
-        a[j][0] = on ? F2{__fdiv_rn(a[j][0].x, fcw), __fdiv_rn(a[j][0].y, fcw)} : F2{0.f, 0.f};
-        a[j][1] = on ? F2{__fdiv_rn(a[j][1].x, fcw), __fdiv_rn(a[j][1].y, fcw)} : F2{0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const F2 q0v = mul2(a[j][h], r2);
+          const F2 rem = fma2(q0v, nc2, a[j][h]);
+          const F2 q1v = fma2(rem, r2, q0v);
+          a[j][h] = on ? q1v : F2{0.f, 0.f};
+        }
       }
     }
 
@@ -446,13 +489,11 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     for (int j = 0; j < NJ; ++j) e[j][0] = e[j][1] = F2{0.f, 0.f};
     float myf0 = 0.f, myf1 = 0.f;  // lane i keeps +-f of targets i and 32+i for the reported loss (:480-483)
     for (int i = 0; i < nt; ++i) {
-      const int tid_row = jobq[q_cons & qmask] & kJobIdMask;
-      mbar_wait(bars + 8u * (unsigned)cslot, (phase >> cslot) & 1u);
-      phase ^= 1u << cslot;
-      const unsigned row = ring + (unsigned)cslot * rowb;
+      float *dst = p.v + (long long)(jobq[q_cons & qmask] & kJobIdMask) * p.D;
+      mbar_wait(c_bar, c_par);
       float4 x[NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) x[j] = lds128(row + W2B_COFF(j));
+      for (int j = 0; j < NJ; ++j) x[j] = lds128(c_row + W2B_COFF(j));
       F2 d0 = F2{0.f, 0.f}, d1 = F2{0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -477,21 +518,17 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
         e[j][1] = fma2(g2, F2{x[j].z, x[j].w}, e[j][1]);
         const F2 u0 = mul2(g2, a[j][0]), u1 = mul2(g2, a[j][1]);  // :490: g*context_avg replaces the row in its slot
         if ((j < NJ - 1) || on_last) {
-          if (RG) red_add_v4(p.v + (long long)tid_row * p.D + (W2B_COFF(j) >> 2), make_float4(u0.x, u0.y, u1.x, u1.y));
-          else sts128(row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
+          if (RG) red_add_v4(dst + (W2B_COFF(j) >> 2), make_float4(u0.x, u0.y, u1.x, u1.y));
+          else sts128(c_row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
         }
       }
-      if (!RG) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) bulk_reduce_add(p.v + (long long)tid_row * p.D, row, rowb);
-      }
-      job_done();
+      if (!RG) fence_async_smem();
+      __syncwarp();
+      finish_job(dst, 1, q0);
     }
 
     // ---- staging job: the error goes to every context row of u (:494-503)
     {
-      const unsigned row = ring + (unsigned)cslot * rowb;
       if (RG) {
         for (int k = 0; k < cw; ++k) {
           float *dst = p.u + (long long)jobq[(q0 + k) & qmask] * p.D;
@@ -503,30 +540,21 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
       } else {
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-          if ((j < NJ - 1) || on_last) sts128(row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
+          if ((j < NJ - 1) || on_last) sts128(c_row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
         fence_async_smem();
-        __syncwarp();
-        if (lane == 0)
-          for (int k = 0; k < cw; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, row, rowb);
       }
+      __syncwarp();
       if (lane < nt) loss += (double)logf(sigmoid_report(myf0));
       if (lane + 32 < nt) loss += (double)logf(sigmoid_report(myf1));
       if (ap.f_out) {
         if (lane < nt) ap.f_out[lane] = lane == 0 ? myf0 : -myf0;
         if (lane + 32 < nt) ap.f_out[lane + 32] = -myf1;
       }
+      finish_job(nullptr, cw, q0);
       if (p.serial) {  // every update of this position has completed before the next position's rows are fetched
-        if (RG) {
-          fence_generic_to_async_global();
-        } else if (lane == 0) {
-          bulk_commit();
-          bulk_wait_all();
-        }
+        if (RG) fence_generic_to_async_global();
+        else if (lane == 0) bulk_wait_all();
         __syncwarp();
-        ++q_cons;
-        if (++cslot == K) cslot = 0;
-      } else {
-        job_done();
       }
     }
   }
