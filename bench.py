@@ -353,14 +353,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         clocks = ClockSampler(sampler_index) if sampler_index is not None else None
-        acc = dict(words=0, positions=0, rows=0, kernel_ms=0.0, launches=0, h2d=0, d2h=0, loss=0.0, sync_ms=0.0)
+        acc = dict(words=0, positions=0, rows=0, kernel_ms=0.0, launches=0, h2d=0, d2h=0, loss=0.0, sync_ms=0.0, syncs=0)
+        sync_ms0, syncs0 = dp.sync_ms, dp.syncs
         t0 = time.time()
         for i in range(steps):
-            ts = time.time()
-            n_sync = dp.syncs
-            st = dp.step(B)  # train_step + (every sync_every steps) the NCCL replica average
-            if dp.syncs != n_sync:
-                acc["sync_ms"] += max(0.0, (time.time() - ts) * 1e3 - st["kernel_ms"])
+            st = dp.step(B)  # train_step + (every sync_every steps) the NCCL replica average (device-timed inside libw2b)
             acc["words"] += st["words"]; acc["positions"] += st["positions"]
             acc["rows"] += st["context_rows"] + st["target_rows"]
             acc["kernel_ms"] += st["kernel_ms"]; acc["launches"] += st["launches"]
@@ -371,6 +368,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t1 = time.time()
+        acc["sync_ms"], acc["syncs"] = dp.sync_ms - sync_ms0, dp.syncs - syncs0
+        dp.finish()  # outside the timed region: leave the replicas averaged, then compare their fingerprints
+        acc["replicas_identical"] = dp.replicas_identical()
         acc["wall_s"] = t1 - t0
         acc["alpha"] = st["alpha"]
         acc["clocks"] = clocks.stop(t0, t1) if clocks else None
@@ -440,6 +440,13 @@ def main():
                       "parallelism": "dp%d, replica all-reduce-average of u and v every %d steps (NCCL)" % (world, args.sync_every) if world > 1 else "single GPU, %d concurrent shards (one warp each)" % S_local},
            "positions_per_s": positions / dev_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
            "sync_ms_per_step": a["sync_ms"] / args.steps,
+           "sync": None if world == 1 else {
+               "every_steps": args.sync_every, "syncs_timed": a["syncs"],
+               "ms_per_sync": a["sync_ms"] / max(a["syncs"], 1),
+               "bytes_per_sync": 2 * (V + 1) * D * 4,
+               "allreduce_bus_gbs": (2.0 * (world - 1) / world) * (2 * (V + 1) * D * 4) / 1e9 / max(a["sync_ms"] / max(a["syncs"], 1) / 1e3, 1e-9),
+               "what": "one NCCL group: ncclAllReduce(avg) of u and of v in place + the exact global word counter, on the training stream (device time incl. waiting for the slowest rank)",
+               "sync_check": {"replicas_bit_identical_after_sync": bool(a["replicas_identical"])}},
            "roofline": roof, "e2e": e2e, "clocks": a["clocks"], "gpu_launches": int(a["launches"]),
            "mean_loss_per_position": a["loss"] / max(a["positions"], 1)}
     if rank == 0:

@@ -217,7 +217,10 @@ int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int64_t thresho
 int w2b_device_ptrs(w2b_ctx *ctx, void **u, void **v, int64_t *elems);
 int w2b_nccl_unique_id(void *id128);                                    /* ncclGetUniqueId */
 int w2b_nccl_init(w2b_ctx *ctx, const void *id128, int rank, int nranks); /* ncclCommInitRank */
-int w2b_sync(w2b_ctx *ctx); /* all-reduce-average u, v; sum word_count_actual deltas */
+int w2b_sync(w2b_ctx *ctx); /* all-reduce-average u, v; exact global word_count_actual — one NCCL group, no host round trip */
+int w2b_sync_timed(w2b_ctx *ctx, float *ms); /* same; *ms = device time of the exchange (CUDA events) */
+/* Fingerprints of u and v (sum of the 32-bit patterns mod 2^64): equal on every rank right after w2b_sync. */
+int w2b_table_checksum(w2b_ctx *ctx, uint64_t *u_sum, uint64_t *v_sum);
 int w2b_scale_tables(w2b_ctx *ctx, float s); /* u*=s, v*=s (for host-driven all-reduce) */
 
 #ifdef __cplusplus

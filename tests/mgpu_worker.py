@@ -42,6 +42,7 @@ def main():
     ref = torch.from_numpy(u2).cuda()
     dist.broadcast(ref, 0)
     assert np.array_equal(ref.cpu().numpy(), u2)  # bit-identical replicas after the average
+    assert dp.replicas_identical()                # ... which is what the bench's sync_check reports
     (tot,), _ = dp.reduce(sums=[words])
     _, wca = t.get_state()
     # every shard is still below the 10k-word cadence except those that crossed it: the synced

@@ -462,6 +462,13 @@ def test_checkpoint_resume_is_exact(tmp_path, medium):
     assert a.get_state() == r.get_state()
     with pytest.raises(w2b.W2BError):
         w2b.Trainer(c, size=24, window=5, negative=6, threads=2).checkpoint_load(ck)  # wrong shape
+    for other in (dict(kw, bitlevel=2), dict(kw, iter=3)):  # another bit level / learning-rate schedule is refused
+        with pytest.raises(w2b.W2BError, match="was written with"):
+            w2b.Trainer(c, **other).checkpoint_load(ck)
+    assert not os.path.exists(ck + ".tmp")  # written beside the target, then renamed over it
+    open(ck + ".junk", "wb").write(open(ck, "rb").read()[:1000])
+    with pytest.raises(w2b.W2BError):
+        w2b.Trainer(c, **kw).checkpoint_load(ck + ".junk")  # truncated file
 
 
 def _analogy_fixture(tmp_path, D=48, pairs=300, sections=8, per_section=120, bits=0, seed=5):

@@ -21,6 +21,10 @@ class FakeTrainer:
     def sync(self):
         dist.barrier()
         self.syncs += 1
+        return 1.5  # device ms of the exchange, as Trainer.sync reports it
+
+    def table_checksum(self):
+        return (1 << 63) + 12345, 777  # equal on every rank after a sync (top bit: must survive the int64 transport)
 
 
 def _worker(rank, world, port, q):
@@ -37,6 +41,7 @@ def _worker(rank, world, port, q):
             words += dp.step(1000)["words"]
         dp.finish()
         sums, maxes = dp.reduce(sums=[words], maxes=[5.0 + rank])
+        assert dp.replicas_identical() and dp.sync_ms == 1.5 * t.syncs
         q.put((rank, lo, hi, uid == bytes(range(128)), t.steps, t.syncs, sums[0], maxes[0]))
     finally:
         dist.destroy_process_group()

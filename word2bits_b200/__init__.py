@@ -256,7 +256,16 @@ class Trainer:
         check(lib.w2b_nccl_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
 
     def sync(self):
-        check(lib.w2b_sync(self.h))
+        """Replica average + exact global word counter; returns the device time of the exchange in ms."""
+        ms = C.c_float(0)
+        check(lib.w2b_sync_timed(self.h, C.byref(ms)))
+        return ms.value
+
+    def table_checksum(self):
+        """(sum of u's bit patterns, sum of v's) mod 2^64: equal on every rank right after sync()."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib.w2b_table_checksum(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "h", None):

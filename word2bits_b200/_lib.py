@@ -66,7 +66,7 @@ EXPORTS = [
     "w2b_init_tables", "w2b_epoch_begin", "w2b_train_step", "w2b_train_epoch", "w2b_trace",
     "w2b_strict_prefix", "w2b_apply_position", "w2b_get_state", "w2b_set_state", "w2b_download_raw",
     "w2b_upload_raw", "w2b_download_table", "w2b_download_exptable", "w2b_export", "w2b_quantize",
-    "w2b_device_ptrs", "w2b_nccl_unique_id", "w2b_nccl_init", "w2b_sync", "w2b_scale_tables",
+    "w2b_device_ptrs", "w2b_nccl_unique_id", "w2b_nccl_init", "w2b_sync", "w2b_sync_timed", "w2b_table_checksum", "w2b_scale_tables",
     "w2b_write_packed", "w2b_read_packed_header", "w2b_read_packed", "w2b_checkpoint_save", "w2b_checkpoint_load", "w2b_compute_accuracy",
     "w2b_host_unigram_bounds", "w2b_host_exptable", "w2b_host_keep_thresholds", "w2b_host_lcg_tables", "w2b_warp_plan_query", "w2b_host_gather_slices",
 ]
@@ -132,6 +132,8 @@ lib.w2b_device_ptrs.argtypes = [_vp, _P(_vp), _P(_vp), _P(_i64)]
 lib.w2b_nccl_unique_id.argtypes = [_vp]
 lib.w2b_nccl_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
 lib.w2b_sync.argtypes = [_vp]
+lib.w2b_sync_timed.argtypes = [_vp, _P(_f)]
+lib.w2b_table_checksum.argtypes = [_vp, _P(C.c_uint64), _P(C.c_uint64)]
 lib.w2b_scale_tables.argtypes = [_vp, _f]
 
 

@@ -164,7 +164,7 @@ int main(int argc, char **argv) {
   Barrier bar(G);
   std::mutex mu;
   double epoch_loss = 0;
-  long long words_done = 0, step_words = 0;
+  long long words_done = 0, words_at_start = 0, step_words = 0;
   int ranks_busy = 0;
   struct timespec t0;
   clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -190,6 +190,13 @@ int main(int argc, char **argv) {
       int64_t done = 0;
       if (w2b_checkpoint_load(ctx, resume_file.c_str(), &done)) die("w2b_checkpoint_load");
       first_epoch = done;
+      if (rank == 0) {  // Progress % continues from the checkpoint's word counter
+        float a0 = 0;
+        int64_t wca = 0;
+        if (w2b_get_state(ctx, &a0, &wca)) die("w2b_get_state");
+        std::lock_guard<std::mutex> lk(mu);
+        words_done = words_at_start = wca;
+      }
     }
     std::vector<float> buf;
     if (rank == 0) buf.resize((size_t)V * layer1_size);
@@ -215,12 +222,15 @@ int main(int argc, char **argv) {
         bar.wait();  // every rank sees the same ranks_busy: collectives stay aligned
         const bool more = ranks_busy > 0;
         if (G > 1 && (step % sync_every == 0 || !more) && w2b_sync(ctx)) die("w2b_sync");
-        if (rank == 0 && debug_mode > 1) {  // :384-387 (Words/sec is wall-clock and whole-job, not per CPU thread)
+        if (rank == 0 && debug_mode > 1) {
+          // :384-387, same line format.  The reference divides by clock(), the CPU time of ALL its threads, i.e. it
+          // prints words per worker-second; here a worker is a shard: words / (wall seconds x shards)
           struct timespec now;
           clock_gettime(CLOCK_MONOTONIC, &now);
           double secs = (now.tv_sec - t0.tv_sec) + (now.tv_nsec - t0.tv_nsec) * 1e-9;
-          printf("%cAlpha: %f  Progress: %.2f%%  Cost: %f Words/sec: %.2fk  ", 13, st.alpha,
-                 words_done / (float)(iter * train_words + 1) * 100, st.loss, words_done / (secs + 1e-9) / 1000);
+          printf("%cAlpha: %f  Progress: %.2f%%  Cost: %f Words/thread/sec: %.2fk  ", 13, st.alpha,
+                 words_done / (float)(iter * train_words + 1) * 100, st.loss,
+                 (words_done - words_at_start) / (secs + 1e-9) / 1000 / cfg.num_shards);
           fflush(stdout);
         }
         bar.wait();

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -68,6 +69,8 @@ struct NcclApi {
   int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
   int (*CommDestroy)(nccl_comm) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -89,7 +92,9 @@ static int nccl_load() {
       (int (*)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t))dlsym(h, "ncclAllReduce");
   g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+  g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
     w2b_set_error("NCCL symbols missing");
     return W2B_ENCCL;
   }
@@ -135,7 +140,9 @@ struct w2b_ctx {
   } pf;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
-  unsigned long long *d_scratch = nullptr;  // 64 B: word-count all-reduce
+  unsigned long long *d_scratch = nullptr;  // 64 B: [0] own words since the last sync (all-reduced), [1] counter at the last sync
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
+  float last_sync_ms = 0.f;
   nccl_comm comm = nullptr;
   int rank = 0, nranks = 1;
   long long wca_at_sync = 0;
@@ -456,6 +463,9 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
     CK(cudaMemcpyToSymbol(c_exptab, t, sizeof t));
   }
   CK(cudaMalloc(&c->d_scratch, 64));
+  CK(cudaMemset(c->d_scratch, 0, 64));
+  CK(cudaEventCreate(&c->ev_s0));
+  CK(cudaEventCreate(&c->ev_s1));
   return W2B_OK;
 }
 
@@ -475,6 +485,8 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->ev_s0) cudaEventDestroy(c->ev_s0);
+  if (c->ev_s1) cudaEventDestroy(c->ev_s1);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -1013,6 +1025,7 @@ extern "C" int w2b_set_state(w2b_ctx *c, float alpha, int64_t wca) {
   unsigned long long w = (unsigned long long)wca;
   CK(cudaMemcpy(c->d_alpha, &alpha, sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_wca, &w, sizeof w, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_scratch + 1, &w, sizeof w, cudaMemcpyHostToDevice));
   c->wca_at_sync = wca;
   return W2B_OK;
 }
@@ -1056,7 +1069,8 @@ struct CkptHeader {
   char magic[8];
   int64_t V, D, epochs_done, wca;
   float alpha;
-  int32_t pad;
+  int32_t bitlevel;
+  int64_t iter, train_words;  // what the learning-rate schedule (:391) is built from
 };
 static int w2b_checkpoint_save_impl(w2b_ctx *c, const char *path, int64_t epochs_done);
 extern "C" int w2b_checkpoint_save(w2b_ctx *c, const char *path, int64_t epochs_done) {
@@ -1068,14 +1082,17 @@ static int w2b_checkpoint_save_impl(w2b_ctx *c, const char *path, int64_t epochs
   CK(cudaSetDevice(c->cfg.device));
   CkptHeader h;
   memset(&h, 0, sizeof h);
-  memcpy(h.magic, "W2BCKPT1", 8);
+  memcpy(h.magic, "W2BCKPT2", 8);
   h.V = c->cfg.vocab_size; h.D = c->cfg.layer1_size; h.epochs_done = epochs_done;
+  h.bitlevel = c->cfg.bitlevel; h.iter = c->cfg.iter; h.train_words = c->train_words;
   unsigned long long w = 0;
   CK(cudaMemcpy(&h.alpha, c->d_alpha, sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost));
   h.wca = (int64_t)w;
-  FILE *f = fopen(path, "wb");
-  if (!f) { w2b_set_error("cannot open %s for writing", path); return W2B_EIO; }
+  // written beside the target and renamed over it: a crash or a full disk mid-write keeps the previous checkpoint
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) { w2b_set_error("cannot open %s for writing", tmp.c_str()); return W2B_EIO; }
   bool ok = fwrite(&h, sizeof h, 1, f) == 1;
   const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
   std::vector<float> buf(std::min(n, piece));
@@ -1084,13 +1101,17 @@ static int w2b_checkpoint_save_impl(w2b_ctx *c, const char *path, int64_t epochs
       const size_t k = std::min(piece, n - o);
       if (cudaMemcpy(buf.data(), src + o, k * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
         fclose(f);
+        remove(tmp.c_str());
         w2b_set_error("checkpoint download failed");
         return W2B_ECUDA;
       }
       ok = fwrite(buf.data(), sizeof(float), k, f) == k;
     }
+  if (ok && fflush(f) != 0) ok = false;
+  if (ok && fsync(fileno(f)) != 0) ok = false;
   if (fclose(f) != 0) ok = false;
-  if (!ok) { w2b_set_error("short write to %s (disk full?)", path); return W2B_EIO; }
+  if (!ok) { remove(tmp.c_str()); w2b_set_error("short write to %s (disk full?)", tmp.c_str()); return W2B_EIO; }
+  if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); w2b_set_error("cannot move %s to %s", tmp.c_str(), path); return W2B_EIO; }
   return W2B_OK;
 }
 
@@ -1105,12 +1126,19 @@ static int w2b_checkpoint_load_impl(w2b_ctx *c, const char *path, int64_t *epoch
   FILE *f = fopen(path, "rb");
   if (!f) { w2b_set_error("cannot open %s", path); return W2B_EIO; }
   CkptHeader h;
-  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "W2BCKPT1", 8) != 0 || h.V != c->cfg.vocab_size ||
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "W2BCKPT2", 8) != 0 || h.V != c->cfg.vocab_size ||
       h.D != c->cfg.layer1_size) {
     fclose(f);
     w2b_set_error("%s is not a checkpoint of a %lld x %lld model", path, (long long)c->cfg.vocab_size,
                   (long long)c->cfg.layer1_size);
     return W2B_EIO;
+  }
+  if (h.bitlevel != c->cfg.bitlevel || h.iter != c->cfg.iter || (c->have_counts && h.train_words != c->train_words)) {
+    fclose(f);  // resuming under another schedule or bit level would silently train something else
+    w2b_set_error("%s was written with -bitlevel %d -iter %lld on %lld training words; this run has -bitlevel %d -iter %lld on %lld",
+                  path, (int)h.bitlevel, (long long)h.iter, (long long)h.train_words, (int)c->cfg.bitlevel,
+                  (long long)c->cfg.iter, (long long)c->train_words);
+    return W2B_EINVAL;
   }
   const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
   std::vector<float> buf(std::min(n, piece));
@@ -1210,31 +1238,74 @@ extern "C" int w2b_scale_tables(w2b_ctx *c, float s) {
   return W2B_OK;
 }
 
-// Replica averaging: u, v <- mean over ranks (ncclAvg, in place, on this context's
-// stream); word_count_actual <- exact global sum.  G=1: no-op, NCCL never touched.
-extern "C" int w2b_sync(w2b_ctx *c) {
+// word_count_actual across ranks, on the device: between two syncs every rank advances its counter by nranks x its
+// own words (TrainParams::wca_scale), so that the learning-rate schedule runs on the global clock; at a sync the
+// exact global count replaces the estimate.  scratch[1] = counter at the last sync.
+__global__ void wca_own_kernel(const unsigned long long *wca, unsigned long long *scratch, int nranks) {
+  scratch[0] = (*wca - scratch[1]) / (unsigned long long)nranks;
+}
+__global__ void wca_apply_kernel(unsigned long long *wca, unsigned long long *scratch) {
+  scratch[1] += scratch[0];
+  *wca = scratch[1];
+}
+// order-independent fingerprint of a table: sum of its 32-bit patterns (mod 2^64)
+__global__ void checksum_kernel(const unsigned *x, long long n, unsigned long long *out) {
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += x[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// Replica averaging: u, v <- mean over ranks (ncclAvg, in place) and word_count_actual <- exact global sum, as ONE
+// NCCL group on this context's stream — no host round trip between the three reductions.  G=1: no-op, NCCL never
+// touched.  *ms (optional) = device time of the exchange (CUDA events).
+extern "C" int w2b_sync_timed(w2b_ctx *c, float *ms) {
   NEED(c);
+  if (ms) *ms = 0.f;
   if (c->nranks <= 1) return W2B_OK;
   if (!c->comm) { w2b_set_error("w2b_nccl_init first"); return W2B_ESTATE; }
   CK(cudaSetDevice(c->cfg.device));
   const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size;
-  int e = g_nccl.AllReduce(c->d_u, c->d_u, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
+  CK(cudaEventRecord(c->ev_s0, c->stream));
+  wca_own_kernel<<<1, 1, 0, c->stream>>>(c->d_wca, c->d_scratch, c->nranks);
+  CK(cudaGetLastError());
+  int e = g_nccl.GroupStart();
+  if (!e) e = g_nccl.AllReduce(c->d_u, c->d_u, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
   if (!e) e = g_nccl.AllReduce(c->d_v, c->d_v, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
+  if (!e) e = g_nccl.AllReduce(c->d_scratch, c->d_scratch, 1, kNcclUint64, kNcclSum, c->comm, c->stream);
+  const int e2 = g_nccl.GroupEnd();
+  if (!e) e = e2;
   if (e) { w2b_set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
-  // local counter holds wca_at_sync + nranks * (own words since the last sync)
-  unsigned long long w = 0;
-  CK(cudaMemcpyAsync(&w, c->d_wca, sizeof w, cudaMemcpyDeviceToHost, c->stream));
+  wca_apply_kernel<<<1, 1, 0, c->stream>>>(c->d_wca, c->d_scratch);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev_s1, c->stream));
+  unsigned long long at_sync = 0;
+  CK(cudaMemcpyAsync(&at_sync, c->d_scratch + 1, sizeof at_sync, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  unsigned long long own = ((long long)w - c->wca_at_sync) / c->nranks;
-  unsigned long long *d_tmp = c->d_scratch;
-  CK(cudaMemcpyAsync(d_tmp, &own, sizeof own, cudaMemcpyHostToDevice, c->stream));
-  e = g_nccl.AllReduce(d_tmp, d_tmp, 1, kNcclUint64, kNcclSum, c->comm, c->stream);
-  if (e) { w2b_set_error("ncclAllReduce(wca): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
-  unsigned long long total = 0;
-  CK(cudaMemcpyAsync(&total, d_tmp, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+  c->wca_at_sync = (long long)at_sync;
+  CK(cudaEventElapsedTime(&c->last_sync_ms, c->ev_s0, c->ev_s1));
+  if (ms) *ms = c->last_sync_ms;
+  return W2B_OK;
+}
+extern "C" int w2b_sync(w2b_ctx *c) { return w2b_sync_timed(c, nullptr); }
+
+// Fingerprints of u and v (sum of the 32-bit patterns): equal on every rank after w2b_sync.
+extern "C" int w2b_table_checksum(w2b_ctx *c, uint64_t *u_sum, uint64_t *v_sum) {
+  NEED(c);
+  NEED(u_sum);
+  NEED(v_sum);
+  CK(cudaSetDevice(c->cfg.device));
+  const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
+  DevTmp t;
+  CK(t.alloc(16));
+  CK(cudaMemsetAsync(t.p, 0, 16, c->stream));
+  checksum_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const unsigned *)c->d_u, n, t.as<unsigned long long>());
+  checksum_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const unsigned *)c->d_v, n, t.as<unsigned long long>() + 1);
+  CK(cudaGetLastError());
+  unsigned long long h[2];
+  CK(cudaMemcpyAsync(h, t.p, 16, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->wca_at_sync += (long long)total;
-  unsigned long long nw = (unsigned long long)c->wca_at_sync;
-  CK(cudaMemcpy(c->d_wca, &nw, sizeof nw, cudaMemcpyHostToDevice));
+  *u_sum = h[0];
+  *v_sum = h[1];
   return W2B_OK;
 }

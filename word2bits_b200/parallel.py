@@ -36,20 +36,32 @@ class DataParallel:
         self.world = dist.get_world_size() if dist else 1
         self.steps = 0
         self.syncs = 0
+        self.sync_ms = 0.0  # device time spent in the replica average (CUDA events inside libw2b)
 
     def step(self, words_per_shard):
         st = self.t.train_step(words_per_shard)
         self.steps += 1
         if self.world > 1 and self.steps % self.k == 0:
-            self.t.sync()
+            self.sync_ms += self.t.sync()
             self.syncs += 1
         return st
 
     def finish(self):
         """Replicas must agree before anything is exported."""
         if self.world > 1 and self.steps % self.k != 0:
-            self.t.sync()
+            self.sync_ms += self.t.sync()
             self.syncs += 1
+
+    def replicas_identical(self):
+        """After a sync every rank holds the same bits: compare table fingerprints across ranks."""
+        if not self.dist or self.world == 1:
+            return True
+        import torch
+        a, b = self.t.table_checksum()
+        mine = torch.tensor([a & 0x7FFFFFFFFFFFFFFF, b & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=self.device)
+        allv = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allv, mine)
+        return all(bool((x == allv[0]).all()) for x in allv)
 
     def reduce(self, sums=(), maxes=()):
         """All-reduce python floats: returns (summed list, maxed list)."""
