@@ -146,6 +146,8 @@ typedef struct {
   int32_t slots;          /* K: shared-memory row slots of a warp's ring (K-2 loads in flight) */
   int32_t queue_entries;  /* job queue capacity (two positions) */
   int32_t warps_per_sm;   /* resident 1-warp CTAs per SM the registers are sized for */
+  int32_t sentence_in_smem; /* 1: the shard's sentence buffer (4000 B) is part of smem_bytes; 0: global scratch */
+  int32_t reserved;
   int64_t smem_bytes;     /* dynamic shared memory per warp */
 } w2b_warp_plan;
 int w2b_warp_plan_query(const w2b_config *cfg, w2b_warp_plan *out);

@@ -67,7 +67,7 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
     p = _lib.ptr
     r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
                alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
-               opt=red, lpr=32, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32,
+               opt=red, lpr=32 if plan["sentence_in_smem"] else 0, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32,
                serial=serial,
                u=p(u), v=p(v), table=p(table), keep=p(keep), exptab=p(exptab), tokens=p(tokens), n_tokens=len(tokens),
                shard_start=p(start), shard_first=p(first), alpha=p(a), wca=p(wca), word_budget=0, max_iters=max_iters,

@@ -320,13 +320,13 @@ bool run_block(int nthreads, void (*entry)()) {
 }
 
 w2b::TrainParams g_p;
-int g_nu, g_nv;
+int g_nu, g_nv, g_sen_smem = 1;
 typedef void (*entry_fn)();
 template <int BM, int NJ, int RG>
 void warp_entry() {
   w2b::ApplyArgs none;
   memset(&none, 0, sizeof none);
-  w2b::train_warp_kernel<BM, NJ, 12, RG>(g_p, g_nv, g_nu, none);
+  w2b::train_warp_kernel<BM, NJ, 12, RG>(g_p, g_nv, g_nu | (g_sen_smem << 31), none);
 }
 template <int BM, int RG>
 entry_fn warp_by_nj(int nj) {
@@ -449,13 +449,16 @@ int emu_run_warp(const EmuRun *r) {
     default: fn = r->opt ? warp_by_nj<9, 1>(nj) : warp_by_nj<9, 0>(nj); break;
   }
   if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
+  std::vector<int> sen((size_t)kMaxS * (r->num_shards + 1));
+  p.sen = sen.data();
+  g_sen_smem = r->lpr == 32 ? 1 : 0;  // r->lpr: 32 = sentence buffer in shared memory, anything else = global
   g_p = p; g_nv = r->nv; g_nu = r->nu;
   {
-    const WarpLayout L = warp_layout(r->D, r->nv, r->nu);
+    const WarpLayout L = warp_layout(r->D, r->nv, r->nu, g_sen_smem);
     if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }
     g_smem_total = L.total;
-    g_rows_end = L.off_sen;  // the ring: rows of 4*D bytes from offset 0
-    g_ring_end = L.off_sen;
+    g_rows_end = (size_t)r->nv * L.rowb;  // the ring: rows of 4*D bytes from offset 0
+    g_ring_end = g_rows_end;
     g_rowb = (unsigned)L.rowb;
   }
   gridDim.x = r->num_shards;

@@ -47,7 +47,8 @@ class Accuracy(C.Structure):
 
 
 class WarpPlan(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("warp", "slots", "queue_entries", "warps_per_sm")] + [("smem_bytes", C.c_int64)]
+    _fields_ = [(n, C.c_int32) for n in ("warp", "slots", "queue_entries", "warps_per_sm", "sentence_in_smem", "reserved")] + \
+               [("smem_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -110,7 +110,9 @@ struct w2b_ctx {
   int vec = 4, ncol = 0, threads = 0, group = 9;
   bool warp = false;       // production warp-per-shard kernel (csrc/w2b_warp.cuh) usable for this configuration
   int warp_k = 0, warp_qcap = 0, warp_minb = 0;  // ring slots per warp, job queue entries, warps per SM
+  int warp_sen_smem = 1;   // the sentence buffer fits shared memory (else d_sen)
   size_t warp_smem = 0;
+  int *d_sen = nullptr;    // global sentence buffers: kMaxS ints per local shard (+ 1 for the parity hooks)
   int sm_count = 0;
   long long train_words = 0;
   float *d_u = nullptr, *d_v = nullptr, *d_keep = nullptr, *d_exptab = nullptr, *d_alpha = nullptr;
@@ -208,18 +210,26 @@ static apply_fn pick_apply(const w2b_ctx *c) {
 typedef void (*warp_fn)(TrainParams, int, int, ApplyArgs);
 // warps (= 1-warp CTAs) per SM the register allocation is sized for; multiples of 4 because the register file is
 // split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96
-static int warp_minb_of(int nj) { return nj >= 5 ? 12 : (nj >= 3 ? 16 : 20); }
+static bool warp_dense() {  // A/B hook: 16 / 20 / 24 instead of 12 / 16 / 20 warps per SM (128 / 96 / 80 registers per thread)
+  static const bool on = getenv("W2B_WARP_DENSE") && atoi(getenv("W2B_WARP_DENSE")) != 0;
+  return on;
+}
+static int warp_minb_of(int nj) {
+  if (warp_dense()) return nj >= 5 ? 16 : (nj >= 3 ? 20 : 24);
+  return nj >= 5 ? 12 : (nj >= 3 ? 16 : 20);
+}
 template <int BM, int RG>
 static warp_fn warp_by_nj(int nj) {
+  const bool d = warp_dense();
   switch (nj) {
-    case 1: return train_warp_kernel<BM, 1, 20, RG>;
-    case 2: return train_warp_kernel<BM, 2, 20, RG>;
-    case 3: return train_warp_kernel<BM, 3, 16, RG>;
-    case 4: return train_warp_kernel<BM, 4, 16, RG>;
-    case 5: return train_warp_kernel<BM, 5, 12, RG>;
-    case 6: return train_warp_kernel<BM, 6, 12, RG>;
-    case 7: return train_warp_kernel<BM, 7, 12, RG>;
-    case 8: return train_warp_kernel<BM, 8, 12, RG>;
+    case 1: return d ? train_warp_kernel<BM, 1, 24, RG> : train_warp_kernel<BM, 1, 20, RG>;
+    case 2: return d ? train_warp_kernel<BM, 2, 24, RG> : train_warp_kernel<BM, 2, 20, RG>;
+    case 3: return d ? train_warp_kernel<BM, 3, 20, RG> : train_warp_kernel<BM, 3, 16, RG>;
+    case 4: return d ? train_warp_kernel<BM, 4, 20, RG> : train_warp_kernel<BM, 4, 16, RG>;
+    case 5: return d ? train_warp_kernel<BM, 5, 16, RG> : train_warp_kernel<BM, 5, 12, RG>;
+    case 6: return d ? train_warp_kernel<BM, 6, 16, RG> : train_warp_kernel<BM, 6, 12, RG>;
+    case 7: return d ? train_warp_kernel<BM, 7, 16, RG> : train_warp_kernel<BM, 7, 12, RG>;
+    case 8: return d ? train_warp_kernel<BM, 8, 16, RG> : train_warp_kernel<BM, 8, 12, RG>;
   }
   return nullptr;
 }
@@ -250,14 +260,27 @@ static void plan_warp(w2b_ctx *c) {
   const int minb = warp_minb_of(nj);
   const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
   const size_t budget = (size_t)(228 * 1024) / minb - 1024;
+  // the sentence buffer (4000 B) moves to global memory when keeping it in shared memory would cost ring slots
+  // below 4 (wide rows)
+  int sen_smem = 1;
   int K = c->cfg.slots > 0 ? std::min(c->cfg.slots, 32) : 16;
-  while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap).total > budget) --K;
+  while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap, sen_smem).total > budget) --K;
+  if (K < 4 && c->cfg.slots <= 0) {
+    int K2 = 16;
+    while (K2 >= 3 && warp_layout(c->cfg.layer1_size, K2, qcap, 0).total > budget) --K2;
+    if (K2 > K) { K = K2; sen_smem = 0; }
+  } else if (K < 3) {
+    sen_smem = 0;
+    K = std::min(c->cfg.slots, 32);
+    while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap, sen_smem).total > budget) --K;
+  }
   if (K < 3) return;
   c->warp = true;
   c->warp_k = K;
   c->warp_qcap = qcap;
   c->warp_minb = minb;
-  c->warp_smem = warp_layout(c->cfg.layer1_size, K, qcap).total;
+  c->warp_sen_smem = sen_smem;
+  c->warp_smem = warp_layout(c->cfg.layer1_size, K, qcap, sen_smem).total;
 }
 
 static size_t dyn_smem(const w2b_ctx *c) {
@@ -294,6 +317,7 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.plain_store = c->cfg.plain_store;
   p.serial = c->cfg.prefetch ? 0 : 1;  // default: the positions of a shard strictly one after another
   p.wca_scale = c->nranks;
+  p.sen = c->d_sen;
   return p;
 }
 
@@ -368,6 +392,7 @@ extern "C" int w2b_warp_plan_query(const w2b_config *cfg, w2b_warp_plan *out) {
   out->warp = tmp.warp ? 1 : 0;
   if (!tmp.warp) return W2B_OK;
   out->slots = tmp.warp_k;
+  out->sentence_in_smem = tmp.warp_sen_smem;
   out->queue_entries = tmp.warp_qcap;
   out->warps_per_sm = tmp.warp_minb;
   out->smem_bytes = (int64_t)tmp.warp_smem;
@@ -464,6 +489,7 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   }
   CK(cudaMalloc(&c->d_scratch, 64));
   CK(cudaMemset(c->d_scratch, 0, 64));
+  if (c->warp && !c->warp_sen_smem) CK(cudaMalloc(&c->d_sen, sizeof(int) * (size_t)kMaxS * (c->nlocal + 1)));
   CK(cudaEventCreate(&c->ev_s0));
   CK(cudaEventCreate(&c->ev_s1));
   return W2B_OK;
@@ -477,6 +503,7 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
   cudaFree(c->d_shards);
   cudaFree(c->d_scratch);
+  cudaFree(c->d_sen);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   for (int b = 0; b < 2; ++b) {
     if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
@@ -721,7 +748,7 @@ static int launch_enqueue(w2b_ctx *c, TrainParams p, w2b_step_stats *acc) {
     p.shard_base = 0;
     ApplyArgs none;
     memset(&none, 0, sizeof none);
-    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
+    wf<<<c->nlocal, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap | (c->warp_sen_smem << 31), none);
   } else {
     train_fn fn = pick_train(c);
     if (!fn) { w2b_set_error("no kernel for this configuration"); return W2B_EINVAL; }
@@ -916,7 +943,8 @@ static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_tra
     CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
     ApplyArgs none;
     memset(&none, 0, sizeof none);
-    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, none);
+    if (p.sen) p.sen += (size_t)kMaxS * c->nlocal;  // the hooks' own sentence buffer (block 0 of the launch)
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap | (c->warp_sen_smem << 31), none);
   } else {
     train_fn fn = pick_train(c);
     const size_t smem = dyn_smem(c);
@@ -993,7 +1021,8 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
     p.serial = 1;
     ApplyArgs ap;
     ap.ctx = d_ids; ap.tg = d_ids + cw; ap.cw = cw; ap.nt = nt; ap.f_out = d_f;
-    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap, ap);
+    if (p.sen) p.sen += (size_t)kMaxS * c->nlocal;
+    wf<<<1, 32, c->warp_smem, c->stream>>>(p, c->warp_k, c->warp_qcap | (c->warp_sen_smem << 31), ap);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     if (f_out && nt) CK(cudaMemcpy(f_out, d_f, nt * sizeof(float), cudaMemcpyDeviceToHost));

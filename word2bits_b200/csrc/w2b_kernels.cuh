@@ -76,6 +76,7 @@ struct TrainParams {
   int plain_store;
   int serial;                   // warp kernel: 1 = position p+1 is fetched after every update of p completed
   int wca_scale;                // multi-GPU: local words stand for wca_scale x as many globally
+  int *sen;                     // warp kernel: global sentence buffers (kMaxS ints per local shard + 1) when they do not fit shared memory
   w2b_trace_rec *trace;
   long long trace_cap;
   unsigned long long *trace_n;

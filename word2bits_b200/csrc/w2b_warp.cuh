@@ -41,19 +41,35 @@ constexpr int kJobTarget = 0x40000000;  // job queue entry: row id | kJobTarget 
 constexpr int kJobIdMask = 0x3fffffff;
 
 // Shared-memory carve-up of one warp (host and device agree through this helper).
+// Sampler state of a shard: warp-uniform, kept in shared memory between positions (the arithmetic needs the
+// registers; every lane stores the same values).
+struct WarpSampler {
+  unsigned long long r;
+  long long cursor, wc, last, wc0, iters;
+  unsigned long long r1_pre;
+  int len, sp, status, done;
+  int have_pre;
+  float alpha_c;
+  unsigned n_pos, n_ctx, n_tgt;  // per launch (a launch is bounded to 4 M words per shard)
+};
+
 struct WarpLayout {
   int rowb, K, qcap;
-  size_t off_ring, off_sen, off_jobq, off_bar, total;
+  size_t off_ring, off_sen, off_jobq, off_samp, off_bar, total;
 };
-__host__ __device__ inline WarpLayout warp_layout(long long D, int K, int qcap) {
+// sen_smem: the shard's current sentence (4000 B) lives in shared memory; 0: in a global scratch buffer
+// (TrainParams::sen) — wide rows at 16 warps per SM leave no room for it.
+__host__ __device__ inline WarpLayout warp_layout(long long D, int K, int qcap, int sen_smem) {
   WarpLayout L;
   L.rowb = (int)(D * 4);
   L.K = K;
   L.qcap = qcap;
   size_t o = 0;
   L.off_ring = o; o += (size_t)K * L.rowb;
-  L.off_sen = o;  o += sizeof(int) * (size_t)kMaxS;  // the shard's current sentence (:394-413)
+  L.off_sen = o;  o += sen_smem ? sizeof(int) * (size_t)kMaxS : 0;  // the shard's current sentence (:394-413)
   L.off_jobq = o; o += sizeof(int) * (size_t)qcap;
+  o = (o + 7) & ~(size_t)7;
+  L.off_samp = o; o += sizeof(WarpSampler);
   o = (o + 7) & ~(size_t)7;
   L.off_bar = o;  o += 8 * (size_t)K;
   L.total = (o + 15) & ~(size_t)15;
@@ -135,18 +151,6 @@ __device__ __forceinline__ float grad_scalar_c(float f, int label, float alpha) 
   return __fmul_rn(__fsub_rn((float)label, ldc_exptab(idx)), alpha);
 }
 
-// Sampler state of a shard (warp-uniform unless noted).
-struct WarpSampler {
-  unsigned long long r;
-  long long cursor, wc, last, wc0, iters;
-  int len, sp, status, done;
-  bool have_pre;
-  unsigned long long r1_pre, rd_pre;  // rd_pre: per lane
-  int t_pre;                          // per lane
-  float alpha_c;
-  unsigned n_pos, n_ctx, n_tgt;       // per launch (a launch is bounded to 4 M words per shard)
-};
-
 // Explicit single position (L1 parity hook, w2b_apply_position): ids instead of draws.
 struct ApplyArgs {
   const int *ctx, *tg;
@@ -159,10 +163,20 @@ struct ApplyArgs {
 // or 0 when the launch is over for this shard (word budget, shard end, slice exhausted, max_iters).
 // Control flow and draw order of :379-460; see train_ring_kernel's sampler warp in round 1 for the prefetch of
 // the next position's unigram-table lookups.
-__device__ inline int warp_next_position(const TrainParams &p, const ShardState &sh, WarpSampler &S, int lane, int *sen,
-                                         int *jobq, int qmask, unsigned qtail, const unsigned long long JA1,
-                                         const unsigned long long JC1, int &cw_out, int &nt_out, float &alpha_out) {
+__device__ inline int warp_next_position(const TrainParams &p, const ShardState &sh, WarpSampler &Ssm, int lane, int *sen,
+                                         int *jobq, int qmask, unsigned qtail, int &t_pre, int &cw_out, int &nt_out,
+                                         float &alpha_out) {
   const int W = p.window, neg = p.negative;
+  const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
+  // every lane works on its own (identical) copy; lane 0 writes it back on the way out.  Updating the shared copy
+  // in place would be a race: lanes of a warp are not guaranteed to take the read-modify-writes in lockstep.
+  WarpSampler S = Ssm;
+  auto leave = [&](int rc) {
+    __syncwarp();
+    if (lane == 0) Ssm = S;
+    __syncwarp();
+    return rc;
+  };
   const int negl = neg < 32 ? neg : 32;
   const unsigned long long JAn = c_JA[neg], JCn = c_JC[neg];
   for (;;) {
@@ -178,15 +192,15 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
       S.last = S.wc;
     }
     if (S.len == 0) {
-      if (p.word_budget > 0 && S.wc - S.wc0 >= p.word_budget) return 0;
+      if (p.word_budget > 0 && S.wc - S.wc0 >= p.word_budget) return leave(0);
       unsigned long long r2 = S.r;
       long long c2 = S.cursor, w2 = S.wc;
       int l2 = 0;
       S.status = build_sentence(p, sh, lane, sen, r2, c2, w2, l2);
       __syncwarp();
-      if (S.status == 2) return 0;  // slice exhausted mid-sentence: nothing committed
+      if (S.status == 2) return leave(0);  // slice exhausted mid-sentence: nothing committed
       S.r = r2; S.cursor = c2; S.wc = w2; S.len = l2; S.sp = 0;
-      S.have_pre = false;
+      S.have_pre = 0;
       // the shared learning rate (:53) is re-read once per sentence: other shards move it every 10k words each
       S.alpha_c = *(volatile float *)p.alpha;
     }
@@ -194,20 +208,20 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
       if (lane == 0) atomicAdd(p.wca, (unsigned long long)(S.wc - S.last) * (unsigned long long)p.wca_scale);
       S.last = S.wc;
       S.done = 1;
-      return 0;
+      return leave(0);
     }
     ++S.iters;
     // ---- draws of this position (:428-460)
     unsigned long long r1, rd;
     int t = 0;
     if (S.have_pre) {
-      r1 = S.r1_pre; rd = S.rd_pre; t = S.t_pre;
+      r1 = S.r1_pre; rd = r1 * JA1 + JC1; t = t_pre;
     } else {
       r1 = lcg(S.r);
       rd = r1 * JA1 + JC1;
       if (lane < negl) t = p.table[(rd >> 16) % (unsigned long long)W2B_TABLE_SIZE];
     }
-    S.have_pre = false;
+    S.have_pre = 0;
     const int b = mod_small(r1, (unsigned)W);
     const int len = S.len, sp = S.sp;
     const int center = len ? sen[sp] : -1;
@@ -226,11 +240,12 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
     if (cw) {
       const unsigned long long r_after = r1 * JAn + JCn;
       if (sp + 1 < len) {  // next position of the sentence: its draws are already determined
-        S.r1_pre = lcg(r_after);
-        S.rd_pre = S.r1_pre * JA1 + JC1;
-        S.t_pre = 0;
-        if (lane < negl) S.t_pre = p.table[(S.rd_pre >> 16) % (unsigned long long)W2B_TABLE_SIZE];
-        S.have_pre = true;
+        const unsigned long long r1n = lcg(r_after);
+        const unsigned long long rdn = r1n * JA1 + JC1;
+        S.r1_pre = r1n;
+        t_pre = 0;
+        if (lane < negl) t_pre = p.table[(rdn >> 16) % (unsigned long long)W2B_TABLE_SIZE];
+        S.have_pre = 1;
       }
       const unsigned tq = qtail + cw;
       if (lane == 0) jobq[tq & qmask] = center | kJobTarget;
@@ -279,13 +294,13 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
     }
     if (p.max_iters >= 0 && S.iters >= p.max_iters) {
       if (cw) { S.n_pos += 1; S.n_ctx += cw; S.n_tgt += nt; }
-      return 0;
+      return leave(0);
     }
     if (cw == 0) continue;  // single-word or empty sentence: one window draw, nothing trained
     S.n_pos += 1; S.n_ctx += cw; S.n_tgt += nt;
     if (!p.train) continue;  // draws only
     cw_out = cw; nt_out = nt; alpha_out = S.alpha_c;
-    return 1;
+    return leave(1);
   }
 }
 
@@ -308,10 +323,11 @@ __device__ __forceinline__ void fence_generic_to_async_global() {
 // RG = 1: the scatter-adds leave through the load/store unit (red.global.add.v4.f32 from registers) instead of the
 // bulk-copy engine (row written back to its slot, one cp.reduce.async.bulk): the engine then only carries the loads.
 template <int BM, int NJ, int MINB, int RG = 0>
-__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap, ApplyArgs ap) {
+__global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap_sen, ApplyArgs ap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
-  const WarpLayout L = warp_layout(p.D, K, qcap);
+  const int qcap = qcap_sen & 0x7fffffff, sen_smem = (qcap_sen >> 31) & 1;  // top bit: sentence in shared memory
+  const WarpLayout L = warp_layout(p.D, K, qcap, sen_smem);
   const unsigned s_base = smem_u32(smem);
   const unsigned ring = s_base + (unsigned)L.off_ring;
   const unsigned bars = s_base + (unsigned)L.off_bar;
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   const int shard = p.shard_base + blockIdx.x;
   ShardState *shp = p.shards + shard;
   if (!ap.ctx && shp->done) return;
-  int *sen = reinterpret_cast<int *>(smem + L.off_sen);
+  int *sen = sen_smem ? reinterpret_cast<int *>(smem + L.off_sen) : p.sen + (size_t)shard * kMaxS;
 
   if (lane == 0) {
     for (int i = 0; i < K; ++i) mbar_init(reinterpret_cast<unsigned long long *>(smem + L.off_bar) + i, 1);
@@ -344,12 +360,13 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
 #define W2B_COFF(j) ((j) < NJ - 1 ? lane16 + (unsigned)(j) * 512u : coff_last)
 
   const ShardState &sh = *shp;
-  WarpSampler S;
+  WarpSampler &S = *reinterpret_cast<WarpSampler *>(smem + L.off_samp);
   S.r = sh.rng; S.cursor = sh.cursor; S.wc = sh.word_count; S.last = sh.last_word_count; S.wc0 = S.wc;
-  S.iters = 0; S.len = 0; S.sp = 0; S.status = 0; S.done = 0; S.have_pre = false;
-  S.r1_pre = 0; S.rd_pre = 0; S.t_pre = 0; S.n_pos = S.n_ctx = S.n_tgt = 0;
+  S.iters = 0; S.len = 0; S.sp = 0; S.status = 0; S.done = 0; S.have_pre = 0;
+  S.r1_pre = 0; S.n_pos = S.n_ctx = S.n_tgt = 0;
   S.alpha_c = *(volatile float *)p.alpha;
-  const unsigned long long JA1 = c_JA[lane + 1], JC1 = c_JC[lane + 1];  // lane's own jump constants
+  int t_pre = 0;  // per lane: the next position's unigram-table lookup, in flight while this one is trained
+  __syncwarp();
 
   // ---- job bookkeeping (all warp-uniform).  Job j lives in slot j mod K; the issue side and the arithmetic each
   // keep their slot's shared-memory address and mbarrier incrementally.  Every job arms its slot's mbarrier exactly
@@ -432,7 +449,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     n_cw = ap.cw; n_nt = ap.nt; n_alpha = S.alpha_c;
     have_next = ap.cw > 0;
   } else {
-    have_next = warp_next_position(p, sh, S, lane, sen, jobq, qmask, q_tail, JA1, JC1, n_cw, n_nt, n_alpha);
+    have_next = warp_next_position(p, sh, S, lane, sen, jobq, qmask, q_tail, t_pre, n_cw, n_nt, n_alpha);
   }
   if (have_next) q_tail += (unsigned)(n_cw + n_nt + 1);
 
@@ -443,7 +460,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     q_limit = q0 + (unsigned)(cw + nt + 1);
     pump();
     // sample one position ahead: its jobs extend the queue (and, without serial, what the ring may prefetch)
-    have_next = ap.ctx ? 0 : warp_next_position(p, sh, S, lane, sen, jobq, qmask, q_tail, JA1, JC1, n_cw, n_nt, n_alpha);
+    have_next = ap.ctx ? 0 : warp_next_position(p, sh, S, lane, sen, jobq, qmask, q_tail, t_pre, n_cw, n_nt, n_alpha);
     if (have_next) q_tail += (unsigned)(n_cw + n_nt + 1);
     if (!p.serial) { q_limit = q_tail; pump(); }
 
