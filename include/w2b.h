@@ -204,13 +204,16 @@ int w2b_quantize(w2b_ctx *ctx, const float *in, float *out, int64_t n, int bitle
 
 /* Analogy evaluator, replaces src/compute-accuracy.c:63-189: same inputs
  * (word2vec-binary vector file, optional re-quantisation, vocabulary threshold, question stream),
- * same report text; all questions are scored on the GPU as one Q x V x D contraction with a fused
- * arg-max.  questions_file NULL = stdin.  report may be NULL. */
+ * same report text; all questions are scored on the GPU: one Q x V x D TF32 tensor-core contraction
+ * (tcgen05 + TMA) as a filter with a proven error bound, then an fp32 re-score of the surviving candidates in the
+ * reference's operation order, so the arg-max (ties included) is the reference's.  questions_file NULL = stdin.  report may be NULL. */
 typedef struct {
   int64_t questions_total, questions_seen, correct;
   int64_t semantic_correct, semantic_seen, syntactic_correct, syntactic_seen;
   int64_t vocab, size;
   float gpu_ms; /* normalise + query build + scoring kernels, CUDA events */
+  int64_t candidates; /* (question, word) pairs the tensor-core filter let through (within 2 eps of the running best) */
+  int64_t rescored;   /* ... of which still within 2 eps of the final best: scored again in fp32, reference order */
 } w2b_accuracy;
 int w2b_compute_accuracy(const char *vectors_file, int bitlevel, int64_t threshold, const char *questions_file,
                          int device, w2b_accuracy *acc, char *report, int64_t report_cap);

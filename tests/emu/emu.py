@@ -46,7 +46,7 @@ class EmuError(RuntimeError):
 
 def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, shards, serial=0, alpha=0.05,
                      sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                     slots=0, red=0, fault=0):
+                     slots=0, fault=0):
     """One pass of every shard (one 32-thread CTA after another) through the emulated warp-per-shard kernel
     (csrc/w2b_warp.cuh).  u, v are updated in place.  Returns a dict of per-shard statistics; `state` carries
     (alpha, word_count_actual) across epochs."""
@@ -67,7 +67,7 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
     p = _lib.ptr
     r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
                alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
-               opt=red, lpr=32 if plan["sentence_in_smem"] else 0, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32,
+               opt=0, lpr=32 if plan["sentence_in_smem"] else 0, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32,
                serial=serial,
                u=p(u), v=p(v), table=p(table), keep=p(keep), exptab=p(exptab), tokens=p(tokens), n_tokens=len(tokens),
                shard_start=p(start), shard_first=p(first), alpha=p(a), wca=p(wca), word_budget=0, max_iters=max_iters,

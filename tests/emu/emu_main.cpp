@@ -322,23 +322,23 @@ bool run_block(int nthreads, void (*entry)()) {
 w2b::TrainParams g_p;
 int g_nu, g_nv, g_sen_smem = 1;
 typedef void (*entry_fn)();
-template <int BM, int NJ, int RG>
+template <int BM, int NJ>
 void warp_entry() {
   w2b::ApplyArgs none;
   memset(&none, 0, sizeof none);
-  w2b::train_warp_kernel<BM, NJ, 12, RG>(g_p, g_nv, g_nu | (g_sen_smem << 31), none);
+  w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu | (g_sen_smem << 31), none);
 }
-template <int BM, int RG>
+template <int BM>
 entry_fn warp_by_nj(int nj) {
   switch (nj) {
-    case 1: return warp_entry<BM, 1, RG>;
-    case 2: return warp_entry<BM, 2, RG>;
-    case 3: return warp_entry<BM, 3, RG>;
-    case 4: return warp_entry<BM, 4, RG>;
-    case 5: return warp_entry<BM, 5, RG>;
-    case 6: return warp_entry<BM, 6, RG>;
-    case 7: return warp_entry<BM, 7, RG>;
-    case 8: return warp_entry<BM, 8, RG>;
+    case 1: return warp_entry<BM, 1>;
+    case 2: return warp_entry<BM, 2>;
+    case 3: return warp_entry<BM, 3>;
+    case 4: return warp_entry<BM, 4>;
+    case 5: return warp_entry<BM, 5>;
+    case 6: return warp_entry<BM, 6>;
+    case 7: return warp_entry<BM, 7>;
+    case 8: return warp_entry<BM, 8>;
   }
   return nullptr;
 }
@@ -442,11 +442,11 @@ int emu_run_warp(const EmuRun *r) {
   if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
   const int nj = ((int)(r->D / 4) + 31) / 32;
   entry_fn fn = nullptr;
-  switch (r->bitlevel) {  // r->opt: scatter-adds through red.global (RG = 1) instead of the bulk-copy engine
-    case 0: fn = r->opt ? warp_by_nj<0, 1>(nj) : warp_by_nj<0, 0>(nj); break;
-    case 1: fn = r->opt ? warp_by_nj<1, 1>(nj) : warp_by_nj<1, 0>(nj); break;
-    case 2: fn = r->opt ? warp_by_nj<2, 1>(nj) : warp_by_nj<2, 0>(nj); break;
-    default: fn = r->opt ? warp_by_nj<9, 1>(nj) : warp_by_nj<9, 0>(nj); break;
+  switch (r->bitlevel) {
+    case 0: fn = warp_by_nj<0>(nj); break;
+    case 1: fn = warp_by_nj<1>(nj); break;
+    case 2: fn = warp_by_nj<2>(nj); break;
+    default: fn = warp_by_nj<9>(nj); break;
   }
   if (!fn) { fail("no emulated instantiation for this shape"); return 1; }
   std::vector<int> sen((size_t)kMaxS * (r->num_shards + 1));

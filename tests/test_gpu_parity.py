@@ -532,6 +532,52 @@ def test_gpu_analogy_evaluator_matches_reference(tmp_path, bits, threshold):
         assert abs(nums(total_w)[0] - nums(total_g)[0]) <= 2.0, (total_w, total_g)
 
 
+@pytest.mark.parametrize("D,bits,vocab", [(200, 1, 30000), (72, 0, 9000), (800, 2, 6000), (130, 0, 700)])
+def test_evaluator_tensor_core_filter_is_exact(tmp_path, D, bits, vocab):
+    """The evaluator scores on the tensor cores (TF32 tcgen05.mma fed by TMA) only to FILTER: words whose approximate
+    score lies within the proven error bound of the best are re-scored in fp32 in the reference's operation order.
+    So its report must equal, character for character, the report of the same pipeline with every score computed
+    in fp32 on the SIMT cores (W2B_EVAL_SIMT=1) — on many 256-word tiles, row pitches that need padding (D = 72,
+    130), exact-tie-heavy 1-/2-bit vectors, and a vocabulary that is not a multiple of the tile."""
+    import subprocess
+    rng = np.random.default_rng(D + bits)
+    pairs = 1500
+    off = rng.normal(size=D).astype(np.float32) * 1.5
+    a = rng.normal(size=(pairs, D)).astype(np.float32)
+    b = a + off + 1.1 * rng.normal(size=(pairs, D)).astype(np.float32)
+    noise = rng.normal(size=(vocab - 2 * pairs - 1, D)).astype(np.float32) if vocab > 2 * pairs + 1 else np.zeros((0, D), np.float32)
+    vec = np.concatenate([np.zeros((1, D), np.float32) + 0.01, a, b, noise])[:vocab]
+    words = (["</s>"] + ["alpha%d" % i for i in range(pairs)] + ["beta%d" % i for i in range(pairs)] +
+             ["noise%d" % i for i in range(len(noise))])[:vocab]
+    if bits:
+        vec = po.quantize(vec * 0.3, bits)
+    vf = str(tmp_path / "vec.bin")
+    with open(vf, "wb") as f:
+        f.write(b"%d %d\n" % (len(words), D))
+        for w, row in zip(words, vec):
+            f.write(w.encode() + b" " + row.astype(np.float32).tobytes() + b"\n")
+    usable = min(pairs, (vocab - 1) // 2)
+    qf = str(tmp_path / "questions.txt")
+    with open(qf, "w") as f:
+        for sec in range(6):
+            f.write(": section-%d\n" % sec)
+            for _ in range(500):
+                i, j = rng.integers(0, usable, 2)
+                f.write("alpha%d beta%d alpha%d beta%d\n" % (i, i, j, j))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "word2bits_b200", "compute_accuracy")
+    out = {}
+    for simt in ("0", "1"):
+        out[simt] = subprocess.run([cli, vf, str(bits), "0"], stdin=open(qf), capture_output=True, text=True,
+                                   env=dict(os.environ, W2B_EVAL_SIMT=simt), timeout=300).stdout
+    assert "Questions seen / total: 3000 3000" in out["0"]
+    assert out["0"] == out["1"]
+    _, acc = w2b.compute_accuracy(vf, qf, bitlevel=bits)
+    print("evaluator D=%d bits=%d vocab=%d: %.2f ms, filter let %.1f candidates per question through, %.1f re-scored in fp32"
+          % (D, bits, vocab, acc["gpu_ms"], acc["candidates"] / 3000.0, acc["rescored"] / 3000.0))
+    assert 3000 <= acc["rescored"] <= acc["candidates"] < 3000 * vocab // 10
+
+
 def test_full_size_shape_properties(tmp_path):
     """BASELINE configs[1] shape (400k-word Zipf vocabulary, D=800, window 10, negative 24, 148 shards),
     checked through size-independent properties: vocabulary/table/InitNet equal the oracle's on the

@@ -415,10 +415,10 @@ def test_default_geometry_is_the_measured_one():
     benchmarked configuration silently."""
     import word2bits_b200 as w2b
     want = {  # (D, window, negative, bitlevel): (slots, queue_entries, warps_per_sm, smem_bytes)
-        (800, 10, 24, 1): (4, 128, 12, 17344),   # BASELINE configs[1]
-        (400, 10, 12, 2): (5, 128, 16, 12560),   # configs[2]
-        (400, 10, 24, 0): (5, 128, 16, 12560),   # configs[3]
-        (200, 8, 24, 1): (7, 128, 20, 10176),    # configs[0] shape
+        (800, 10, 24, 1): (4, 128, 12, 17440),   # BASELINE configs[1]
+        (400, 10, 12, 2): (5, 128, 16, 12656),   # configs[2]
+        (400, 10, 24, 0): (5, 128, 16, 12656),   # configs[3]
+        (200, 8, 24, 1): (7, 128, 20, 10272),    # configs[0] shape
     }
     for (D, W, neg, b), geo in want.items():
         p = w2b.warp_plan(size=D, window=W, negative=neg, bitlevel=b, vocab_size=400001)

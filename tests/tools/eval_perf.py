@@ -33,8 +33,17 @@ t0 = time.time()
 rep, acc = w2b.compute_accuracy(vf, qf, bitlevel=1)
 wall = time.time() - t0
 flops = 2.0 * acc["questions_seen"] * acc["vocab"] * acc["size"]
-print("GPU evaluator: %d questions x V=%d x D=%d: kernels %.1f ms (%.1f TFLOP/s fp32), wall %.1f s (file read + H2D included)"
-      % (acc["questions_seen"], acc["vocab"], acc["size"], acc["gpu_ms"], flops / acc["gpu_ms"] / 1e9, wall), flush=True)
+print("GPU evaluator: %d questions x V=%d x D=%d: kernels %.1f ms (%.1f TFLOP/s of contraction), wall %.1f s (file read + H2D included); "
+      "tensor-core filter let %.1f candidates per question through, %.1f re-scored in fp32"
+      % (acc["questions_seen"], acc["vocab"], acc["size"], acc["gpu_ms"], flops / acc["gpu_ms"] / 1e9, wall,
+         acc["candidates"] / max(acc["questions_seen"], 1), acc["rescored"] / max(acc["questions_seen"], 1)), flush=True)
+os.environ["W2B_EVAL_SIMT"] = "1"
+rep2, acc2 = w2b.compute_accuracy(vf, qf, bitlevel=1)
+del os.environ["W2B_EVAL_SIMT"]
+print("same with every score in fp32 on the SIMT cores (W2B_EVAL_SIMT=1): kernels %.1f ms; reports identical: %s"
+      % (acc2["gpu_ms"], rep == rep2), flush=True)
+if len(sys.argv) > 4 and sys.argv[4] == "eval-only":
+    sys.exit(0)
 refbin = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle", "_ref", "compute_accuracy")
 if os.path.exists(refbin):
     qs = os.path.join(tmp, "qs.txt")

@@ -43,7 +43,7 @@ class StepStats(C.Structure):
 class Accuracy(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("questions_total", "questions_seen", "correct", "semantic_correct",
                                          "semantic_seen", "syntactic_correct", "syntactic_seen", "vocab", "size")] + \
-               [("gpu_ms", C.c_float)]
+               [("gpu_ms", C.c_float), ("candidates", C.c_int64), ("rescored", C.c_int64)]
 
 
 class WarpPlan(C.Structure):

@@ -209,45 +209,30 @@ static apply_fn pick_apply(const w2b_ctx *c) {
 // ---- warp-per-shard kernel (csrc/w2b_warp.cuh)
 typedef void (*warp_fn)(TrainParams, int, int, ApplyArgs);
 // warps (= 1-warp CTAs) per SM the register allocation is sized for; multiples of 4 because the register file is
-// split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96
-static bool warp_dense() {  // A/B hook: 16 / 20 / 24 instead of 12 / 16 / 20 warps per SM (128 / 96 / 80 registers per thread)
-  static const bool on = getenv("W2B_WARP_DENSE") && atoi(getenv("W2B_WARP_DENSE")) != 0;
-  return on;
-}
-static int warp_minb_of(int nj) {
-  if (warp_dense()) return nj >= 5 ? 16 : (nj >= 3 ? 20 : 24);
-  return nj >= 5 ? 12 : (nj >= 3 ? 16 : 20);
-}
-template <int BM, int RG>
+// split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96, 24 -> 80.
+// Measured (profiles/r02_warp_sweep_more_warps.md): one step denser is 2-11 % slower, except for the narrowest rows.
+static int warp_minb_of(int nj) { return nj >= 5 ? 12 : (nj >= 3 ? 16 : (nj == 2 ? 20 : 24)); }
+template <int BM>
 static warp_fn warp_by_nj(int nj) {
-  const bool d = warp_dense();
   switch (nj) {
-    case 1: return d ? train_warp_kernel<BM, 1, 24, RG> : train_warp_kernel<BM, 1, 20, RG>;
-    case 2: return d ? train_warp_kernel<BM, 2, 24, RG> : train_warp_kernel<BM, 2, 20, RG>;
-    case 3: return d ? train_warp_kernel<BM, 3, 20, RG> : train_warp_kernel<BM, 3, 16, RG>;
-    case 4: return d ? train_warp_kernel<BM, 4, 20, RG> : train_warp_kernel<BM, 4, 16, RG>;
-    case 5: return d ? train_warp_kernel<BM, 5, 16, RG> : train_warp_kernel<BM, 5, 12, RG>;
-    case 6: return d ? train_warp_kernel<BM, 6, 16, RG> : train_warp_kernel<BM, 6, 12, RG>;
-    case 7: return d ? train_warp_kernel<BM, 7, 16, RG> : train_warp_kernel<BM, 7, 12, RG>;
-    case 8: return d ? train_warp_kernel<BM, 8, 16, RG> : train_warp_kernel<BM, 8, 12, RG>;
+    case 1: return train_warp_kernel<BM, 1, 24>;
+    case 2: return train_warp_kernel<BM, 2, 20>;
+    case 3: return train_warp_kernel<BM, 3, 16>;
+    case 4: return train_warp_kernel<BM, 4, 16>;
+    case 5: return train_warp_kernel<BM, 5, 12>;
+    case 6: return train_warp_kernel<BM, 6, 12>;
+    case 7: return train_warp_kernel<BM, 7, 12>;
+    case 8: return train_warp_kernel<BM, 8, 12>;
   }
   return nullptr;
 }
 static warp_fn pick_warp(const w2b_ctx *c) {
   const int nj = (c->ncol + 31) / 32;
-  static const bool rg = getenv("W2B_WARP_RED") && atoi(getenv("W2B_WARP_RED")) != 0;  // A/B hook (scatter path)
-  if (rg)
-    switch (bm_of(c->cfg.bitlevel)) {
-      case 0: return warp_by_nj<0, 1>(nj);
-      case 1: return warp_by_nj<1, 1>(nj);
-      case 2: return warp_by_nj<2, 1>(nj);
-      default: return warp_by_nj<9, 1>(nj);
-    }
   switch (bm_of(c->cfg.bitlevel)) {
-    case 0: return warp_by_nj<0, 0>(nj);
-    case 1: return warp_by_nj<1, 0>(nj);
-    case 2: return warp_by_nj<2, 0>(nj);
-    default: return warp_by_nj<9, 0>(nj);
+    case 0: return warp_by_nj<0>(nj);
+    case 1: return warp_by_nj<1>(nj);
+    case 2: return warp_by_nj<2>(nj);
+    default: return warp_by_nj<9>(nj);
   }
 }
 // Geometry: as many ring slots as the warp's share of the SM's 228 KB holds (each resident CTA also costs 1 KB of

@@ -4,8 +4,9 @@
 // (:155) and the arg-max cosine over the whole vocabulary except the three query words
 // (:158-177), first index winning ties and only strictly positive scores counting (bestd
 // starts at 0, :150).  Here all questions are scored together as one Q x V x D contraction
-// (fp32 SIMT tiles — arg-max parity needs fp32, so no tensor-core path yet) with a fused
-// arg-max epilogue; the report text is the reference's, line for line.
+// on the tensor cores (w2b_eval_tc.cuh: TF32 tcgen05.mma fed by TMA, accumulators in TMEM) used as a FILTER
+// with a proven error bound, followed by an fp32 re-score of the surviving candidates in the reference's
+// operation order — so the arg-max is the reference's arg-max; the report text is the reference's, line for line.
 #include <cuda_runtime.h>
 #include <ctype.h>
 #include <math.h>
@@ -20,6 +21,7 @@
 #include "w2b.h"
 #include "w2b_internal.h"
 #include "w2b_quant.cuh"
+#include "w2b_eval_tc.cuh"
 
 using namespace w2b;
 
@@ -51,14 +53,14 @@ struct FileCloser {
 };
 
 // quantize (:102) + L2 normalise (:103-106): one warp per row.
-__global__ void eval_normalize_kernel(float *M, long long words, long long D, int bits) {
+__global__ void eval_normalize_kernel(float *M, long long words, long long D, long long Dp, int bits) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= words) return;
   QParams qp;
   qp.bits = bits;
   qp.seg = (bits >= 4) ? exp2f((float)(bits - 1)) : 1.f;
-  float *r = M + row * D;
+  float *r = M + row * Dp;  // rows are padded to Dp floats (zeros) for the tensor-core pass
   float s = 0.f;
   for (long long a = lane; a < D; a += 32) {
     const float q = quant<9>(r[a], qp);
@@ -71,20 +73,58 @@ __global__ void eval_normalize_kernel(float *M, long long words, long long D, in
 }
 
 // vec = (M[b2] - M[b1]) + M[b3] (:155), rows padded to a multiple of 64 with zeros.
-__global__ void eval_query_kernel(const float *M, const int *q3, float *Q, long long nq, long long D) {
+__global__ void eval_query_kernel(const float *M, const int *q3, float *Q, long long nq, long long D, long long Dp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq * D) return;
   const long long q = i / D, a = i % D;
-  const int b1 = q3[q * 3], b2 = q3[q * 3 + 1], b3 = q3[q * 3 + 2];
-  Q[i] = __fadd_rn(__fsub_rn(M[b2 * D + a], M[b1 * D + a]), M[b3 * D + a]);
+  const long long b1 = q3[q * 3], b2 = q3[q * 3 + 1], b3 = q3[q * 3 + 2];
+  Q[q * Dp + a] = __fadd_rn(__fsub_rn(M[b2 * Dp + a], M[b1 * Dp + a]), M[b3 * Dp + a]);
 }
 
-// scores = Q (nq x D) . M^T (D x words), 64 x 64 tile per CTA, 4 x 4 per thread, fused arg-max:
+// eps of the tensor-core filter per question: TF32 keeps 10 explicit mantissa bits of each operand (the rest is
+// dropped), so each product is off by at most 2^-9 relative; with Cauchy-Schwarz |approx - exact| <= 2^-9 |vec| |m|,
+// |m| = 1 after normalisation; fp32 accumulation order (tensor core vs sequential) adds < 1e-4 |vec|.  5 % slack.
+__global__ void eval_qeps_kernel(const float *Q, float *qeps, long long nq, long long Dp) {
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  float n2 = 0.f;
+  for (long long a = lane; a < Dp; a += 32) {
+    const float x = Q[q * Dp + a];
+    n2 = fmaf(x, x, n2);
+  }
+  for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
+  if (lane == 0) qeps[q] = (0.001953125f + 1e-4f) * 1.05f * sqrtf(n2);
+}
+
+// Pass 2: exact scores of the surviving candidates.  Thread per candidate: one whose approximate score is still
+// within 2*eps of the question's FINAL best is scored in fp32 exactly like the reference loop (:160-163) — dist = sum
+// over a ascending of vec[a] * M[a + c*size], one fused multiply-add per term, the order the fp32 SIMT scorer uses —
+// and competes for best[q] with the reference's rule: strictly positive, larger score wins, smaller index on ties.
+__global__ void eval_rescore_kernel(const float *Q, const float *M, const tc::Candidate *cand, unsigned long long n_cand,
+                                    const float *qeps, const unsigned *gmax, unsigned long long *best,
+                                    unsigned long long *n_rescored, int D, long long Dp) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const tc::Candidate cd = cand[i];
+  const unsigned g = gmax[cd.q];
+  if (!(cd.s >= __uint_as_float(g & 0x7fffffffu) - 2.f * qeps[cd.q])) return;
+  const float *v = Q + (size_t)cd.q * Dp, *m = M + (size_t)cd.c * Dp;
+  float acc = 0.f;
+  for (int a = 0; a < D; ++a) acc = fmaf(v[a], m[a], acc);
+  atomicAdd(n_rescored, 1ull);
+  if (acc > 0.f)
+    atomicMax(best + cd.q, ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cd.c));
+}
+
+// Parity hook (W2B_EVAL_SIMT=1) and fall-back for pathological inputs: every score in fp32 on the SIMT cores, same
+// operation order per (question, word) as the re-score pass — tests hold the tensor-core pipeline to an identical
+// report against it.  scores = Q (nq x D) . M^T (D x words), 64 x 64 tile per CTA, 4 x 4 per thread, fused arg-max:
 // best[q] = max over c not in {b1,b2,b3} with score > 0 of (score, smallest c).
 constexpr int TM = 64, TN = 64, TK = 16;
 __global__ void __launch_bounds__(256) eval_score_kernel(const float *Q, const float *M, const int *q3,
                                                          unsigned long long *best, long long nq, long long words,
-                                                         long long D) {
+                                                         long long D, long long Dp) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -102,8 +142,8 @@ __global__ void __launch_bounds__(256) eval_score_kernel(const float *Q, const f
       const int e = tid + l * 256;
       const int r = e >> 4, k = e & 15;
       const long long qa = q0 + r, ca = c0 + r, ka = k0 + k;
-      As[k][r] = (qa < nq && ka < D) ? Q[qa * D + ka] : 0.f;
-      Bs[k][r] = (ca < words && ka < D) ? M[ca * D + ka] : 0.f;
+      As[k][r] = (qa < nq && ka < D) ? Q[qa * Dp + ka] : 0.f;
+      Bs[k][r] = (ca < words && ka < D) ? M[ca * Dp + ka] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -261,7 +301,7 @@ static int compute_accuracy_impl(const char *vectors_file, int bitlevel, int64_t
   }
   const long long nq = (long long)q3.size() / 3;
 
-  // ---- GPU: normalise, build queries, score + arg-max
+  // ---- GPU: normalise, build queries, tensor-core candidate pass, exact re-score of the candidate tiles
   std::vector<unsigned long long> best(nq > 0 ? nq : 1, 0);
   float ms = 0.f;
   if (nq > 0) {
@@ -271,29 +311,76 @@ static int compute_accuracy_impl(const char *vectors_file, int bitlevel, int64_t
       return W2B_ECUDA;
     }
     CKE(cudaSetDevice(device));
-    DevBuf bM, bQ, bq3, bbest;
-    CKE(bM.alloc(M.size() * sizeof(float)));
-    CKE(bQ.alloc((size_t)nq * size * sizeof(float)));
+    const long long Dp = (size + tc::BK - 1) / tc::BK * tc::BK;  // row pitch: whole 128-byte k-blocks, zero padded
+    const int ntiles = (int)((words + tc::BN - 1) / tc::BN);
+    if (acc) acc->candidates = acc->rescored = 0;
+    const char *dbg = getenv("W2B_EVAL_SIMT");  // parity hook: score everything with the fp32 SIMT kernel instead
+    const bool simt = dbg && atoi(dbg) != 0;
+    DevBuf bM, bQ, bq3, bbest, bgmax, bcand, bqeps, bcnt;
+    const unsigned long long cand_cap = (unsigned long long)nq * 1024ull;  // measured: tens to hundreds per question
+    CKE(bM.alloc((size_t)words * Dp * sizeof(float)));
+    CKE(bQ.alloc((size_t)nq * Dp * sizeof(float)));
     CKE(bq3.alloc(q3.size() * sizeof(int)));
     CKE(bbest.alloc(nq * sizeof(unsigned long long)));
+    CKE(bgmax.alloc(nq * sizeof(unsigned)));
+    CKE(bqeps.alloc(nq * sizeof(float)));
+    CKE(bcnt.alloc(2 * sizeof(unsigned long long)));
+    if (!simt) CKE(bcand.alloc(cand_cap * sizeof(tc::Candidate)));
     float *dM = bM.as<float>(), *dQ = bQ.as<float>();
     int *dq3 = bq3.as<int>();
-    unsigned long long *dbest = bbest.as<unsigned long long>();
-    CKE(cudaMemcpy(dM, M.data(), M.size() * sizeof(float), cudaMemcpyHostToDevice));
+    unsigned long long *dbest = bbest.as<unsigned long long>(), *dcnt = bcnt.as<unsigned long long>();
+    CKE(cudaMemset(dM, 0, (size_t)words * Dp * sizeof(float)));
+    CKE(cudaMemset(dQ, 0, (size_t)nq * Dp * sizeof(float)));
+    CKE(cudaMemcpy2D(dM, Dp * sizeof(float), M.data(), size * sizeof(float), size * sizeof(float), words, cudaMemcpyHostToDevice));
     CKE(cudaMemcpy(dq3, q3.data(), q3.size() * sizeof(int), cudaMemcpyHostToDevice));
     CKE(cudaMemset(dbest, 0, nq * sizeof(unsigned long long)));
+    CKE(cudaMemset(bgmax.p, 0, nq * sizeof(unsigned)));
+    CKE(cudaMemset(dcnt, 0, 2 * sizeof(unsigned long long)));
     DevEvent e0, e1;
     CKE(cudaEventCreate(&e0.e));
     CKE(cudaEventCreate(&e1.e));
     CKE(cudaEventRecord(e0.e));
-    eval_normalize_kernel<<<(unsigned)((words + 7) / 8), 256>>>(dM, words, size, bitlevel);
-    eval_query_kernel<<<(unsigned)((nq * size + 255) / 256), 256>>>(dM, dq3, dQ, nq, size);
-    dim3 grid((unsigned)((words + TN - 1) / TN), (unsigned)((nq + TM - 1) / TM));
-    eval_score_kernel<<<grid, 256>>>(dQ, dM, dq3, dbest, nq, words, size);
+    eval_normalize_kernel<<<(unsigned)((words + 7) / 8), 256>>>(dM, words, size, Dp, bitlevel);
+    eval_query_kernel<<<(unsigned)((nq * size + 255) / 256), 256>>>(dM, dq3, dQ, nq, size, Dp);
+    bool need_simt = simt;
+    unsigned long long h_cnt[2] = {0, 0};
+    if (!simt) {
+      CUtensorMap mapQ, mapM;
+      if (!tc::make_map(&mapQ, dQ, nq, Dp, tc::BM) || !tc::make_map(&mapM, dM, words, Dp, tc::BN)) {
+        w2b_set_error("cuTensorMapEncodeTiled failed (driver too old for TMA?)");
+        return W2B_ECUDA;
+      }
+      eval_qeps_kernel<<<(unsigned)((nq + 7) / 8), 256>>>(dQ, bqeps.as<float>(), nq, Dp);
+      CKE(cudaFuncSetAttribute(tc::eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      // x = question tile (fastest): the CTAs that share a 256-word tile of M run together, M streams from HBM once
+      dim3 grid((unsigned)((nq + tc::BM - 1) / tc::BM), (unsigned)ntiles);
+      tc::eval_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES>>>(mapQ, mapM, dq3, bqeps.as<float>(), bgmax.as<unsigned>(),
+                                                               bcand.as<tc::Candidate>(), dcnt, cand_cap, (int)nq, (int)words,
+                                                               (int)Dp);
+      CKE(cudaGetLastError());
+      CKE(cudaMemcpy(h_cnt, dcnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      if (h_cnt[0] > cand_cap) {
+        need_simt = true;  // pathological input (e.g. all vectors equal): score everything in fp32 instead
+      } else if (h_cnt[0]) {
+        eval_rescore_kernel<<<(unsigned)((h_cnt[0] + 127) / 128), 128>>>(dQ, dM, bcand.as<tc::Candidate>(), h_cnt[0],
+                                                                       bqeps.as<float>(), bgmax.as<unsigned>(), dbest, dcnt + 1,
+                                                                       (int)size, Dp);
+      }
+    }
+    if (need_simt) {
+      CKE(cudaMemset(dbest, 0, nq * sizeof(unsigned long long)));
+      dim3 grid((unsigned)((words + TN - 1) / TN), (unsigned)((nq + TM - 1) / TM));
+      eval_score_kernel<<<grid, 256>>>(dQ, dM, dq3, dbest, nq, words, size, Dp);
+    }
     CKE(cudaGetLastError());
     CKE(cudaEventRecord(e1.e));
     CKE(cudaMemcpy(best.data(), dbest, nq * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CKE(cudaEventElapsedTime(&ms, e0.e, e1.e));
+    if (acc && !simt) {
+      CKE(cudaMemcpy(h_cnt, dcnt, sizeof h_cnt, cudaMemcpyDeviceToHost));
+      acc->candidates = (int64_t)h_cnt[0];
+      acc->rescored = (int64_t)h_cnt[1];
+    }
   }
 
   // ---- replay the control flow of :113-187 to produce the same report

@@ -306,23 +306,11 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
 
 // BM: compile-time bitlevel 0/1/2, 9 = run time.  NJ = float4 columns per lane = ceil(D / 128).  MINB = CTAs (warps)
 // per SM the register allocation is sized for.
-#ifdef W2B_EMULATE
-__device__ __forceinline__ void red_add_v4(float *dst, float4 v) { dst[0] += v.x; dst[1] += v.y; dst[2] += v.z; dst[3] += v.w; }
-__device__ __forceinline__ void fence_generic_to_async_global() {}
-#else
-__device__ __forceinline__ void red_add_v4(float *dst, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// every earlier red of this thread is performed, and ordered before later bulk copies (async proxy) from global
-__device__ __forceinline__ void fence_generic_to_async_global() {
-  __threadfence();
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-#endif
-
-// RG = 1: the scatter-adds leave through the load/store unit (red.global.add.v4.f32 from registers) instead of the
-// bulk-copy engine (row written back to its slot, one cp.reduce.async.bulk): the engine then only carries the loads.
-template <int BM, int NJ, int MINB, int RG = 0>
+// (Measured alternatives that did not pay on B200, profiles/r02_warp_sweep_*.md: scatter-adds through the load/store
+// unit — red.global.add.v4.f32 from registers — instead of the bulk-copy engine: same throughput, same memory-system
+// ceiling; 16 / 20 / 24 instead of 12 / 16 / 20 warps per SM: 2-11 % slower except for rows of <= 128 floats; 2 or 3
+// bulk-reduce groups left pending instead of 1: no change.)
+template <int BM, int NJ, int MINB>
 __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap_sen, ApplyArgs ap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
@@ -381,10 +369,9 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   unsigned c_row = ring, c_bar = bars;  // slot of the job being worked on
   unsigned c_par = 0;
   double loss = 0.0;     // per lane: reported loss of the targets this lane looked after
-  // a job may be issued once the job K before it has left its slot: with the bulk-reduce scatter that is known
-  // after the `wait_group.read 1` that follows the NEXT job (ahead = K - 2 loads in flight); with the red.global
-  // scatter (RG) a slot is free as soon as the warp has read it (ahead = K - 1)
-  const unsigned ahead = (unsigned)K - (RG ? 1u : 2u);
+  // a job may be issued once the job K before it has left its slot, which is known after the `wait_group.read 1`
+  // that follows the NEXT job: K - 2 loads in flight behind the row being worked on
+  const unsigned ahead = (unsigned)K - 2u;
 
   auto issue_one = [&]() {  // all lanes; lane 0 acts.  Precondition: q_issue < q_limit, slot free.
     const int e = jobq[q_issue & qmask];
@@ -406,19 +393,17 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   };
   // End of a job, after every lane is done with the slot (__syncwarp by the caller): lane 0 hands the slot's row to
   // the bulk-copy engine as an atomic-add scatter — to `dst` (target job), or to the position's n_dst context rows
-  // of u (staging job; none for a context job or with RG) — confirms the previous job's slot and refills it: one
-  // divergent region per job.
+  // of u (staging job; none for a context job) — confirms the previous job's slot and refills it: one divergent
+  // region per job.
   auto finish_job = [&](float *dst, int n_dst, unsigned q0) {
     ++q_cons;
     const bool can = q_issue < q_limit && q_issue <= q_cons + ahead;
     const int e = can ? jobq[q_issue & qmask] : -1;
     if (lane == 0) {
-      if (!RG) {
-        if (dst) bulk_reduce_add(dst, c_row, rowb);
-        else for (int k = 0; k < n_dst; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, c_row, rowb);
-        bulk_commit();
-        bulk_wait_read<1>();
-      }
+      if (dst) bulk_reduce_add(dst, c_row, rowb);
+      else for (int k = 0; k < n_dst; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, c_row, rowb);
+      bulk_commit();
+      bulk_wait_read<1>();
       if (can) {
         if (e >= 0) {
           const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
@@ -534,32 +519,19 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
         e[j][0] = fma2(g2, F2{x[j].x, x[j].y}, e[j][0]);  // :487, quantized OLD v
         e[j][1] = fma2(g2, F2{x[j].z, x[j].w}, e[j][1]);
         const F2 u0 = mul2(g2, a[j][0]), u1 = mul2(g2, a[j][1]);  // :490: g*context_avg replaces the row in its slot
-        if ((j < NJ - 1) || on_last) {
-          if (RG) red_add_v4(dst + (W2B_COFF(j) >> 2), make_float4(u0.x, u0.y, u1.x, u1.y));
-          else sts128(c_row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
-        }
+        if ((j < NJ - 1) || on_last) sts128(c_row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
       }
-      if (!RG) fence_async_smem();
+      fence_async_smem();
       __syncwarp();
       finish_job(dst, 1, q0);
     }
 
     // ---- staging job: the error goes to every context row of u (:494-503)
     {
-      if (RG) {
-        for (int k = 0; k < cw; ++k) {
-          float *dst = p.u + (long long)jobq[(q0 + k) & qmask] * p.D;
 #pragma unroll
-          for (int j = 0; j < NJ; ++j)
-            if ((j < NJ - 1) || on_last)
-              red_add_v4(dst + (W2B_COFF(j) >> 2), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-          if ((j < NJ - 1) || on_last) sts128(c_row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
-        fence_async_smem();
-      }
+      for (int j = 0; j < NJ; ++j)
+        if ((j < NJ - 1) || on_last) sts128(c_row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
+      fence_async_smem();
       __syncwarp();
       if (lane < nt) loss += (double)logf(sigmoid_report(myf0));
       if (lane + 32 < nt) loss += (double)logf(sigmoid_report(myf1));
@@ -569,8 +541,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
       }
       finish_job(nullptr, cw, q0);
       if (p.serial) {  // every update of this position has completed before the next position's rows are fetched
-        if (RG) fence_generic_to_async_global();
-        else if (lane == 0) bulk_wait_all();
+        if (lane == 0) bulk_wait_all();
         __syncwarp();
       }
     }
