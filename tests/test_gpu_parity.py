@@ -541,7 +541,7 @@ def test_evaluator_tensor_core_filter_is_exact(tmp_path, D, bits, vocab):
     130), exact-tie-heavy 1-/2-bit vectors, and a vocabulary that is not a multiple of the tile."""
     import subprocess
     rng = np.random.default_rng(D + bits)
-    pairs = 1500
+    pairs = min(1500, (vocab - 1) // 3)
     off = rng.normal(size=D).astype(np.float32) * 1.5
     a = rng.normal(size=(pairs, D)).astype(np.float32)
     b = a + off + 1.1 * rng.normal(size=(pairs, D)).astype(np.float32)
@@ -556,7 +556,7 @@ def test_evaluator_tensor_core_filter_is_exact(tmp_path, D, bits, vocab):
         f.write(b"%d %d\n" % (len(words), D))
         for w, row in zip(words, vec):
             f.write(w.encode() + b" " + row.astype(np.float32).tobytes() + b"\n")
-    usable = min(pairs, (vocab - 1) // 2)
+    usable = pairs
     qf = str(tmp_path / "questions.txt")
     with open(qf, "w") as f:
         for sec in range(6):
