@@ -27,7 +27,7 @@ class EmuRun(C.Structure):
                 ("loss", C.c_void_p), ("words", C.c_void_p), ("n_pos", C.c_void_p), ("n_ctx", C.c_void_p),
                 ("n_tgt", C.c_void_p), ("done", C.c_void_p),
                 ("trace", C.c_void_p), ("trace_cap", C.c_int64), ("trace_n", C.c_void_p), ("only_shard", C.c_int32),
-                ("fault", C.c_int32)]
+                ("fault", C.c_int32), ("reg", C.c_float)]
 
 
 def lib():
@@ -46,12 +46,12 @@ class EmuError(RuntimeError):
 
 def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, shards, serial=0, alpha=0.05,
                      sample=1e-3, iters=1, async_mode=1, seed=1, state=None, trace_shard=None, trace_cap=0, max_iters=-1,
-                     slots=0, fault=0):
+                     slots=0, fault=0, reg=0.0):
     """One pass of every shard (one 32-thread CTA after another) through the emulated warp-per-shard kernel
     (csrc/w2b_warp.cuh).  u, v are updated in place.  Returns a dict of per-shard statistics; `state` carries
     (alpha, word_count_actual) across epochs."""
     plan = w2b.warp_plan(size=size, window=window, negative=negative, bitlevel=bitlevel, vocab_size=corpus.vocab_size,
-                         slots=slots)
+                         slots=slots, reg=reg)
     if not plan["warp"]:
         raise EmuError("the warp kernel does not apply to this shape")
     start, first = corpus.shards(shards)
@@ -76,7 +76,7 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
                n_tgt=p(out["n_tgt"]), done=p(out["done"]),
                trace=C.cast(trace, C.c_void_p) if trace_cap else None, trace_cap=trace_cap,
                trace_n=p(trace_n) if trace_cap else None, only_shard=-1 if trace_shard is None else trace_shard,
-               fault=fault)
+               fault=fault, reg=reg)
     rc = lib().emu_run_warp(C.byref(r))
     if rc:
         raise EmuError(lib().emu_last_error().decode())

@@ -326,7 +326,8 @@ template <int BM, int NJ>
 void warp_entry() {
   w2b::ApplyArgs none;
   memset(&none, 0, sizeof none);
-  w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu | (g_sen_smem << 31), none);
+  if (g_p.reg != 0.f) w2b::train_warp_kernel<9, NJ, 8, 1>(g_p, g_nv, g_nu | (g_sen_smem << 31), none);
+  else w2b::train_warp_kernel<BM, NJ, 12>(g_p, g_nv, g_nu | (g_sen_smem << 31), none);
 }
 template <int BM>
 entry_fn warp_by_nj(int nj) {
@@ -374,6 +375,7 @@ struct EmuRun {
   uint64_t *trace_n;
   int32_t only_shard;  // >= 0: run just this shard
   int32_t fault;       // 0; 1 / 2: injected protocol faults (negative controls, see g_fault)
+  float reg;           // -reg
 };
 
 const char *emu_last_error() { return g_error ? g_error : ""; }
@@ -417,7 +419,7 @@ static void emu_setup(const EmuRun *r, std::vector<w2b::ShardState> &shards, w2b
   p.u = r->u; p.v = r->v; p.table = r->table; p.keep_thr = r->keep; p.exptab = r->exptab; p.tokens = r->tokens;
   p.shards = shards.data(); p.alpha = r->alpha; p.wca = (unsigned long long *)r->wca;
   p.D = r->D; p.V = r->V; p.ncol = (int)(r->D / 4); p.window = r->window; p.negative = r->negative; p.bitlevel = r->bitlevel;
-  p.sample = r->sample; p.reg = 0.f; p.starting_alpha = r->alpha0;
+  p.sample = r->sample; p.reg = r->reg; p.starting_alpha = r->alpha0;
   p.alpha_denom = (float)(r->iter * r->train_words + 1);
   p.shard_word_limit = r->train_words / r->num_shards;
   p.word_budget = r->word_budget; p.max_iters = r->max_iters; p.shard_base = 0; p.train = r->train;

@@ -375,6 +375,32 @@ def test_cli_end_to_end(tmp_path):
     assert set(np.frombuffer(body, np.uint32).tolist()) <= {0x3EAAAAAB, 0xBEAAAAAB}  # README.md:124-131
 
 
+def test_cli_debug2_lines_match_the_reference(tmp_path, medium):
+    """A `-debug 2` training run prints what the reference prints (:295-298,:523,:533,:384-387,:539): the fixed lines
+    are identical, the progress line has the reference's format and label — anything that parses the reference's
+    log parses this one.  (Numbers differ: different machine, Hogwild.)"""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    refbin = os.path.join(root, "oracle", "_ref", "word2bits")
+    if not os.path.exists(refbin):
+        pytest.skip("oracle/_ref/word2bits not built")
+    args = ["-train", medium, "-size", "40", "-window", "5", "-negative", "6", "-bitlevel", "1", "-threads", "4",
+            "-iter", "2", "-min-count", "5", "-binary", "1", "-debug", "2"]
+    outs = {}
+    for name, exe in (("ref", refbin), ("ours", os.path.join(root, "word2bits_b200", "word2bits"))):
+        r = subprocess.run([exe] + args + ["-output", str(tmp_path / (name + ".bin"))], capture_output=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[name] = r.stdout.decode("latin1")  # (bytes: the carriage returns must survive)
+    prog = re.compile(r"\rAlpha: \d+\.\d{6}  Progress: \d+\.\d{2}%  Cost: -?\d+\.\d{6} Words/thread/sec: \d+\.\d{2}k  ")
+    def skeleton(txt):
+        assert prog.search(txt), txt[:500]
+        txt = prog.sub("", txt)
+        return [re.sub(r"-?\d+\.\d+", "#", line) for line in txt.split("\n")]
+    assert skeleton(outs["ref"]) == skeleton(outs["ours"]), (outs["ref"][:800], outs["ours"][:800])
+    assert "Starting training using file" in outs["ours"] and outs["ours"].count("Epoch Loss: ") == 2
+
+
 def test_planted_topic_quality(tmp_path):
     """L3 statistical end-to-end: on a corpus with planted topics the trained
     1-bit vectors must recover the topics as well as the reference's own (kNN purity within 0.04,

@@ -83,6 +83,25 @@ def test_every_geometry_trains_what_the_oracle_trains(D, W, neg, b, S, tiny):
         assert abs(out["loss"].sum() - lo) <= 0.06 * abs(lo), (slots, out["loss"].sum(), lo)
 
 
+@pytest.mark.parametrize("b,D", [(0, 64), (2, 200)])
+def test_regularised_training_tracks_the_oracle(b, D, medium):
+    """-reg != 0 on the production kernel (decay of every touched row in its scatter, regularisation terms in the
+    reported loss): one shard, sequential mode, against the oracle with the same reg."""
+    c, o, table = medium
+    reg = 0.002
+    m = po.OracleModel(o, D, 5, 6, b, shards=1, iters=1, table=table, reg=reg)
+    lo = m.train_shard(0)
+    u, v, out = _run(c, table, D, 5, 6, b, 1, serial=1, async_mode=2, seed=3, reg=reg)
+    assert abs(out["loss"].sum() - lo) <= 2e-3 * abs(lo), (out["loss"].sum(), lo)
+    if b == 0:
+        assert np.abs(u - m.u).max() < 5e-3 and np.abs(v - m.v).max() < 5e-3
+    else:
+        assert np.corrcoef(u.ravel(), m.u.ravel())[0, 1] > 0.9 and np.corrcoef(v.ravel(), m.v.ravel())[0, 1] > 0.9
+    m0 = po.OracleModel(o, D, 5, 6, b, shards=1, iters=1, table=table)
+    m0.train_shard(0)
+    assert np.abs(m0.u - m.u).max() > 1e-3  # the regulariser really moved the weights: the comparison above is not vacuous
+
+
 def test_sampler_trace_equals_oracle(tiny):
     c, o, table = tiny
     for neg, shard in ((40, 0), (40, 2), (5, 1)):
@@ -120,4 +139,4 @@ def test_plan_fits_an_sm():
     assert n == 256 * 6
     assert w2b.warp_plan(size=1028, window=5, negative=5)["warp"] == 0   # wider than the instantiated kernels
     assert w2b.warp_plan(size=6, window=5, negative=5)["warp"] == 0      # rows must be 16-byte multiples
-    assert w2b.warp_plan(size=64, window=5, negative=5, reg=0.1)["warp"] == 0
+    assert w2b.warp_plan(size=64, window=5, negative=5, reg=0.1)["warps_per_sm"] == 20  # -reg: own instantiations

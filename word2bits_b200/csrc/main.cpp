@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 #include <time.h>
 
 #include <condition_variable>
@@ -210,8 +212,12 @@ int main(int argc, char **argv) {
       for (long long step = 1;; ++step) {
         w2b_step_stats st;
         // 50k words per shard per step: progress lines 5x less often than the reference (:379), steps
-        // long enough that the whole-sentence overshoot at a step boundary (<= ~1.2k words) stays ~1 %
-        if (w2b_train_step(ctx, (debug_mode > 1 || G > 1) ? 50000 : 0, &st)) die("w2b_train_step");
+        // long enough that the whole-sentence overshoot at a step boundary (<= ~1.2k words) stays ~1 %.
+        // Several GPUs: replicas must meet often enough to stay one model — at least ~32 steps per epoch
+        // (sync_every of them between two averages), but never steps shorter than a couple of sentences.
+        long long step_words = 50000;
+        if (G > 1) step_words = std::max<long long>(2000, std::min<long long>(50000, train_words / cfg.num_shards / 32));
+        if (w2b_train_step(ctx, (debug_mode > 1 || G > 1) ? step_words : 0, &st)) die("w2b_train_step");
         {
           std::lock_guard<std::mutex> lk(mu);
           epoch_loss += st.loss;

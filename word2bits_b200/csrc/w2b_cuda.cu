@@ -226,8 +226,21 @@ static warp_fn warp_by_nj(int nj) {
   }
   return nullptr;
 }
+template <int NJ, int MINB>
+static warp_fn warp_reg() { return train_warp_kernel<9, NJ, MINB, 1>; }
 static warp_fn pick_warp(const w2b_ctx *c) {
   const int nj = (c->ncol + 31) / 32;
+  if (c->cfg.reg != 0.f)  // -reg: one instantiation per width (run-time bit level; lower occupancy: the raw row stays live)
+    switch (nj) {
+      case 1: return warp_reg<1, 20>();
+      case 2: return warp_reg<2, 16>();
+      case 3: return warp_reg<3, 12>();
+      case 4: return warp_reg<4, 12>();
+      case 5: return warp_reg<5, 8>();
+      case 6: return warp_reg<6, 8>();
+      case 7: return warp_reg<7, 8>();
+      case 8: return warp_reg<8, 8>();
+    }
   switch (bm_of(c->cfg.bitlevel)) {
     case 0: return warp_by_nj<0>(nj);
     case 1: return warp_by_nj<1>(nj);
@@ -239,10 +252,10 @@ static warp_fn pick_warp(const w2b_ctx *c) {
 // reserved shared memory); at least 3 (one row being worked on, one draining, one in flight).
 static void plan_warp(w2b_ctx *c) {
   c->warp = false;
-  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.reg != 0.f || c->cfg.kernel == 1) return;
+  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.kernel == 1) return;
   const int nj = (c->ncol + 31) / 32;
   if (nj > 8) return;  // kernels are instantiated for D <= 1024
-  const int minb = warp_minb_of(nj);
+  const int minb = c->cfg.reg != 0.f ? (nj >= 5 ? 8 : (nj >= 3 ? 12 : (nj == 2 ? 16 : 20))) : warp_minb_of(nj);
   const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
   const size_t budget = (size_t)(228 * 1024) / minb - 1024;
   // the sentence buffer (4000 B) moves to global memory when keeping it in shared memory would cost ring slots

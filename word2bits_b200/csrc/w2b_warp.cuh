@@ -310,7 +310,11 @@ __device__ inline int warp_next_position(const TrainParams &p, const ShardState 
 // unit — red.global.add.v4.f32 from registers — instead of the bulk-copy engine: same throughput, same memory-system
 // ceiling; 16 / 20 / 24 instead of 12 / 16 / 20 warps per SM: 2-11 % slower except for rows of <= 128 floats; 2 or 3
 // bulk-reduce groups left pending instead of 1: no change.)
-template <int BM, int NJ, int MINB>
+// REG = 1: -reg != 0 (:443-445,:471,:490,:501).  Every row then also decays by 2*alpha*reg times its own (raw) value:
+// a target row in the same scatter as its update (g*context_avg - 2*alpha*reg*v), a context row by a scatter of its
+// own when it is read (the reference subtracts at the end of the position from a value this thread has not changed
+// in between — same sum, other order); the regularisation terms of the reported loss are accumulated per lane.
+template <int BM, int NJ, int MINB, int REG = 0>
 __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int K, int qcap_sen, ApplyArgs ap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
@@ -453,18 +457,28 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     F2 a[NJ][2];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) a[j][0] = a[j][1] = F2{0.f, 0.f};
+    float regsum = 0.f;                                    // REG: sum of squared quantized values this lane saw
+    const float decay = REG ? -2.f * alpha * p.reg : 0.f;  // REG: row += decay * row
     for (int k = 0; k < cw; ++k) {
+      float *urow = REG ? p.u + (long long)jobq[q_cons & qmask] * p.D : nullptr;
       mbar_wait(c_bar, c_par);
       float4 x[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) x[j] = lds128(c_row + W2B_COFF(j));
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        a[j][0] = add2(a[j][0], F2{quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp)});
-        a[j][1] = add2(a[j][1], F2{quant_fast<BM>(x[j].z, qp), quant_fast<BM>(x[j].w, qp)});
+        const float4 xq = make_float4(quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp), quant_fast<BM>(x[j].z, qp),
+                                      quant_fast<BM>(x[j].w, qp));
+        a[j][0] = add2(a[j][0], F2{xq.x, xq.y});
+        a[j][1] = add2(a[j][1], F2{xq.z, xq.w});
+        if (REG && ((j < NJ - 1) || on_last)) {
+          regsum += (xq.x * xq.x + xq.y * xq.y) + (xq.z * xq.z + xq.w * xq.w);
+          sts128(c_row + W2B_COFF(j), make_float4(decay * x[j].x, decay * x[j].y, decay * x[j].z, decay * x[j].w));
+        }
       }
+      if (REG) fence_async_smem();
       __syncwarp();
-      finish_job(nullptr, 0, q0);
+      finish_job(urow, 0, q0);
     }
     {  // context_avg = sum / cw (:449), correctly rounded without the division subroutine: q = a*r, then one
        // Newton step on the exact remainder (r = RN(1/cw); equals IEEE division for every cw <= 128 and every
@@ -497,12 +511,16 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
 #pragma unroll
       for (int j = 0; j < NJ; ++j) x[j] = lds128(c_row + W2B_COFF(j));
       F2 d0 = F2{0.f, 0.f}, d1 = F2{0.f, 0.f};
+      float4 raw[REG ? NJ : 1];  // REG: the decay needs the row as it was loaded
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
+        if (REG) raw[j] = x[j];
         x[j] = make_float4(quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp), quant_fast<BM>(x[j].z, qp),
                            quant_fast<BM>(x[j].w, qp));
         d0 = fma2(a[j][0], F2{x[j].x, x[j].y}, d0);
         d1 = fma2(a[j][1], F2{x[j].z, x[j].w}, d1);
+        if (REG && ((j < NJ - 1) || on_last))
+          regsum += (x[j].x * x[j].x + x[j].y * x[j].y) + (x[j].z * x[j].z + x[j].w * x[j].w);
       }
       float f = (d0.x + d0.y) + (d1.x + d1.y);
 #pragma unroll
@@ -518,7 +536,11 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
       for (int j = 0; j < NJ; ++j) {
         e[j][0] = fma2(g2, F2{x[j].x, x[j].y}, e[j][0]);  // :487, quantized OLD v
         e[j][1] = fma2(g2, F2{x[j].z, x[j].w}, e[j][1]);
-        const F2 u0 = mul2(g2, a[j][0]), u1 = mul2(g2, a[j][1]);  // :490: g*context_avg replaces the row in its slot
+        F2 u0 = mul2(g2, a[j][0]), u1 = mul2(g2, a[j][1]);  // :490: g*context_avg replaces the row in its slot
+        if (REG) {
+          u0 = F2{fmaf(decay, raw[j].x, u0.x), fmaf(decay, raw[j].y, u0.y)};
+          u1 = F2{fmaf(decay, raw[j].z, u1.x), fmaf(decay, raw[j].w, u1.y)};
+        }
         if ((j < NJ - 1) || on_last) sts128(c_row + W2B_COFF(j), make_float4(u0.x, u0.y, u1.x, u1.y));
       }
       fence_async_smem();
@@ -535,6 +557,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
       __syncwarp();
       if (lane < nt) loss += (double)logf(sigmoid_report(myf0));
       if (lane + 32 < nt) loss += (double)logf(sigmoid_report(myf1));
+      if (REG) loss -= (double)(p.reg * regsum);  // :443-445 and :471, summed over the position's rows
       if (ap.f_out) {
         if (lane < nt) ap.f_out[lane] = lane == 0 ? myf0 : -myf0;
         if (lane + 32 < nt) ap.f_out[lane + 32] = -myf1;
