@@ -285,6 +285,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--words-per-shard", type=int, default=65536)
     ap.add_argument("--sync-every", type=int, default=4)
+    ap.add_argument("--sync-mode", default="avg", choices=["avg", "sum"],
+                    help="replica exchange: average (BASELINE.json's north_star) or sum of every rank's updates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
@@ -336,7 +338,7 @@ def main():
 
     def make(resident):
         t = w2b.Trainer(None, vocab_size=V + 1, threads=S, shard_range=(rank * S_local, (rank + 1) * S_local),
-                        init=False, **cfg0)
+                        init=False, sync_mode=1 if args.sync_mode == "sum" else 0, **cfg0)
         t.set_vocab_counts(cn, train_words)
         t.set_corpus(ids, start, first, resident)
         t.init_tables()
@@ -448,7 +450,7 @@ def main():
            "positions_per_s": positions / dev_s, "wall_ms_per_step": wall_s / args.steps * 1e3,
            "sync_ms_per_step": a["sync_ms"] / args.steps,
            "sync": None if world == 1 else {
-               "every_steps": args.sync_every, "syncs_timed": a["syncs"],
+               "every_steps": args.sync_every, "mode": args.sync_mode, "syncs_timed": a["syncs"],
                "ms_per_sync": a["sync_ms"] / max(a["syncs"], 1),
                "bytes_per_sync": 2 * (V + 1) * D * 4,
                "allreduce_bus_gbs": (2.0 * (world - 1) / world) * (2 * (V + 1) * D * 4) / 1e9 / max(a["sync_ms"] / max(a["syncs"], 1) / 1e3, 1e-9),

@@ -111,6 +111,9 @@ typedef struct {
   int32_t prefetch;    /* warp kernel: 0 = the positions of a shard strictly one after another, like a reference
                           thread (default; measured free on B200); 1 = rows of position p+1 are fetched before p's
                           updates have landed (a context row shared by neighbours is read one update stale) */
+  int32_t sync_mode;   /* multi-GPU exchange (w2b_sync): 0 = replicas are averaged (default); 1 = every rank's
+                          updates since the last exchange are summed onto the common base (needs two more tables;
+                          call w2b_nccl_init after w2b_init_tables / w2b_checkpoint_load) */
 } w2b_config;
 
 typedef struct {

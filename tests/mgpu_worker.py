@@ -51,6 +51,27 @@ def main():
     for _ in range(2):
         dp.step(3000)
     dp.finish()
+    t.close()
+    # ---- sync_mode 1: every rank's updates since the last exchange are summed onto the common base
+    t = w2b.Trainer(c, size=64, window=5, negative=6, bitlevel=1, threads=S, shard_range=(lo, hi), iter=1, device=local,
+                    sync_mode=1)
+    t.nccl_init(exchange_unique_id(dist, w2b.nccl_unique_id, device="cuda"), rank, world)
+    u0, v0 = t.download_raw()
+    dp = DataParallel(t, dist, sync_every=1000, device="cuda")
+    for _ in range(3):
+        dp.step(3000)
+    u, v = t.download_raw()
+    gu = [torch.empty_like(torch.from_numpy(u)).cuda() for _ in range(world)]
+    dist.all_gather(gu, torch.from_numpy(u).cuda())
+    want_u = (torch.from_numpy(u0).cuda().double() + sum(g.double() - torch.from_numpy(u0).cuda().double() for g in gu)).float().cpu().numpy()
+    t.sync()
+    u2, v2 = t.download_raw()
+    assert np.allclose(u2, want_u, rtol=0, atol=1e-6) and not np.allclose(u2, u, rtol=0, atol=1e-4)
+    assert dp.replicas_identical()
+    for _ in range(2):
+        dp.step(3000)
+    t.sync()
+    assert dp.replicas_identical()
     if rank == 0:
         print("MGPU_OK world=%d words=%d wca=%d" % (world, int(tot), wca))
     t.close()

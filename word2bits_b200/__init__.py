@@ -56,7 +56,7 @@ def warp_plan(*, size, window, negative, bitlevel=1, reg=0.0, vocab_size=1000, m
     """Geometry of the production (warp-per-shard) kernel for a configuration (pure host arithmetic)."""
     cfg = _lib.Config(vocab_size=vocab_size, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
                       alpha=0.05, sample=1e-3, reg=reg, iter=1, num_shards=1, shard_begin=0, shard_end=0, device=0,
-                      mode=mode, group=0, plain_store=0, kernel=kernel, slots=slots, prefetch=0)
+                      mode=mode, group=0, plain_store=0, kernel=kernel, slots=slots, prefetch=0, sync_mode=0)
     out = _lib.WarpPlan()
     check(lib.w2b_warp_plan_query(C.byref(cfg), C.byref(out)))
     return out.as_dict()
@@ -123,12 +123,12 @@ class Trainer:
 
     def __init__(self, corpus=None, *, size=100, window=5, negative=5, bitlevel=1, alpha=0.05, sample=1e-3,
                  reg=0.0, iter=5, threads=None, device=0, mode=MODE_FAST, shard_range=None, group=0,
-                 plain_store=0, resident=True, vocab_size=None, init=True, kernel=0, slots=0, prefetch=0):
+                 plain_store=0, resident=True, vocab_size=None, init=True, kernel=0, slots=0, prefetch=0, sync_mode=0):
         V = corpus.vocab_size if corpus is not None else vocab_size
         cfg = _lib.Config(vocab_size=V, layer1_size=size, window=window, negative=negative, bitlevel=bitlevel,
                           alpha=alpha, sample=sample, reg=reg, iter=iter, num_shards=threads or 1,
                           shard_begin=0, shard_end=0, device=device, mode=mode, group=group,
-                          plain_store=plain_store, kernel=kernel, slots=slots, prefetch=prefetch)
+                          plain_store=plain_store, kernel=kernel, slots=slots, prefetch=prefetch, sync_mode=sync_mode)
         if threads is None:
             n = C.c_int(0)
             check(lib.w2b_suggest_shards(C.byref(cfg), C.byref(n)))

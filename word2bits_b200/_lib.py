@@ -27,7 +27,7 @@ class Config(C.Structure):
                 ("iter", C.c_int64),
                 ("num_shards", C.c_int32), ("shard_begin", C.c_int32), ("shard_end", C.c_int32),
                 ("device", C.c_int32), ("mode", C.c_int32), ("group", C.c_int32), ("plain_store", C.c_int32),
-                ("kernel", C.c_int32), ("slots", C.c_int32), ("prefetch", C.c_int32)]
+                ("kernel", C.c_int32), ("slots", C.c_int32), ("prefetch", C.c_int32), ("sync_mode", C.c_int32)]
 
 
 class StepStats(C.Structure):

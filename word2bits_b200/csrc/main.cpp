@@ -108,6 +108,8 @@ int main(int argc, char **argv) {
   int ngpus = 1, sync_every = 4;
   if ((i = arg_pos("-gpus", argc, argv)) > 0) ngpus = atoi(argv[i + 1]);
   if ((i = arg_pos("-sync-every", argc, argv)) > 0) sync_every = atoi(argv[i + 1]);
+  int sync_mode = 0;  // 0 = average the replicas, 1 = sum every GPU's updates onto the common base
+  if ((i = arg_pos("-sync-mode", argc, argv)) > 0) sync_mode = atoi(argv[i + 1]);
   if (ngpus < 1) ngpus = 1;
   if (sync_every < 1) sync_every = 1;
 
@@ -138,6 +140,7 @@ int main(int argc, char **argv) {
   cfg.iter = iter;
   cfg.device = device;
   cfg.mode = strict ? W2B_MODE_STRICT : W2B_MODE_FAST;
+  cfg.sync_mode = sync_mode == 1 ? 1 : 0;
   cfg.num_shards = num_threads > 0 ? num_threads : 1;
   if (num_threads <= 0) {
     int s = 0;
@@ -186,7 +189,6 @@ int main(int argc, char **argv) {
     if (w2b_set_corpus(ctx, w2b_corpus_tokens(corpus), w2b_corpus_num_tokens(corpus), start.data(), first.data(), 1))
       die("w2b_set_corpus");
     if (w2b_init_tables(ctx)) die("w2b_init_tables");
-    if (G > 1 && w2b_nccl_init(ctx, uid, rank, G)) die("w2b_nccl_init");
     long long first_epoch = 0;
     if (!resume_file.empty()) {
       int64_t done = 0;
@@ -200,6 +202,7 @@ int main(int argc, char **argv) {
         words_done = words_at_start = wca;
       }
     }
+    if (G > 1 && w2b_nccl_init(ctx, uid, rank, G)) die("w2b_nccl_init");  // (after the tables hold their starting point)
     std::vector<float> buf;
     if (rank == 0) buf.resize((size_t)V * layer1_size);
     for (int iteration = (int)first_epoch; iteration < iter; iteration++) {
@@ -215,9 +218,9 @@ int main(int argc, char **argv) {
         // long enough that the whole-sentence overshoot at a step boundary (<= ~1.2k words) stays ~1 %.
         // Several GPUs: replicas must meet often enough to stay one model — at least ~32 steps per epoch
         // (sync_every of them between two averages), but never steps shorter than a couple of sentences.
-        long long step_words = 50000;
-        if (G > 1) step_words = std::max<long long>(2000, std::min<long long>(50000, train_words / cfg.num_shards / 32));
-        if (w2b_train_step(ctx, (debug_mode > 1 || G > 1) ? step_words : 0, &st)) die("w2b_train_step");
+        long long per_step = 50000;
+        if (G > 1) per_step = std::max<long long>(2000, std::min<long long>(50000, train_words / cfg.num_shards / 32));
+        if (w2b_train_step(ctx, (debug_mode > 1 || G > 1) ? per_step : 0, &st)) die("w2b_train_step");
         {
           std::lock_guard<std::mutex> lk(mu);
           epoch_loss += st.loss;

@@ -116,6 +116,7 @@ struct w2b_ctx {
   int sm_count = 0;
   long long train_words = 0;
   float *d_u = nullptr, *d_v = nullptr, *d_keep = nullptr, *d_exptab = nullptr, *d_alpha = nullptr;
+  float *d_base_u = nullptr, *d_base_v = nullptr;  // sync_mode 1: the tables as they were after the last exchange
   int *d_table = nullptr, *d_tokens = nullptr;
   unsigned long long *d_wca = nullptr;
   ShardState *d_shards = nullptr;
@@ -498,6 +499,7 @@ extern "C" int w2b_destroy(w2b_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_u); cudaFree(c->d_v); cudaFree(c->d_keep); cudaFree(c->d_exptab);
+  cudaFree(c->d_base_u); cudaFree(c->d_base_v);
   cudaFree(c->d_alpha); cudaFree(c->d_wca); cudaFree(c->d_table); cudaFree(c->d_tokens);
   cudaFree(c->d_shards);
   cudaFree(c->d_scratch);
@@ -1251,6 +1253,13 @@ extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks
   if (e) { w2b_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
   c->rank = rank;
   c->nranks = nranks;
+  if (c->cfg.sync_mode == 1) {  // sum of deltas: remember the common starting point (same InitNet / checkpoint on every rank)
+    const size_t bytes = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
+    if (!c->d_base_u) CK(cudaMalloc(&c->d_base_u, bytes));
+    if (!c->d_base_v) CK(cudaMalloc(&c->d_base_v, bytes));
+    CK(cudaMemcpy(c->d_base_u, c->d_u, bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(c->d_base_v, c->d_v, bytes, cudaMemcpyDeviceToDevice));
+  }
   return W2B_OK;
 }
 
@@ -1275,6 +1284,18 @@ __global__ void wca_apply_kernel(unsigned long long *wca, unsigned long long *sc
   scratch[1] += scratch[0];
   *wca = scratch[1];
 }
+// sync_mode 1 (sum of deltas): x <- x - base before the all-reduce(sum); x <- base + x, base <- x after it
+__global__ void delta_kernel(float *x, const float *base, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = __fsub_rn(x[i], base[i]);
+}
+__global__ void rebase_kernel(float *x, float *base, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float y = __fadd_rn(base[i], x[i]);
+    x[i] = y;
+    base[i] = y;
+  }
+}
 // order-independent fingerprint of a table: sum of its 32-bit patterns (mod 2^64)
 __global__ void checksum_kernel(const unsigned *x, long long n, unsigned long long *out) {
   unsigned long long acc = 0;
@@ -1283,7 +1304,10 @@ __global__ void checksum_kernel(const unsigned *x, long long n, unsigned long lo
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-// Replica averaging: u, v <- mean over ranks (ncclAvg, in place) and word_count_actual <- exact global sum, as ONE
+// Replica exchange: u, v <- mean over ranks (ncclAvg, in place; cfg.sync_mode 0, what BASELINE.json's north_star
+// names) or u, v <- common base + SUM over ranks of what each rank added since the last exchange (sync_mode 1: every
+// rank's updates land in full, as the reference's threads' do in shared memory; averaging divides them by the number
+// of ranks, which for rows only one rank touched is a G-fold smaller step), and word_count_actual <- exact global sum, as ONE
 // NCCL group on this context's stream — no host round trip between the three reductions.  G=1: no-op, NCCL never
 // touched.  *ms (optional) = device time of the exchange (CUDA events).
 extern "C" int w2b_sync_timed(w2b_ctx *c, float *ms) {
@@ -1293,17 +1317,31 @@ extern "C" int w2b_sync_timed(w2b_ctx *c, float *ms) {
   if (!c->comm) { w2b_set_error("w2b_nccl_init first"); return W2B_ESTATE; }
   CK(cudaSetDevice(c->cfg.device));
   const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size;
+  const bool sum = c->cfg.sync_mode == 1;
+  if (sum && !c->d_base_u) {  // first exchange: every rank still holds the common starting point in `base`
+    w2b_set_error("w2b_sync: sync_mode 1 needs w2b_nccl_init after the tables were initialised");
+    return W2B_ESTATE;
+  }
   CK(cudaEventRecord(c->ev_s0, c->stream));
   wca_own_kernel<<<1, 1, 0, c->stream>>>(c->d_wca, c->d_scratch, c->nranks);
+  if (sum) {
+    delta_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, c->d_base_u, (long long)n);
+    delta_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_v, c->d_base_v, (long long)n);
+  }
   CK(cudaGetLastError());
+  const int op = sum ? kNcclSum : kNcclAvg;
   int e = g_nccl.GroupStart();
-  if (!e) e = g_nccl.AllReduce(c->d_u, c->d_u, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
-  if (!e) e = g_nccl.AllReduce(c->d_v, c->d_v, n, kNcclFloat32, kNcclAvg, c->comm, c->stream);
+  if (!e) e = g_nccl.AllReduce(c->d_u, c->d_u, n, kNcclFloat32, op, c->comm, c->stream);
+  if (!e) e = g_nccl.AllReduce(c->d_v, c->d_v, n, kNcclFloat32, op, c->comm, c->stream);
   if (!e) e = g_nccl.AllReduce(c->d_scratch, c->d_scratch, 1, kNcclUint64, kNcclSum, c->comm, c->stream);
   const int e2 = g_nccl.GroupEnd();
   if (!e) e = e2;
   if (e) { w2b_set_error("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
   wca_apply_kernel<<<1, 1, 0, c->stream>>>(c->d_wca, c->d_scratch);
+  if (sum) {
+    rebase_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, c->d_base_u, (long long)n);
+    rebase_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_v, c->d_base_v, (long long)n);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev_s1, c->stream));
   unsigned long long at_sync = 0;

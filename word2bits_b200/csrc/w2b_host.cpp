@@ -411,14 +411,18 @@ static int w2b_corpus_load_impl(const char *path, int min_count, w2b_corpus **ou
     w2b_set_error("ERROR: training data file not found!");
     return W2B_EIO;
   }
-  w2b_corpus *c = new w2b_corpus();
+  // owned until the very end: an exception below (std::bad_alloc, std::system_error from a thread) unwinds through
+  // this guard, which unmaps the file, closes the descriptor and frees the object (w2b_guarded turns it into a code)
+  struct Owner {
+    w2b_corpus *c;
+    ~Owner() { if (c) w2b_corpus_free(c); }
+  } owner{new w2b_corpus()};
+  w2b_corpus *c = owner.c;
   c->fd = fd;
   c->file_size = st.st_size;  // == ftell at EOF, :299
   if (st.st_size > 0) {
     void *m = mmap(nullptr, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     if (m == MAP_FAILED) {
-      close(fd);
-      delete c;
       w2b_set_error("mmap failed for %s", path);
       return W2B_EIO;
     }
@@ -514,8 +518,7 @@ static int w2b_corpus_load_impl(const char *path, int min_count, w2b_corpus **ou
     int64_t max_distinct = 21000000;
     if (const char *e = getenv("W2B_TOKENIZER_MAX_DISTINCT")) max_distinct = atoll(e);  // (tests)
     const int64_t distinct = (int64_t)part_base[kParts] + (eos_entry >= 0 ? 0 : 1);
-    if (distinct > max_distinct) {
-      w2b_corpus_free(c);
+    if (distinct > max_distinct) {  // (the guard above releases the corpus)
       w2b_set_error("%lld distinct words: above 21 M the reference prunes its vocabulary mid-scan (ReduceVocab), "
                     "which this reader does not reproduce", (long long)distinct);
       return W2B_EINVAL;
@@ -578,6 +581,7 @@ static int w2b_corpus_load_impl(const char *path, int min_count, w2b_corpus **ou
   }
   lap("compact");
   *out = c;
+  owner.c = nullptr;
   return W2B_OK;
 }
 
