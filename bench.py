@@ -284,13 +284,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--words-per-shard", type=int, default=65536)
-    ap.add_argument("--sync-every", type=int, default=4)
+    ap.add_argument("--sync-every", type=int, default=0,
+                    help="steps between two replica exchanges; 0 = 4, or more when the tables are large (one exchange per ~3.2 GB-steps: C2 4, C5 8)")
     ap.add_argument("--sync-mode", default="avg", choices=["avg", "sum"],
                     help="replica exchange: average (BASELINE.json's north_star) or sum of every rank's updates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     select_workload(args.workload)
+    if args.sync_every <= 0:
+        args.sync_every = max(4, int(round(2.0 * (V + 1) * D * 4 / 3.2e9)))
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
