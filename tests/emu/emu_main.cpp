@@ -380,6 +380,16 @@ struct EmuRun {
 
 const char *emu_last_error() { return g_error ? g_error : ""; }
 
+// the kernel's division-free context average (w2b::div_by_count) on n numerators: out[i] = a[i] / cw
+void emu_div_by_count(const float *a, int n, int cw, float *out) {
+  const float fcw = (float)cw, rc = __frcp_rn(fcw);
+  for (int i = 0; i + 1 < n; i += 2) {
+    const w2b::F2 q = w2b::div_by_count(w2b::F2{a[i], a[i + 1]}, fcw, rc);
+    out[i] = q.x;
+    out[i + 1] = q.y;
+  }
+}
+
 // negative control of the shared-memory checks: would an access of `bytes` at `off` be reported under the
 // carve-up of the last run?  (returns the planned total through *total)
 int emu_check_probe(unsigned off, unsigned bytes, uint64_t *total) {

@@ -123,6 +123,27 @@ def test_emulator_checks_the_async_proxy_rules(tiny):
                                  async_mode=2, seed=3, fault=fault)
 
 
+def test_division_free_average_is_ieee_division():
+    """context_avg = sum / cw (:449) is computed as a*r followed by one Newton step on the exact remainder
+    (w2b::div_by_count, the kernel's own function, run here on the host): identical bits to float32 division for
+    every context count 1..128 — sums of quantized levels (many exactly zero), random values, tiny and large ones."""
+    import ctypes as C
+    L = emu.lib()
+    L.emu_div_by_count.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(1)
+    n = 200000
+    for cw in list(range(1, 129)):
+        k = rng.integers(-cw, cw + 1, n // 4)
+        levels = (k.astype(np.float32) * np.float32(0.33333334)).astype(np.float32)
+        vals = np.concatenate([levels, (rng.standard_normal(n // 4) * cw).astype(np.float32),
+                               (rng.integers(-1000, 1001, n // 4) * 0.25).astype(np.float32),
+                               (rng.standard_normal(n // 4) * 1e-3).astype(np.float32)]).astype(np.float32)
+        out = np.empty_like(vals)
+        L.emu_div_by_count(vals.ctypes.data, len(vals), cw, out.ctypes.data)
+        want = (vals / np.float32(cw)).astype(np.float32)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), cw
+
+
 def test_plan_fits_an_sm():
     """Planner invariants over the shapes it accepts: K >= 3 slots, the job queue holds two positions, and the
     warps the register allocation is sized for fit the SM's 228 KB with 1 KB reserved per CTA."""

@@ -131,6 +131,17 @@ __device__ __forceinline__ float sign_level(float x, float level) {  // (x & 0x8
 __device__ __forceinline__ float ldc_exptab(int i) { return c_exptab[i]; }
 #endif
 
+// a / fcw for a small integer fcw with rc = RN(1 / fcw), correctly rounded without the division subroutine (which
+// takes its slow path for every exactly-zero numerator — and sums of +-1/3 are often exactly zero): q = a*rc, then
+// one Newton step on the exact remainder.  Equals IEEE division for every fcw <= 128 and every numerator in range
+// (tests/test_warp_emulation.py::test_division_free_average_is_ieee_division runs this very function on the host).
+__device__ __forceinline__ F2 div_by_count(F2 a, float fcw, float rc) {
+  const F2 r2 = F2{rc, rc}, nc2 = F2{-fcw, -fcw};
+  const F2 q0 = mul2(a, r2);
+  const F2 rem = fma2(q0, nc2, a);
+  return fma2(rem, r2, q0);
+}
+
 // quantize() (:73-108) as the training loop uses it.  bitlevel 1 and 2 copy the SIGN BIT onto the level instead
 // of testing x < 0: identical for every value except -0.0 (and NaNs with the sign bit set), which the reference
 // maps to the positive level; a master weight can only become -0.0 through a flushed negative denormal sum.
@@ -465,37 +476,39 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
       float4 x[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) x[j] = lds128(c_row + W2B_COFF(j));
+      if constexpr (REG) {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float4 xq = make_float4(quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp), quant_fast<BM>(x[j].z, qp),
-                                      quant_fast<BM>(x[j].w, qp));
-        a[j][0] = add2(a[j][0], F2{xq.x, xq.y});
-        a[j][1] = add2(a[j][1], F2{xq.z, xq.w});
-        if (REG && ((j < NJ - 1) || on_last)) {
-          regsum += (xq.x * xq.x + xq.y * xq.y) + (xq.z * xq.z + xq.w * xq.w);
-          sts128(c_row + W2B_COFF(j), make_float4(decay * x[j].x, decay * x[j].y, decay * x[j].z, decay * x[j].w));
+        for (int j = 0; j < NJ; ++j) {
+          const float4 xq = make_float4(quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp), quant_fast<BM>(x[j].z, qp),
+                                        quant_fast<BM>(x[j].w, qp));
+          a[j][0] = add2(a[j][0], F2{xq.x, xq.y});
+          a[j][1] = add2(a[j][1], F2{xq.z, xq.w});
+          if ((j < NJ - 1) || on_last) {
+            regsum += (xq.x * xq.x + xq.y * xq.y) + (xq.z * xq.z + xq.w * xq.w);
+            sts128(c_row + W2B_COFF(j), make_float4(decay * x[j].x, decay * x[j].y, decay * x[j].z, decay * x[j].w));
+          }
         }
+        fence_async_smem();
+        __syncwarp();
+        finish_job(urow, 0, q0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          a[j][0] = add2(a[j][0], F2{quant_fast<BM>(x[j].x, qp), quant_fast<BM>(x[j].y, qp)});
+          a[j][1] = add2(a[j][1], F2{quant_fast<BM>(x[j].z, qp), quant_fast<BM>(x[j].w, qp)});
+        }
+        __syncwarp();
+        finish_job(nullptr, 0, q0);
       }
-      if (REG) fence_async_smem();
-      __syncwarp();
-      finish_job(urow, 0, q0);
     }
-    {  // context_avg = sum / cw (:449), correctly rounded without the division subroutine: q = a*r, then one
-       // Newton step on the exact remainder (r = RN(1/cw); equals IEEE division for every cw <= 128 and every
-       // numerator in range — tests/test_host_cpu.py checks the identity on the host)
+    {  // context_avg = sum / cw (:449)
       const float fcw = (float)cw;
       const float rc = __frcp_rn(fcw);
-      const F2 r2 = F2{rc, rc}, nc2 = F2{-fcw, -fcw};
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const bool on = (j < NJ - 1) || on_last;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const F2 q0v = mul2(a[j][h], r2);
-          const F2 rem = fma2(q0v, nc2, a[j][h]);
-          const F2 q1v = fma2(rem, r2, q0v);
-          a[j][h] = on ? q1v : F2{0.f, 0.f};
-        }
+        for (int h = 0; h < 2; ++h) a[j][h] = on ? div_by_count(a[j][h], fcw, rc) : F2{0.f, 0.f};
       }
     }
 
