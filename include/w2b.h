@@ -106,7 +106,7 @@ typedef struct {
   int32_t group;       /* register kernel: target rows in flight per CTA step (0 = default) */
   int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
   int32_t kernel;      /* fast mode: 0 = warp-per-shard kernel when applicable (default; csrc/w2b_warp.cuh),
-                          1 = register kernel (one CTA per shard; also serves strict mode, D % 4 != 0, D > 1024) */
+                          1 = register kernel (one CTA per shard; also serves strict mode and D > 1024) */
   int32_t slots;       /* warp kernel: shared-memory row slots per warp (0 = as many as fit, at most 16) */
   int32_t prefetch;    /* warp kernel: 0 = the positions of a shard strictly one after another, like a reference
                           thread (default; measured free on B200); 1 = rows of position p+1 are fetched before p's
@@ -142,8 +142,7 @@ const char *w2b_last_error(void);
 int w2b_device_count(int *n);
 
 /* Geometry the production (warp-per-shard) kernel would run with for a configuration: pure host arithmetic (no
- * CUDA call).  warp = 0: the configuration runs the register kernel instead (D % 4 != 0, D > 1024, reg != 0,
- * strict mode, kernel = 1). */
+ * CUDA call).  warp = 0: the configuration runs the register kernel instead (D > 1024, strict mode, kernel = 1). */
 typedef struct {
   int32_t warp;           /* 1 = the warp kernel applies */
   int32_t slots;          /* K: shared-memory row slots of a warp's ring (K-2 loads in flight) */

@@ -65,6 +65,11 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
     trace = (_lib.TraceRec * max(trace_cap, 1))()
     trace_n = np.zeros(1, np.uint64)
     p = _lib.ptr
+    pitch = (size + 3) // 4 * 4  # the device layout: rows padded to whole float4s, padding zero
+    u_in, v_in = u, v
+    if pitch != size:
+        u = np.zeros((u_in.shape[0], pitch), np.float32); u[:, :size] = u_in
+        v = np.zeros((v_in.shape[0], pitch), np.float32); v[:, :size] = v_in
     r = EmuRun(V=corpus.vocab_size, D=size, window=window, negative=negative, bitlevel=bitlevel, sample=sample,
                alpha0=alpha, iter=iters, train_words=corpus.train_words, num_shards=shards,
                opt=0, lpr=32 if plan["sentence_in_smem"] else 0, xw=0, nu=plan["queue_entries"], nv=plan["slots"], G=0, threads=32,
@@ -80,6 +85,10 @@ def train_epoch_warp(corpus, table, u, v, *, size, window, negative, bitlevel, s
     rc = lib().emu_run_warp(C.byref(r))
     if rc:
         raise EmuError(lib().emu_last_error().decode())
+    if pitch != size:
+        assert not v[:, size:].any()  # the padding of v never moves
+        u_in[:] = u[:, :size]
+        v_in[:] = v[:, :size]
     out["alpha"], out["wca"] = float(a[0]), int(wca[0])
     out["plan"] = plan
     if trace_cap:

@@ -428,7 +428,7 @@ static void emu_setup(const EmuRun *r, std::vector<w2b::ShardState> &shards, w2b
   memset(&p, 0, sizeof p);
   p.u = r->u; p.v = r->v; p.table = r->table; p.keep_thr = r->keep; p.exptab = r->exptab; p.tokens = r->tokens;
   p.shards = shards.data(); p.alpha = r->alpha; p.wca = (unsigned long long *)r->wca;
-  p.D = r->D; p.V = r->V; p.ncol = (int)(r->D / 4); p.window = r->window; p.negative = r->negative; p.bitlevel = r->bitlevel;
+  p.D = r->D; p.V = r->V; p.pitch = (r->D + 3) & ~3LL; p.ncol = (int)(p.pitch / 4); p.window = r->window; p.negative = r->negative; p.bitlevel = r->bitlevel;
   p.sample = r->sample; p.reg = r->reg; p.starting_alpha = r->alpha0;
   p.alpha_denom = (float)(r->iter * r->train_words + 1);
   p.shard_word_limit = r->train_words / r->num_shards;
@@ -451,8 +451,7 @@ int emu_run_warp(const EmuRun *r) {
   std::vector<ShardState> shards;
   TrainParams p;
   emu_setup(r, shards, p);
-  if (r->D % 4) { fail("D must be a multiple of 4"); return 1; }
-  const int nj = ((int)(r->D / 4) + 31) / 32;
+  const int nj = ((int)(p.pitch / 4) + 31) / 32;  // (u, v: rows of p.pitch floats, padding zero)
   entry_fn fn = nullptr;
   switch (r->bitlevel) {
     case 0: fn = warp_by_nj<0>(nj); break;
@@ -466,7 +465,7 @@ int emu_run_warp(const EmuRun *r) {
   g_sen_smem = r->lpr == 32 ? 1 : 0;  // r->lpr: 32 = sentence buffer in shared memory, anything else = global
   g_p = p; g_nv = r->nv; g_nu = r->nu;
   {
-    const WarpLayout L = warp_layout(r->D, r->nv, r->nu, g_sen_smem);
+    const WarpLayout L = warp_layout(p.pitch, r->nv, r->nu, g_sen_smem);
     if (L.total > sizeof(w2b::smem)) { fail("planned shared memory exceeds the emulator's buffer"); return 1; }
     g_smem_total = L.total;
     g_rows_end = (size_t)r->nv * L.rowb;  // the ring: rows of 4*D bytes from offset 0

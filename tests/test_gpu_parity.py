@@ -439,9 +439,11 @@ def test_planted_topic_quality(tmp_path):
 
 @pytest.mark.parametrize("D,W,neg,b", [(4, 1, 0, 1), (8, 2, 1, 2), (100, 5, 5, 1), (256, 20, 40, 0), (1024, 3, 7, 1),
                                          (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (12, 5, 3, 4), (800, 10, 63, 1),
-                                         (100, 5, 63, 1), (132, 64, 63, 1)])
+                                         (100, 5, 63, 1), (132, 64, 63, 1), (50, 5, 6, 1), (150, 8, 12, 2), (6, 2, 3, 0),
+                                         (250, 5, 24, 1), (3, 1, 1, 1)])
 def test_production_kernel_odd_shapes(D, W, neg, b, medium):
-    """Production kernel on edge geometries (negative=0, window 1..64, D 4..1024, > 32 negatives):
+    """Production kernel on edge geometries (negative=0, window 1..64, D 3..1024 incl. D % 4 != 0 — rows padded to whole
+    float4s on the device —, > 32 negatives):
     terminates, trains every position the oracle's trace holds, loss within 2 % of the oracle."""
     shards = 6
     c = w2b.Corpus(medium, 5)
@@ -472,7 +474,7 @@ def test_checkpoint_resume_is_exact(tmp_path, medium):
     """fp32 master tables + alpha + word counter on disk; a run resumed from the
     checkpoint after epoch 1 ends bit-identical to an uninterrupted run (strict mode)."""
     c = w2b.Corpus(medium, 5)
-    kw = dict(size=20, window=5, negative=6, bitlevel=1, threads=2, iter=2, mode=w2b.MODE_STRICT)
+    kw = dict(size=22, window=5, negative=6, bitlevel=1, threads=2, iter=2, mode=w2b.MODE_STRICT)  # (22: padded rows)
     a = w2b.Trainer(c, **kw)
     a.train_epoch(); a.train_epoch()
     b = w2b.Trainer(c, **kw)
@@ -487,7 +489,7 @@ def test_checkpoint_resume_is_exact(tmp_path, medium):
         assert np.array_equal(bits(x), bits(y))
     assert a.get_state() == r.get_state()
     with pytest.raises(w2b.W2BError):
-        w2b.Trainer(c, size=24, window=5, negative=6, threads=2).checkpoint_load(ck)  # wrong shape
+        w2b.Trainer(c, size=24, window=5, negative=6, threads=2, iter=2).checkpoint_load(ck)  # wrong shape
     for other in (dict(kw, bitlevel=2), dict(kw, iter=3)):  # another bit level / learning-rate schedule is refused
         with pytest.raises(w2b.W2BError, match="was written with"):
             w2b.Trainer(c, **other).checkpoint_load(ck)

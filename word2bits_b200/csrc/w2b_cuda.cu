@@ -107,6 +107,7 @@ enum { kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclAvg = 4 };
 struct w2b_ctx {
   w2b_config cfg;
   int nlocal = 0;  // shards owned by this context
+  long long pitch = 0;  // floats per row of u / v: layer1_size rounded up to a multiple of 4 (bulk copies move 16-byte units)
   int vec = 4, ncol = 0, threads = 0, group = 9;
   bool warp = false;       // production warp-per-shard kernel (csrc/w2b_warp.cuh) usable for this configuration
   int warp_k = 0, warp_qcap = 0, warp_minb = 0;  // ring slots per warp, job queue entries, warps per SM
@@ -150,6 +151,9 @@ struct w2b_ctx {
   int rank = 0, nranks = 1;
   long long wca_at_sync = 0;
 };
+
+static long long pitch_of(long long D) { return (D + 3) & ~3LL; }
+static size_t table_elems(const w2b_ctx *c) { return (size_t)c->cfg.vocab_size * (size_t)c->pitch; }
 
 static void lcg_tables(unsigned long long *JA, unsigned long long *JC, unsigned long long *PA,
                        unsigned long long *PC) {
@@ -230,7 +234,7 @@ static warp_fn warp_by_nj(int nj) {
 template <int NJ, int MINB>
 static warp_fn warp_reg() { return train_warp_kernel<9, NJ, MINB, 1>; }
 static warp_fn pick_warp(const w2b_ctx *c) {
-  const int nj = (c->ncol + 31) / 32;
+  const int nj = (int)((pitch_of(c->cfg.layer1_size) / 4 + 31) / 32);
   if (c->cfg.reg != 0.f)  // -reg: one instantiation per width (run-time bit level; lower occupancy: the raw row stays live)
     switch (nj) {
       case 1: return warp_reg<1, 20>();
@@ -253,8 +257,9 @@ static warp_fn pick_warp(const w2b_ctx *c) {
 // reserved shared memory); at least 3 (one row being worked on, one draining, one in flight).
 static void plan_warp(w2b_ctx *c) {
   c->warp = false;
-  if (c->cfg.mode != W2B_MODE_FAST || c->vec != 4 || c->cfg.kernel == 1) return;
-  const int nj = (c->ncol + 31) / 32;
+  if (c->cfg.mode != W2B_MODE_FAST || c->cfg.kernel == 1) return;
+  const long long pitch = pitch_of(c->cfg.layer1_size);
+  const int nj = (int)((pitch / 4 + 31) / 32);
   if (nj > 8) return;  // kernels are instantiated for D <= 1024
   const int minb = c->cfg.reg != 0.f ? (nj >= 5 ? 8 : (nj >= 3 ? 12 : (nj == 2 ? 16 : 20))) : warp_minb_of(nj);
   const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
@@ -263,15 +268,15 @@ static void plan_warp(w2b_ctx *c) {
   // below 4 (wide rows)
   int sen_smem = 1;
   int K = c->cfg.slots > 0 ? std::min(c->cfg.slots, 32) : 16;
-  while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap, sen_smem).total > budget) --K;
+  while (K >= 3 && warp_layout(pitch, K, qcap, sen_smem).total > budget) --K;
   if (K < 4 && c->cfg.slots <= 0) {
     int K2 = 16;
-    while (K2 >= 3 && warp_layout(c->cfg.layer1_size, K2, qcap, 0).total > budget) --K2;
+    while (K2 >= 3 && warp_layout(pitch, K2, qcap, 0).total > budget) --K2;
     if (K2 > K) { K = K2; sen_smem = 0; }
   } else if (K < 3) {
     sen_smem = 0;
     K = std::min(c->cfg.slots, 32);
-    while (K >= 3 && warp_layout(c->cfg.layer1_size, K, qcap, sen_smem).total > budget) --K;
+    while (K >= 3 && warp_layout(pitch, K, qcap, sen_smem).total > budget) --K;
   }
   if (K < 3) return;
   c->warp = true;
@@ -279,7 +284,7 @@ static void plan_warp(w2b_ctx *c) {
   c->warp_qcap = qcap;
   c->warp_minb = minb;
   c->warp_sen_smem = sen_smem;
-  c->warp_smem = warp_layout(c->cfg.layer1_size, K, qcap, sen_smem).total;
+  c->warp_smem = warp_layout(pitch, K, qcap, sen_smem).total;
 }
 
 static size_t dyn_smem(const w2b_ctx *c) {
@@ -299,6 +304,7 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.alpha = c->d_alpha;
   p.wca = c->d_wca;
   p.D = c->cfg.layer1_size;
+  p.pitch = c->pitch;
   p.V = c->cfg.vocab_size;
   p.ncol = c->ncol;
   p.window = c->cfg.window;
@@ -449,6 +455,7 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   c->nlocal = c->cfg.shard_end - c->cfg.shard_begin;
   c->vec = (cfg->layer1_size % 4 == 0) ? 4 : 1;
   c->ncol = (int)((cfg->layer1_size + c->vec - 1) / c->vec);
+  c->pitch = pitch_of(cfg->layer1_size);
   c->threads = std::max(32, (c->ncol + 31) / 32 * 32);
   c->group = cfg->group ? cfg->group : (cfg->negative + 1 > 9 ? 13 : (cfg->negative + 1 > 5 ? 9 : 5));
   if (c->group != 5 && c->group != 9 && c->group != 13) c->group = 9;  // register kernel instantiations
@@ -468,9 +475,13 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   CK(cudaMemcpyToSymbol(c_JC, JC, sizeof JC));
   CK(cudaMemcpyToSymbol(c_PA, PA, sizeof PA));
   CK(cudaMemcpyToSymbol(c_PC, PC, sizeof PC));
-  const size_t n = (size_t)cfg->vocab_size * cfg->layer1_size;
+  const size_t n = table_elems(c);
   CK(cudaMalloc(&c->d_u, n * sizeof(float)));
   CK(cudaMalloc(&c->d_v, n * sizeof(float)));
+  if (c->pitch != cfg->layer1_size) {  // padding columns start (and, in v, stay) at zero
+    CK(cudaMemset(c->d_u, 0, n * sizeof(float)));
+    CK(cudaMemset(c->d_v, 0, n * sizeof(float)));
+  }
   CK(cudaMalloc(&c->d_keep, cfg->vocab_size * sizeof(float)));
   CK(cudaMalloc(&c->d_exptab, kExpN * sizeof(float)));
   CK(cudaMalloc(&c->d_alpha, sizeof(float)));
@@ -554,7 +565,7 @@ extern "C" int w2b_init_tables(w2b_ctx *c) {
   CK(cudaSetDevice(c->cfg.device));
   const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
   const long long threads = (2 * n + 3) / 4;
-  init_net_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->d_v, c->d_u, n);
+  init_net_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(c->d_v, c->d_u, n, c->cfg.layer1_size, c->pitch);
   CK(cudaGetLastError());
   float t[kExpN];
   w2b_exptable(t);
@@ -1062,18 +1073,18 @@ extern "C" int w2b_set_state(w2b_ctx *c, float alpha, int64_t wca) {
 extern "C" int w2b_download_raw(w2b_ctx *c, float *u, float *v) {
   NEED(c);
   CK(cudaSetDevice(c->cfg.device));
-  const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
-  if (u) CK(cudaMemcpy(u, c->d_u, n, cudaMemcpyDeviceToHost));
-  if (v) CK(cudaMemcpy(v, c->d_v, n, cudaMemcpyDeviceToHost));
+  const size_t row = (size_t)c->cfg.layer1_size * sizeof(float), dp = (size_t)c->pitch * sizeof(float);
+  if (u) CK(cudaMemcpy2D(u, row, c->d_u, dp, row, c->cfg.vocab_size, cudaMemcpyDeviceToHost));
+  if (v) CK(cudaMemcpy2D(v, row, c->d_v, dp, row, c->cfg.vocab_size, cudaMemcpyDeviceToHost));
   return W2B_OK;
 }
 
 extern "C" int w2b_upload_raw(w2b_ctx *c, const float *u, const float *v) {
   NEED(c);
   CK(cudaSetDevice(c->cfg.device));
-  const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
-  if (u) CK(cudaMemcpy(c->d_u, u, n, cudaMemcpyHostToDevice));
-  if (v) CK(cudaMemcpy(c->d_v, v, n, cudaMemcpyHostToDevice));
+  const size_t row = (size_t)c->cfg.layer1_size * sizeof(float), dp = (size_t)c->pitch * sizeof(float);
+  if (u) CK(cudaMemcpy2D(c->d_u, dp, u, row, row, c->cfg.vocab_size, cudaMemcpyHostToDevice));
+  if (v) CK(cudaMemcpy2D(c->d_v, dp, v, row, row, c->cfg.vocab_size, cudaMemcpyHostToDevice));
   return W2B_OK;
 }
 
@@ -1123,18 +1134,20 @@ static int w2b_checkpoint_save_impl(w2b_ctx *c, const char *path, int64_t epochs
   FILE *f = fopen(tmp.c_str(), "wb");
   if (!f) { w2b_set_error("cannot open %s for writing", tmp.c_str()); return W2B_EIO; }
   bool ok = fwrite(&h, sizeof h, 1, f) == 1;
-  const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
-  std::vector<float> buf(std::min(n, piece));
+  // the file holds V x D contiguous floats per table whatever the row pitch on the device: whole rows per piece
+  const size_t D = (size_t)h.D, rows_per_piece = std::max<size_t>(1, (16u << 20) / D);
+  std::vector<float> buf(std::min((size_t)h.V, rows_per_piece) * D);
   for (const float *src : {c->d_u, c->d_v})
-    for (size_t o = 0; o < n && ok; o += piece) {
-      const size_t k = std::min(piece, n - o);
-      if (cudaMemcpy(buf.data(), src + o, k * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    for (size_t r0 = 0; r0 < (size_t)h.V && ok; r0 += rows_per_piece) {
+      const size_t nr = std::min(rows_per_piece, (size_t)h.V - r0);
+      if (cudaMemcpy2D(buf.data(), D * sizeof(float), src + r0 * c->pitch, (size_t)c->pitch * sizeof(float),
+                       D * sizeof(float), nr, cudaMemcpyDeviceToHost) != cudaSuccess) {
         fclose(f);
         remove(tmp.c_str());
         w2b_set_error("checkpoint download failed");
         return W2B_ECUDA;
       }
-      ok = fwrite(buf.data(), sizeof(float), k, f) == k;
+      ok = fwrite(buf.data(), sizeof(float), nr * D, f) == nr * D;
     }
   if (ok && fflush(f) != 0) ok = false;
   if (ok && fsync(fileno(f)) != 0) ok = false;
@@ -1169,13 +1182,14 @@ static int w2b_checkpoint_load_impl(w2b_ctx *c, const char *path, int64_t *epoch
                   (long long)c->cfg.iter, (long long)c->train_words);
     return W2B_EINVAL;
   }
-  const size_t n = (size_t)h.V * h.D, piece = 16u << 20;
-  std::vector<float> buf(std::min(n, piece));
+  const size_t D = (size_t)h.D, rows_per_piece = std::max<size_t>(1, (16u << 20) / D);
+  std::vector<float> buf(std::min((size_t)h.V, rows_per_piece) * D);
   for (float *dst : {c->d_u, c->d_v})
-    for (size_t o = 0; o < n; o += piece) {
-      const size_t k = std::min(piece, n - o);
-      if (fread(buf.data(), sizeof(float), k, f) != k ||
-          cudaMemcpy(dst + o, buf.data(), k * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    for (size_t r0 = 0; r0 < (size_t)h.V; r0 += rows_per_piece) {
+      const size_t nr = std::min(rows_per_piece, (size_t)h.V - r0);
+      if (fread(buf.data(), sizeof(float), nr * D, f) != nr * D ||
+          cudaMemcpy2D(dst + r0 * c->pitch, (size_t)c->pitch * sizeof(float), buf.data(), D * sizeof(float),
+                       D * sizeof(float), nr, cudaMemcpyHostToDevice) != cudaSuccess) {
         fclose(f);
         w2b_set_error("checkpoint %s is truncated or the upload failed", path);
         return W2B_EIO;
@@ -1195,7 +1209,7 @@ extern "C" int w2b_export(w2b_ctx *c, float *out) {
   DevTmp t_out;
   CK(t_out.alloc(n * sizeof(float)));
   float *d_out = t_out.as<float>();
-  export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, c->d_v, d_out, n, c->cfg.bitlevel);
+  export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, c->d_v, d_out, n, c->cfg.layer1_size, c->pitch, c->cfg.bitlevel);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1224,7 +1238,7 @@ extern "C" int w2b_device_ptrs(w2b_ctx *c, void **u, void **v, int64_t *elems) {
   NEED(c);
   if (u) *u = c->d_u;
   if (v) *v = c->d_v;
-  if (elems) *elems = c->cfg.vocab_size * c->cfg.layer1_size;
+  if (elems) *elems = (int64_t)table_elems(c);  // rows of pitch = round_up(layer1_size, 4) floats
   return W2B_OK;
 }
 
@@ -1254,7 +1268,7 @@ extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks
   c->rank = rank;
   c->nranks = nranks;
   if (c->cfg.sync_mode == 1) {  // sum of deltas: remember the common starting point (same InitNet / checkpoint on every rank)
-    const size_t bytes = (size_t)c->cfg.vocab_size * c->cfg.layer1_size * sizeof(float);
+    const size_t bytes = table_elems(c) * sizeof(float);
     if (!c->d_base_u) CK(cudaMalloc(&c->d_base_u, bytes));
     if (!c->d_base_v) CK(cudaMalloc(&c->d_base_v, bytes));
     CK(cudaMemcpy(c->d_base_u, c->d_u, bytes, cudaMemcpyDeviceToDevice));
@@ -1266,7 +1280,7 @@ extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks
 extern "C" int w2b_scale_tables(w2b_ctx *c, float s) {
   NEED(c);
   CK(cudaSetDevice(c->cfg.device));
-  const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
+  const long long n = (long long)table_elems(c);
   scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_u, n, s);
   scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_v, n, s);
   CK(cudaGetLastError());
@@ -1316,7 +1330,7 @@ extern "C" int w2b_sync_timed(w2b_ctx *c, float *ms) {
   if (c->nranks <= 1) return W2B_OK;
   if (!c->comm) { w2b_set_error("w2b_nccl_init first"); return W2B_ESTATE; }
   CK(cudaSetDevice(c->cfg.device));
-  const size_t n = (size_t)c->cfg.vocab_size * c->cfg.layer1_size;
+  const size_t n = table_elems(c);
   const bool sum = c->cfg.sync_mode == 1;
   if (sum && !c->d_base_u) {  // first exchange: every rank still holds the common starting point in `base`
     w2b_set_error("w2b_sync: sync_mode 1 needs w2b_nccl_init after the tables were initialised");
@@ -1360,7 +1374,7 @@ extern "C" int w2b_table_checksum(w2b_ctx *c, uint64_t *u_sum, uint64_t *v_sum) 
   NEED(u_sum);
   NEED(v_sum);
   CK(cudaSetDevice(c->cfg.device));
-  const long long n = c->cfg.vocab_size * c->cfg.layer1_size;
+  const long long n = (long long)table_elems(c);
   DevTmp t;
   CK(t.alloc(16));
   CK(cudaMemsetAsync(t.p, 0, 16, c->stream));

@@ -65,7 +65,8 @@ struct TrainParams {
   float *alpha;                 // shared learning rate (:53), racy like the reference
   unsigned long long *wca;      // word_count_actual (:51)
   long long D, V;
-  int ncol;                     // threads that own columns = ceil(D / VEC)
+  long long pitch;              // floats between two rows of u / v: D, rounded up to a multiple of 4 (16-byte rows)
+  int ncol;                     // register kernel: threads that own columns = ceil(D / VEC)
   int window, negative, bitlevel;
   float sample, reg, starting_alpha, alpha_denom;  // alpha_denom = (float)(iter*train_words+1)
   long long shard_word_limit;   // train_words / num_shards (:414)
@@ -314,7 +315,7 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
     Vec<VEC> x[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k)
-      if (k0 + k < cw && active) x[k].load(p.u + (long long)d->ctx[k0 + k] * D + col);
+      if (k0 + k < cw && active) x[k].load(p.u + (long long)d->ctx[k0 + k] * p.pitch + col);
 #pragma unroll
     for (int k = 0; k < CB; ++k) {
       if (k0 + k < cw) {
@@ -349,7 +350,7 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
     Vec<VEC> x[GG];
 #pragma unroll
     for (int k = 0; k < GG; ++k)
-      if (k < ng && active) x[k].load(p.v + (long long)d->tg[g0 + k] * D + col);
+      if (k < ng && active) x[k].load(p.v + (long long)d->tg[g0 + k] * p.pitch + col);
     float fs = 0.f, qs = 0.f;  // strict mode: the single target's sums
     if (STRICT) {
       if (active)
@@ -451,7 +452,7 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
             }
             upd.a[i] = (STRICT || p.plain_store) ? __fadd_rn(x[k].a[i], dv) : dv;
           }
-          float *row = p.v + (long long)d->tg[g0 + k] * D + col;
+          float *row = p.v + (long long)d->tg[g0 + k] * p.pitch + col;
           if (STRICT || p.plain_store) upd.store(row);
           else upd.red_add(row);
         }
@@ -462,7 +463,7 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
   // ---- scatter the accumulated error to every context row (:494-503)
   if (active) {
     for (int k = 0; k < cw; ++k) {
-      float *row = p.u + (long long)d->ctx[k] * D + col;
+      float *row = p.u + (long long)d->ctx[k] * p.pitch + col;
       if (STRICT || HAS_REG || p.plain_store) {
         Vec<VEC> x;
         x.load(row);
@@ -637,8 +638,9 @@ __global__ void apply_position_kernel(TrainParams p, const int *ctx, int cw, con
 }
 
 // ------------------------------------------------------------------- auxiliary kernels
-// InitNet (:343-361): element e (v first, then u) takes draw e+1 of the LCG seeded with 1.
-__global__ void init_net_kernel(float *v, float *u, long long n) {
+// InitNet (:343-361): element e (v first, then u) takes draw e+1 of the LCG seeded with 1.  n = V*D elements per table;
+// element (row, col) is stored at row*pitch + col (padding columns, if any, stay zero).
+__global__ void init_net_kernel(float *v, float *u, long long n, long long D, long long pitch) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long e0 = t * 4;
   if (e0 >= 2 * n) return;
@@ -648,8 +650,10 @@ __global__ void init_net_kernel(float *v, float *u, long long n) {
     if (e >= 2 * n) break;
     r = lcg(r);
     float val = __fsub_rn((float)(r & 0xFFFFull) / 65536.0f, 0.5f);
-    if (e < n) v[e] = val;
-    else u[e - n] = val;
+    const long long x = e < n ? e : e - n;
+    const long long at = pitch == D ? x : (x / D) * pitch + x % D;
+    if (e < n) v[at] = val;
+    else u[at] = val;
   }
 }
 
@@ -665,13 +669,15 @@ __global__ void fill_table_kernel(int *table, const int *start, int V) {
   table[a] = lo;
 }
 
-// quantize(u+v), :568-569
-__global__ void export_kernel(const float *u, const float *v, float *out, long long n, int bits) {
+// quantize(u+v), :568-569; out is V x D contiguous, u and v have rows of `pitch` floats
+__global__ void export_kernel(const float *u, const float *v, float *out, long long n, long long D, long long pitch, int bits) {
   QParams qp;
   qp.bits = bits;
   qp.seg = (bits >= 4) ? exp2f((float)(bits - 1)) : 1.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = quant<9>(__fadd_rn(u[i], v[i]), qp);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long at = pitch == D ? i : (i / D) * pitch + i % D;
+    out[i] = quant<9>(__fadd_rn(u[at], v[at]), qp);
+  }
 }
 
 __global__ void quantize_kernel(const float *in, float *out, long long n, int bits) {

@@ -330,14 +330,14 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
   const int qcap = qcap_sen & 0x7fffffff, sen_smem = (qcap_sen >> 31) & 1;  // top bit: sentence in shared memory
-  const WarpLayout L = warp_layout(p.D, K, qcap, sen_smem);
+  const WarpLayout L = warp_layout(p.pitch, K, qcap, sen_smem);
   const unsigned s_base = smem_u32(smem);
   const unsigned ring = s_base + (unsigned)L.off_ring;
   const unsigned bars = s_base + (unsigned)L.off_bar;
   int *jobq = reinterpret_cast<int *>(smem + L.off_jobq);
   const int qmask = qcap - 1;
   const unsigned rowb = (unsigned)L.rowb;
-  const int D4 = p.ncol;
+  const int D4 = (int)(p.pitch >> 2);  // float4 columns of a row
   const int shard = p.shard_base + blockIdx.x;
   ShardState *shp = p.shards + shard;
   if (!ap.ctx && shp->done) return;
@@ -360,6 +360,9 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
   const unsigned lane16 = (unsigned)lane * 16u;
   const bool on_last = (NJ - 1) * 32 + lane < D4;
   const unsigned coff_last = (unsigned)(on_last ? (NJ - 1) * 32 + lane : D4 - 1) * 16u;
+  // D % 4 != 0: rows are padded to whole float4s; the lane that holds the last float4 keeps only its first `tail`
+  // components of context_avg (the padding must not enter a dot product: quantize(0) is a level, not zero)
+  const int tail = ((NJ - 1) * 32 + lane == D4 - 1) ? (int)(p.D & 3) : 0;
 #define W2B_COFF(j) ((j) < NJ - 1 ? lane16 + (unsigned)(j) * 512u : coff_last)
 
   const ShardState &sh = *shp;
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     const int e = jobq[q_issue & qmask];
     if (lane == 0) {
       if (e >= 0) {
-        const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
+        const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.pitch : p.u + (long long)e * p.pitch;
         mbar_expect_tx(i_bar, rowb);
         bulk_load(i_row, src, rowb, i_bar);
       } else {
@@ -416,12 +419,12 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     const int e = can ? jobq[q_issue & qmask] : -1;
     if (lane == 0) {
       if (dst) bulk_reduce_add(dst, c_row, rowb);
-      else for (int k = 0; k < n_dst; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.D, c_row, rowb);
+      else for (int k = 0; k < n_dst; ++k) bulk_reduce_add(p.u + (long long)jobq[(q0 + k) & qmask] * p.pitch, c_row, rowb);
       bulk_commit();
       bulk_wait_read<1>();
       if (can) {
         if (e >= 0) {
-          const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.D : p.u + (long long)e * p.D;
+          const float *src = (e & kJobTarget) ? p.v + (long long)(e & kJobIdMask) * p.pitch : p.u + (long long)e * p.pitch;
           mbar_expect_tx(i_bar, rowb);
           bulk_load(i_row, src, rowb, i_bar);
         } else {
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     float regsum = 0.f;                                    // REG: sum of squared quantized values this lane saw
     const float decay = REG ? -2.f * alpha * p.reg : 0.f;  // REG: row += decay * row
     for (int k = 0; k < cw; ++k) {
-      float *urow = REG ? p.u + (long long)jobq[q_cons & qmask] * p.D : nullptr;
+      float *urow = REG ? p.u + (long long)jobq[q_cons & qmask] * p.pitch : nullptr;
       mbar_wait(c_bar, c_par);
       float4 x[NJ];
 #pragma unroll
@@ -484,7 +487,9 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
           a[j][0] = add2(a[j][0], F2{xq.x, xq.y});
           a[j][1] = add2(a[j][1], F2{xq.z, xq.w});
           if ((j < NJ - 1) || on_last) {
-            regsum += (xq.x * xq.x + xq.y * xq.y) + (xq.z * xq.z + xq.w * xq.w);
+            const bool tl = tail && j == NJ - 1;  // padding components do not count
+            regsum += (xq.x * xq.x + ((tl && tail < 2) ? 0.f : xq.y * xq.y)) +
+                      (((tl && tail < 3) ? 0.f : xq.z * xq.z) + (tl ? 0.f : xq.w * xq.w));
             sts128(c_row + W2B_COFF(j), make_float4(decay * x[j].x, decay * x[j].y, decay * x[j].z, decay * x[j].w));
           }
         }
@@ -510,6 +515,11 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
 #pragma unroll
         for (int h = 0; h < 2; ++h) a[j][h] = on ? div_by_count(a[j][h], fcw, rc) : F2{0.f, 0.f};
       }
+      if (tail) {  // (tail lanes are in the last column group)
+        if (tail < 2) a[NJ - 1][0].y = 0.f;
+        if (tail < 3) a[NJ - 1][1].x = 0.f;
+        a[NJ - 1][1].y = 0.f;
+      }
     }
 
     // ---- target jobs (:450-492)
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
     for (int j = 0; j < NJ; ++j) e[j][0] = e[j][1] = F2{0.f, 0.f};
     float myf0 = 0.f, myf1 = 0.f;  // lane i keeps +-f of targets i and 32+i for the reported loss (:480-483)
     for (int i = 0; i < nt; ++i) {
-      float *dst = p.v + (long long)(jobq[q_cons & qmask] & kJobIdMask) * p.D;
+      float *dst = p.v + (long long)(jobq[q_cons & qmask] & kJobIdMask) * p.pitch;
       mbar_wait(c_bar, c_par);
       float4 x[NJ];
 #pragma unroll
@@ -532,8 +542,11 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
                            quant_fast<BM>(x[j].w, qp));
         d0 = fma2(a[j][0], F2{x[j].x, x[j].y}, d0);
         d1 = fma2(a[j][1], F2{x[j].z, x[j].w}, d1);
-        if (REG && ((j < NJ - 1) || on_last))
-          regsum += (x[j].x * x[j].x + x[j].y * x[j].y) + (x[j].z * x[j].z + x[j].w * x[j].w);
+        if (REG && ((j < NJ - 1) || on_last)) {
+          const bool tl = tail && j == NJ - 1;
+          regsum += (x[j].x * x[j].x + ((tl && tail < 2) ? 0.f : x[j].y * x[j].y)) +
+                    (((tl && tail < 3) ? 0.f : x[j].z * x[j].z) + (tl ? 0.f : x[j].w * x[j].w));
+        }
       }
       float f = (d0.x + d0.y) + (d1.x + d1.y);
 #pragma unroll
