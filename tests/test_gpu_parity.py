@@ -311,7 +311,7 @@ def test_fast_streaming_and_steps(large):
 
 
 @pytest.mark.parametrize("kernel,prefetch", [(1, 0), (0, 0), (0, 1)])
-@pytest.mark.parametrize("b,D", [(0, 64), (0, 200), (2, 64), (0, 800)])
+@pytest.mark.parametrize("b,D", [(0, 64), (0, 200), (2, 64), (0, 800), (0, 50)])
 def test_fast_single_shard_tracks_oracle(kernel, prefetch, b, D, medium):
     """One shard, positions in order (register kernel; production kernel in its default mode): the
     production arithmetic (FMA, shuffle-tree dot, atomic-add scatter) must stay close to the
