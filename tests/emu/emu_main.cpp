@@ -340,6 +340,9 @@ entry_fn warp_by_nj(int nj) {
     case 6: return warp_entry<BM, 6>;
     case 7: return warp_entry<BM, 7>;
     case 8: return warp_entry<BM, 8>;
+    case 10: return warp_entry<BM, 10>;
+    case 12: return warp_entry<BM, 12>;
+    case 16: return warp_entry<9, 16>;
   }
   return nullptr;
 }

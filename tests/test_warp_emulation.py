@@ -58,6 +58,7 @@ SHAPES = [  # D, window, negative, bitlevel, shards — BASELINE shapes, wide wi
     (800, 10, 24, 1, 2), (400, 10, 12, 2, 2), (400, 10, 24, 0, 2), (200, 8, 24, 1, 3), (100, 5, 63, 1, 2),
     (64, 30, 12, 0, 2), (8, 2, 1, 2, 2), (4, 1, 0, 1, 2), (1024, 3, 7, 5, 1), (132, 64, 63, 1, 1),
     (50, 5, 6, 1, 2), (150, 5, 6, 2, 1), (6, 2, 3, 0, 2), (257, 5, 6, 1, 1), (3, 1, 1, 1, 1),  # D % 4 != 0: padded rows
+    (1200, 5, 6, 1, 1), (1530, 3, 4, 0, 1), (2048, 2, 3, 2, 1),  # wider than 1024 floats (the reference publishes D = 1200)
 ]
 
 
@@ -149,7 +150,7 @@ def test_plan_fits_an_sm():
     """Planner invariants over the shapes it accepts: K >= 3 slots, the job queue holds two positions, and the
     warps the register allocation is sized for fit the SM's 228 KB with 1 KB reserved per CTA."""
     n = 0
-    for D in list(range(4, 1025, 4)) + [1, 2, 3, 50, 150, 1021]:
+    for D in list(range(4, 1025, 4)) + [1, 2, 3, 50, 150, 1021, 1200, 1536, 1900, 2048]:
         for W, neg in ((1, 0), (5, 5), (10, 24), (64, 63), (8, 24), (30, 12)):
             p = w2b.warp_plan(size=D, window=W, negative=neg)
             assert p["warp"] == 1, (D, W, neg)
@@ -158,7 +159,7 @@ def test_plan_fits_an_sm():
             assert p["warps_per_sm"] % 4 == 0
             assert p["warps_per_sm"] * (p["smem_bytes"] + 1024) <= 228 * 1024
             n += 1
-    assert n == (256 + 6) * 6
-    assert w2b.warp_plan(size=1028, window=5, negative=5)["warp"] == 0   # wider than the instantiated kernels
+    assert n == (256 + 10) * 6
+    assert w2b.warp_plan(size=2052, window=5, negative=5)["warp"] == 0   # wider than the instantiated kernels
     assert w2b.warp_plan(size=6, window=5, negative=5)["smem_bytes"] == w2b.warp_plan(size=8, window=5, negative=5)["smem_bytes"]  # rows padded to 16 bytes
     assert w2b.warp_plan(size=64, window=5, negative=5, reg=0.1)["warps_per_sm"] == 20  # -reg: own instantiations

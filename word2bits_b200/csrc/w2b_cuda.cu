@@ -216,7 +216,9 @@ typedef void (*warp_fn)(TrainParams, int, int, ApplyArgs);
 // warps (= 1-warp CTAs) per SM the register allocation is sized for; multiples of 4 because the register file is
 // split over the four SM sub-partitions: 12 warps -> 168 registers per thread, 16 -> 128, 20 -> 96, 24 -> 80.
 // Measured (profiles/r02_warp_sweep_more_warps.md): one step denser is 2-11 % slower, except for the narrowest rows.
-static int warp_minb_of(int nj) { return nj >= 5 ? 12 : (nj >= 3 ? 16 : (nj == 2 ? 20 : 24)); }
+// Rows wider than 1024 floats (the reference publishes 1200-dimensional vectors): 8 warps (216 registers) up to
+// 1536 floats, 4 warps (248 registers) up to 2048.
+static int warp_minb_of(int nj) { return nj >= 13 ? 4 : (nj >= 9 ? 8 : (nj >= 5 ? 12 : (nj >= 3 ? 16 : (nj == 2 ? 20 : 24)))); }
 template <int BM>
 static warp_fn warp_by_nj(int nj) {
   switch (nj) {
@@ -228,6 +230,14 @@ static warp_fn warp_by_nj(int nj) {
     case 6: return train_warp_kernel<BM, 6, 12>;
     case 7: return train_warp_kernel<BM, 7, 12>;
     case 8: return train_warp_kernel<BM, 8, 12>;
+    case 9: return train_warp_kernel<BM, 9, 8>;
+    case 10: return train_warp_kernel<BM, 10, 8>;
+    case 11: return train_warp_kernel<BM, 11, 8>;
+    case 12: return train_warp_kernel<BM, 12, 8>;
+    case 13: return train_warp_kernel<9, 13, 4>;  // (run-time bit level beyond 1536 floats: fewer instantiations)
+    case 14: return train_warp_kernel<9, 14, 4>;
+    case 15: return train_warp_kernel<9, 15, 4>;
+    case 16: return train_warp_kernel<9, 16, 4>;
   }
   return nullptr;
 }
@@ -245,6 +255,14 @@ static warp_fn pick_warp(const w2b_ctx *c) {
       case 6: return warp_reg<6, 8>();
       case 7: return warp_reg<7, 8>();
       case 8: return warp_reg<8, 8>();
+      case 9: return warp_reg<9, 4>();
+      case 10: return warp_reg<10, 4>();
+      case 11: return warp_reg<11, 4>();
+      case 12: return warp_reg<12, 4>();
+      case 13: return warp_reg<13, 4>();
+      case 14: return warp_reg<14, 4>();
+      case 15: return warp_reg<15, 4>();
+      case 16: return warp_reg<16, 4>();
     }
   switch (bm_of(c->cfg.bitlevel)) {
     case 0: return warp_by_nj<0>(nj);
@@ -260,8 +278,8 @@ static void plan_warp(w2b_ctx *c) {
   if (c->cfg.mode != W2B_MODE_FAST || c->cfg.kernel == 1) return;
   const long long pitch = pitch_of(c->cfg.layer1_size);
   const int nj = (int)((pitch / 4 + 31) / 32);
-  if (nj > 8) return;  // kernels are instantiated for D <= 1024
-  const int minb = c->cfg.reg != 0.f ? (nj >= 5 ? 8 : (nj >= 3 ? 12 : (nj == 2 ? 16 : 20))) : warp_minb_of(nj);
+  if (nj > 16) return;  // kernels are instantiated for D <= 2048
+  const int minb = c->cfg.reg != 0.f ? (nj >= 9 ? 4 : (nj >= 5 ? 8 : (nj >= 3 ? 12 : (nj == 2 ? 16 : 20)))) : warp_minb_of(nj);
   const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
   const size_t budget = (size_t)(228 * 1024) / minb - 1024;
   // the sentence buffer (4000 B) moves to global memory when keeping it in shared memory would cost ring slots
@@ -349,8 +367,11 @@ static int validate(const w2b_config *c) {
   if (c->num_shards < 1) { w2b_set_error("num_shards must be >= 1"); return W2B_EINVAL; }
   if (c->iter < 1) { w2b_set_error("iter must be >= 1"); return W2B_EINVAL; }
   const long long D = c->layer1_size;
-  if ((D % 4 == 0 && D / 4 > 1024) || (D % 4 != 0 && D > 1024)) {
-    w2b_set_error("layer1_size %lld unsupported (max 4096 when divisible by 4, else 1024)", D);
+  // production kernel: any D <= 2048 (rows padded to whole float4s); register kernel: D <= 4096 when divisible by 4
+  // (a thread per float4), else D <= 1024 (a thread per float) — strict mode and kernel = 1 always run the latter
+  const bool reg_kernel = c->mode == W2B_MODE_STRICT || c->kernel == 1 || D > 2048;
+  if (D > 4096 || (reg_kernel && D % 4 != 0 && D > 1024)) {
+    w2b_set_error("layer1_size %lld unsupported (max 2048; 4096 when divisible by 4; strict mode / kernel 1: 1024 unless divisible by 4)", D);
     return W2B_EINVAL;
   }
   return W2B_OK;
