@@ -107,8 +107,9 @@ def test_single_step(b, D, reg, medium):
         tg = rng.choice(np.arange(1, V), 25, replace=False).astype(np.int32)
         f_gpu = t.apply_position(ctx, tg)
         f_cpu, _ = m.apply_position(ctx, tg)
-        # f within 1e-5 relative (reduction order only)
-        assert np.allclose(f_gpu, f_cpu, rtol=1e-5, atol=1e-6)
+        # f within 1e-5 relative (reduction order only; twice that beyond 1024 terms per dot product)
+        k = max(1, D // 1024)
+        assert np.allclose(f_gpu, f_cpu, rtol=k * 1e-5, atol=k * 1e-6)
         u, v = t.download_raw()
         touched_v = np.zeros(V, bool); touched_v[tg] = True
         touched_u = np.zeros(V, bool); touched_u[ctx] = True
@@ -309,6 +310,41 @@ def test_fast_streaming_and_steps(large):
         assert st["shards_done"] == 12
         tot.append((words, pos))
     assert tot[0] == tot[1]
+
+
+def test_set_corpus_validates_and_can_be_repeated(medium):
+    """The kernels use token ids as row indices and shard starts as stream offsets: w2b_set_corpus refuses ids outside
+    the vocabulary and starts outside the stream (W2B_EINVAL, nothing uploaded).  Switching a context between
+    resident and streaming corpora, and setting a streaming corpus twice, keeps working (the staging buffers of the
+    previous stream are not reused blindly)."""
+    c = w2b.Corpus(medium, 5)
+    S = 4
+    t = w2b.Trainer(c, size=32, window=5, negative=6, bitlevel=1, threads=S, iter=1)
+    start, first = c.shards(S)
+    bad = np.array(c.tokens, np.int32).copy()
+    bad[len(bad) // 2] = c.vocab_size
+    with pytest.raises(w2b.W2BError, match="token id"):
+        t.set_corpus(bad, start, first, True)
+    bad[len(bad) // 2] = -3
+    with pytest.raises(w2b.W2BError, match="token id"):
+        t.set_corpus(bad, start, first, False)
+    s2 = np.array(start, np.int64).copy()
+    s2[-1] = len(c.tokens) + 5
+    with pytest.raises(w2b.W2BError, match="outside the stream"):
+        t.set_corpus(c.tokens, s2, first, True)
+    totals = []
+    for resident in (False, False, True, False):
+        t.set_corpus(c.tokens, start, first, resident)
+        words = 0
+        for _ in range(1000):
+            st = t.train_step(3000)
+            words += st["words"]
+            if st["shards_done"] == S:
+                break
+        assert st["shards_done"] == S
+        totals.append(words)
+    assert len(set(totals)) == 1 and totals[0] > 0
+    t.close()
 
 
 @pytest.mark.parametrize("kernel,prefetch", [(1, 0), (0, 0), (0, 1)])
