@@ -27,8 +27,8 @@ extern "C" {
 
 #define W2B_TABLE_SIZE 100000000 /* table_size, :60 */
 #define W2B_MAX_SENTENCE 1000    /* MAX_SENTENCE_LENGTH, :32 */
-#define W2B_MAX_WINDOW 64
-#define W2B_MAX_NEGATIVE 63
+#define W2B_MAX_WINDOW 512   /* a sentence has at most 1000 words (:32): beyond ~500 every word is context anyway */
+#define W2B_MAX_NEGATIVE 63   /* 1 + negative targets per position fit one 64-entry trace record / two lanes-worth of loss terms */
 
 #define W2B_MODE_FAST 0   /* production: one warp per shard, all shards concurrent (Hogwild) */
 #define W2B_MODE_STRICT 1 /* parity: shards one after another, sequential IEEE op order */

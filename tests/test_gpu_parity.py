@@ -477,9 +477,10 @@ def test_planted_topic_quality(tmp_path):
 @pytest.mark.parametrize("D,W,neg,b", [(4, 1, 0, 1), (8, 2, 1, 2), (100, 5, 5, 1), (256, 20, 40, 0), (1024, 3, 7, 1),
                                          (300, 10, 63, 2), (800, 10, 24, 1), (64, 30, 12, 1), (12, 5, 3, 4), (800, 10, 63, 1),
                                          (100, 5, 63, 1), (132, 64, 63, 1), (50, 5, 6, 1), (150, 8, 12, 2), (6, 2, 3, 0),
-                                         (250, 5, 24, 1), (3, 1, 1, 1), (1200, 5, 12, 1), (1530, 3, 4, 0), (2048, 2, 3, 2)])
+                                         (250, 5, 24, 1), (3, 1, 1, 1), (1200, 5, 12, 1), (1530, 3, 4, 0), (2048, 2, 3, 2),
+                                         (64, 200, 10, 1), (32, 512, 63, 1), (800, 300, 24, 1)])
 def test_production_kernel_odd_shapes(D, W, neg, b, medium):
-    """Production kernel on edge geometries (negative=0, window 1..64, D 3..2048 incl. D % 4 != 0 — rows padded to whole
+    """Production kernel on edge geometries (negative=0, window 1..512 — as wide as a sentence —, D 3..2048 incl. D % 4 != 0 — rows padded to whole
     float4s on the device — and the reference's published 1200 dimensions, > 32 negatives):
     terminates, trains every position the oracle's trace holds, loss within 2 % of the oracle."""
     shards = 6

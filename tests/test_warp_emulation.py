@@ -59,6 +59,7 @@ SHAPES = [  # D, window, negative, bitlevel, shards — BASELINE shapes, wide wi
     (64, 30, 12, 0, 2), (8, 2, 1, 2, 2), (4, 1, 0, 1, 2), (1024, 3, 7, 5, 1), (132, 64, 63, 1, 1),
     (50, 5, 6, 1, 2), (150, 5, 6, 2, 1), (6, 2, 3, 0, 2), (257, 5, 6, 1, 1), (3, 1, 1, 1, 1),  # D % 4 != 0: padded rows
     (1200, 5, 6, 1, 1), (1530, 3, 4, 0, 1), (2048, 2, 3, 2, 1),  # wider than 1024 floats (the reference publishes D = 1200)
+    (64, 200, 10, 1, 1), (16, 512, 63, 1, 1),  # windows as wide as a sentence
 ]
 
 

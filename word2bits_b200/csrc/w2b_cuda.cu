@@ -281,26 +281,28 @@ static void plan_warp(w2b_ctx *c) {
   if (nj > 16) return;  // kernels are instantiated for D <= 2048
   const int minb = c->cfg.reg != 0.f ? (nj >= 9 ? 4 : (nj >= 5 ? 8 : (nj >= 3 ? 12 : (nj == 2 ? 16 : 20)))) : warp_minb_of(nj);
   const int qcap = warp_queue_capacity(c->cfg.window, c->cfg.negative);
-  const size_t budget = (size_t)(228 * 1024) / minb - 1024;
   // the sentence buffer (4000 B) moves to global memory when keeping it in shared memory would cost ring slots
-  // below 4 (wide rows)
-  int sen_smem = 1;
-  int K = c->cfg.slots > 0 ? std::min(c->cfg.slots, 32) : 16;
-  while (K >= 3 && warp_layout(pitch, K, qcap, sen_smem).total > budget) --K;
-  if (K < 4 && c->cfg.slots <= 0) {
-    int K2 = 16;
-    while (K2 >= 3 && warp_layout(pitch, K2, qcap, 0).total > budget) --K2;
-    if (K2 > K) { K = K2; sen_smem = 0; }
-  } else if (K < 3) {
-    sen_smem = 0;
-    K = std::min(c->cfg.slots, 32);
+  // below 4 (wide rows); a job queue too large for the warp's share of shared memory (very wide windows) is paid
+  // for with fewer resident warps (the kernel compiled for `minb` warps runs at any lower occupancy)
+  int sen_smem = 1, K = 0, wps = minb;
+  for (; wps >= 4; wps -= 4) {
+    const size_t budget = (size_t)(228 * 1024) / wps - 1024;
+    sen_smem = 1;
+    K = c->cfg.slots > 0 ? std::min(c->cfg.slots, 32) : 16;
     while (K >= 3 && warp_layout(pitch, K, qcap, sen_smem).total > budget) --K;
+    if (K < 4) {
+      int K2 = c->cfg.slots > 0 ? std::min(c->cfg.slots, 32) : 16;
+      while (K2 >= 3 && warp_layout(pitch, K2, qcap, 0).total > budget) --K2;
+      if (K2 > K) { K = K2; sen_smem = 0; }
+    }
+    if (K >= 3) break;
   }
-  if (K < 3) return;
+  if (wps < 4 || K < 3) return;
+  const int minb_eff = wps;
   c->warp = true;
   c->warp_k = K;
   c->warp_qcap = qcap;
-  c->warp_minb = minb;
+  c->warp_minb = minb_eff;
   c->warp_sen_smem = sen_smem;
   c->warp_smem = warp_layout(pitch, K, qcap, sen_smem).total;
 }
