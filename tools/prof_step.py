@@ -12,7 +12,7 @@ kernel = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 words = int(sys.argv[5]) if len(sys.argv) > 5 else 1500
 V, N = 400000, 24_000_000
 ids, cn = synth(V, N)
-t = w2b.Trainer(None, vocab_size=V + 1, size=D, window=10, negative=neg, bitlevel=b, iter=1, kernel=kernel)
+t = w2b.Trainer(None, vocab_size=V + 1, size=D, window=10 if D != 200 else 8, negative=neg, bitlevel=b, iter=1, kernel=kernel)
 S = t.threads
 t.set_vocab_counts(cn, N)
 t.set_corpus(ids, np.arange(S, dtype=np.int64) * (N // S), np.full(S, -1, np.int32), True)
