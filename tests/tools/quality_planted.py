@@ -49,4 +49,5 @@ if os.path.exists(ref):
     run("reference -threads 16", ref, ["-threads", "16"])
 run("gpu default shards", ours, [])
 run("gpu -threads 16", ours, ["-threads", "16"])
-run("gpu -threads 1184", ours, ["-threads", "1184"])
+run("gpu -threads 148", ours, ["-threads", "148"])
+run("gpu -threads 2960", ours, ["-threads", "2960"])
