@@ -457,7 +457,8 @@ def main():
                "ms_per_sync": a["sync_ms"] / max(a["syncs"], 1),
                "bytes_per_sync": 2 * (V + 1) * D * 4,
                "allreduce_bus_gbs": (2.0 * (world - 1) / world) * (2 * (V + 1) * D * 4) / 1e9 / max(a["sync_ms"] / max(a["syncs"], 1) / 1e3, 1e-9),
-               "what": "one NCCL group: ncclAllReduce(avg) of u and of v in place + the exact global word counter, on the training stream (device time incl. waiting for the slowest rank)",
+               "what": "one NCCL group: ncclAllReduce(%s) of u and of v in place + the exact global word counter, on the training stream (device time incl. waiting for the slowest rank)" % (
+                   "sum of each rank's updates since the last exchange, added to the common base" if args.sync_mode == "sum" else "avg"),
                "sync_check": {"replicas_bit_identical_after_sync": bool(a["replicas_identical"])}},
            "roofline": roof, "e2e": e2e, "clocks": a["clocks"], "gpu_launches": int(a["launches"]),
            "mean_loss_per_position": a["loss"] / max(a["positions"], 1)}

@@ -6,7 +6,8 @@
 //                shard count that fills the GPU is used instead of the reference's 12.
 //   -gpu N       first CUDA device ordinal (default 0).
 //   -gpus G      train on G GPUs (devices gpu..gpu+G-1): shards split in G blocks, full replicas,
-//                NCCL all-reduce-average every -sync-every steps (default 4) and at every epoch end.
+//                NCCL all-reduce-average every -sync-every steps (default 4) and at every epoch end;
+//                -sync-mode 1 sums every GPU's updates onto the common base instead of averaging.
 //   -strict 1    parity mode: shards one after another, sequential IEEE arithmetic.
 //   -binary 2    packed output: bitlevel bits per value (bitlevel 1 and 2), see w2b_write_packed.
 //   -checkpoint F  write a resumable checkpoint (fp32 u, v, alpha, word counter) to F after every epoch.

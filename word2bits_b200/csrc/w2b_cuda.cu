@@ -525,6 +525,8 @@ static int create_impl(const w2b_config *cfg, w2b_ctx **out) {
   if (c->warp && !c->warp_sen_smem) CK(cudaMalloc(&c->d_sen, sizeof(int) * (size_t)kMaxS * (c->nlocal + 1)));
   CK(cudaEventCreate(&c->ev_s0));
   CK(cudaEventCreate(&c->ev_s1));
+  // the memsets above ran on the legacy stream, which the context's non-blocking streams do not wait for
+  CK(cudaDeviceSynchronize());
   return W2B_OK;
 }
 
@@ -569,13 +571,13 @@ static int w2b_set_vocab_counts_impl(w2b_ctx *c, const int64_t *cn, int64_t V, i
   // sub-sampling threshold `ran` (:403-404), float32 throughout
   std::vector<float> keep(V);
   w2b_keep_thresholds(cn, V, train_words, c->cfg.sample, keep.data());
-  CK(cudaMemcpy(c->d_keep, keep.data(), V * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(c->d_keep, keep.data(), V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   // unigram boundaries (:112-128) with the host libm pow(); the device expands them
   std::vector<int> start(V + 1);
   w2b_unigram_bounds(cn, V, start.data());
   DevTmp d_start;
   CK(d_start.alloc((V + 1) * sizeof(int)));
-  CK(cudaMemcpy(d_start.p, start.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(d_start.p, start.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   fill_table_kernel<<<(W2B_TABLE_SIZE + 255) / 256, 256, 0, c->stream>>>(c->d_table, d_start.as<int>(), (int)V);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
@@ -635,7 +637,8 @@ static int w2b_set_corpus_impl(w2b_ctx *c, const int32_t *ids, int64_t n, const 
   c->pf.valid = false;  // slices prefetched from the previous stream are void
   if (c->resident) {
     CK(cudaMalloc(&c->d_tokens, std::max<int64_t>(n, 1) * sizeof(int)));
-    CK(cudaMemcpy(c->d_tokens, ids, n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(c->d_tokens, ids, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     c->h_ids = nullptr;
   } else {
     c->h_ids = ids;
@@ -660,7 +663,8 @@ extern "C" int w2b_epoch_begin(w2b_ctx *c) {
     s.limit_is_eof = 1;
     s.xlate = 0;
   }
-  CK(cudaMemcpy(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(c->d_shards, c->h_shards.data(), sizeof(ShardState) * c->nlocal, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return W2B_OK;
 }
 
@@ -959,9 +963,9 @@ static int w2b_trace_impl(w2b_ctx *c, int shard, int64_t max_iterations, w2b_tra
   float *d_alpha = t_alpha.as<float>();
   unsigned long long *d_cnt = t_cnt.as<unsigned long long>();
   w2b_trace_rec *d_tr = t_tr.as<w2b_trace_rec>();
-  CK(cudaMemcpy(d_s, &s, sizeof s, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_alpha, &c->cfg.alpha, sizeof(float), cudaMemcpyHostToDevice));
-  CK(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(d_s, &s, sizeof s, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_alpha, &c->cfg.alpha, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), c->stream));
   TrainParams p = base_params(c);
   p.shards = d_s;
   p.alpha = d_alpha;
@@ -1037,8 +1041,8 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
   CK(t_f.alloc((nt + 1) * sizeof(float)));
   int *d_ids = t_ids.as<int>();
   float *d_f = t_f.as<float>();
-  if (cw) CK(cudaMemcpy(d_ids, ctx_ids, cw * sizeof(int), cudaMemcpyHostToDevice));
-  if (nt) CK(cudaMemcpy(d_ids + cw, targets, nt * sizeof(int), cudaMemcpyHostToDevice));
+  if (cw) CK(cudaMemcpyAsync(d_ids, ctx_ids, cw * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (nt) CK(cudaMemcpyAsync(d_ids + cw, targets, nt * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   TrainParams p = base_params(c);
   if (c->warp) {  // L1 hook through the production kernel itself: one explicit position, one launch
     if (cw > 2 * c->cfg.window || nt > c->cfg.negative + 1) {
@@ -1050,7 +1054,7 @@ extern "C" int w2b_apply_position(w2b_ctx *c, const int32_t *ctx_ids, int cw, co
     CK(cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem));
     DevTmp t_s;
     CK(t_s.alloc(sizeof(ShardState)));
-    CK(cudaMemset(t_s.p, 0, sizeof(ShardState)));
+    CK(cudaMemsetAsync(t_s.p, 0, sizeof(ShardState), c->stream));
     p.shards = t_s.as<ShardState>();
     p.serial = 1;
     ApplyArgs ap;
@@ -1086,9 +1090,10 @@ extern "C" int w2b_set_state(w2b_ctx *c, float alpha, int64_t wca) {
   NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   unsigned long long w = (unsigned long long)wca;
-  CK(cudaMemcpy(c->d_alpha, &alpha, sizeof(float), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d_wca, &w, sizeof w, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d_scratch + 1, &w, sizeof w, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(c->d_alpha, &alpha, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_wca, &w, sizeof w, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_scratch + 1, &w, sizeof w, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   c->wca_at_sync = wca;
   return W2B_OK;
 }
@@ -1106,8 +1111,9 @@ extern "C" int w2b_upload_raw(w2b_ctx *c, const float *u, const float *v) {
   NEED(c);
   CK(cudaSetDevice(c->cfg.device));
   const size_t row = (size_t)c->cfg.layer1_size * sizeof(float), dp = (size_t)c->pitch * sizeof(float);
-  if (u) CK(cudaMemcpy2D(c->d_u, dp, u, row, row, c->cfg.vocab_size, cudaMemcpyHostToDevice));
-  if (v) CK(cudaMemcpy2D(c->d_v, dp, v, row, row, c->cfg.vocab_size, cudaMemcpyHostToDevice));
+  if (u) CK(cudaMemcpy2DAsync(c->d_u, dp, u, row, row, c->cfg.vocab_size, cudaMemcpyHostToDevice, c->stream));
+  if (v) CK(cudaMemcpy2DAsync(c->d_v, dp, v, row, row, c->cfg.vocab_size, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return W2B_OK;
 }
 
@@ -1219,6 +1225,7 @@ static int w2b_checkpoint_load_impl(w2b_ctx *c, const char *path, int64_t *epoch
       }
     }
   fclose(f);
+  CK(cudaDeviceSynchronize());  // the uploads ran on the legacy stream
   if (epochs_done) *epochs_done = h.epochs_done;
   c->have_tables = true;  // u and v now hold trained values
   return w2b_set_state(c, h.alpha, h.wca);
@@ -1248,7 +1255,7 @@ extern "C" int w2b_quantize(w2b_ctx *c, const float *in, float *out, int64_t n, 
   DevTmp t;
   CK(t.alloc(2 * n * sizeof(float)));
   float *d = t.as<float>();
-  CK(cudaMemcpy(d, in, n * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(d, in, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   quantize_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d, d + n, n, bitlevel);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d + n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1294,8 +1301,9 @@ extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks
     const size_t bytes = table_elems(c) * sizeof(float);
     if (!c->d_base_u) CK(cudaMalloc(&c->d_base_u, bytes));
     if (!c->d_base_v) CK(cudaMalloc(&c->d_base_v, bytes));
-    CK(cudaMemcpy(c->d_base_u, c->d_u, bytes, cudaMemcpyDeviceToDevice));
-    CK(cudaMemcpy(c->d_base_v, c->d_v, bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpyAsync(c->d_base_u, c->d_u, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_base_v, c->d_v, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
   }
   return W2B_OK;
 }

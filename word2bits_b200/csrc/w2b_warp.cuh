@@ -172,8 +172,8 @@ struct ApplyArgs {
 // Samples forward to the next trained position (cw > 0) of the shard and appends its jobs — cw context ids, nt
 // target ids | kJobTarget, -1 — to the job queue at index qtail.  Returns 1 with cw / nt / alpha of the position,
 // or 0 when the launch is over for this shard (word budget, shard end, slice exhausted, max_iters).
-// Control flow and draw order of :379-460; see train_ring_kernel's sampler warp in round 1 for the prefetch of
-// the next position's unigram-table lookups.
+// Control flow and draw order of :379-460.  While a position is trained, the unigram-table lookups of the next
+// position of the same sentence (whose draws are already determined) are in flight in `t_pre` / S.r1_pre.
 __device__ inline int warp_next_position(const TrainParams &p, const ShardState &sh, WarpSampler &Ssm, int lane, int *sen,
                                          int *jobq, int qmask, unsigned qtail, int &t_pre, int &cw_out, int &nt_out,
                                          float &alpha_out) {
