@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (runs the compiled reference under oracle/_ref next to the product).
 SURVEY Appendix B quality protocol at full size: planted-topic corpus (V=20000, 50 topics, 250k
 sentences x 20 tokens), D=200 W=8 neg=24 bitlevel 1, 3 epochs.  Reference (16 CPU threads) vs the GPU
-CLI at its default shard count (hundreds of concurrent shards) and at 16 shards.  Prints epoch losses
+CLI at its default shard count and at chosen shard counts.  Prints epoch losses
 and same-topic purity of the top-10 neighbours of the 3000 most frequent words."""
 import os, re, subprocess, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -45,9 +45,13 @@ def run(name, exe, extra):
 
 ref = os.path.join(ROOT, "oracle", "_ref", "word2bits")
 ours = os.path.join(ROOT, "word2bits_b200", "word2bits")
-if os.path.exists(ref):
-    run("reference -threads 16", ref, ["-threads", "16"])
-run("gpu default shards", ours, [])
-run("gpu -threads 16", ours, ["-threads", "16"])
-run("gpu -threads 148", ours, ["-threads", "148"])
-run("gpu -threads 2960", ours, ["-threads", "2960"])
+# python tests/tools/quality_planted.py [shard counts; 0 = the CLI's default, "ref" = the reference at 16 threads]
+which = sys.argv[1:] or ["ref", "0", "16", "148", "2960"]
+for w in which:
+    if w == "ref":
+        if os.path.exists(ref):
+            run("reference -threads 16", ref, ["-threads", "16"])
+    elif w == "0":
+        run("gpu default shards", ours, [])
+    else:
+        run("gpu -threads %s" % w, ours, ["-threads", w])
