@@ -70,7 +70,7 @@ struct WarpX { unsigned long long gen = 0; int arrived = 0, op = -1, arg = 0; ui
 std::vector<WarpX> g_warp;
 struct BlockBar { unsigned long long gen = 0; int arrived = 0; };
 BlockBar g_bar[16];
-struct MBar { int count = 0, pending = 0; long long tx = 0; unsigned phase = 0; bool init = false; };
+struct MBar { int count = 0, pending = 0; long long tx = 0; unsigned phase = 0; bool init = false, unobserved = false; };
 std::vector<MBar> g_mbar(sizeof(w2b::smem) / 8);
 struct Load { unsigned dst_off, bytes, bar_off; const void *src; };
 std::vector<Load> g_loads;
@@ -118,7 +118,7 @@ void make_fiber(Fiber &f) {
 void complete_tx(unsigned bar_off, unsigned bytes) {
   MBar &m = g_mbar[bar_off / 8];
   m.tx -= bytes;
-  if (m.pending == 0 && m.tx == 0) { m.phase ^= 1; m.pending = m.count; }
+  if (m.pending == 0 && m.tx == 0) { m.phase ^= 1; m.pending = m.count; m.unobserved = true; }
 }
 void land(const Load &l) {
   ++g_progress;
@@ -222,14 +222,19 @@ void emu_mbar_expect_tx(unsigned off, unsigned bytes) {
   MBar &m = g_mbar[off / 8];
   if (!m.init) fail("expect_tx on an uninitialised mbarrier");
   if (m.pending <= 0) fail("mbarrier armed twice in one phase");
+  // what compute-sanitizer's synccheck calls "Missing wait": a phase completed and the barrier is armed for the next
+  // one although no thread ever waited for it (harmless for the hardware, but every job is expected to wait)
+  if (m.unobserved) fail("mbarrier armed again although no thread waited for its previous phase");
   ++g_progress;
   m.tx += bytes;
   m.pending -= 1;
-  if (m.pending == 0 && m.tx == 0) { m.phase ^= 1; m.pending = m.count; }
+  if (m.pending == 0 && m.tx == 0) { m.phase ^= 1; m.pending = m.count; m.unobserved = true; }
 }
 bool emu_mbar_try_wait(unsigned off, unsigned parity) {
-  const MBar &m = g_mbar[off / 8];
-  return (m.phase & 1u) != (parity & 1u);  // the phase with this parity has completed
+  MBar &m = g_mbar[off / 8];
+  const bool done = (m.phase & 1u) != (parity & 1u);  // the phase with this parity has completed
+  if (done) m.unobserved = false;
+  return done;
 }
 void emu_bulk_load(unsigned dst_off, const void *src, unsigned bytes, unsigned bar_off) {
   if (bytes % 16 || dst_off % 16 || ((uintptr_t)src) % 16) fail("bulk copy operands must be 16-byte aligned");

@@ -18,6 +18,7 @@ for D, bits, reg, prefetch in ((200, 1, 0.0, 0), (103, 2, 0.0, 1), (800, 1, 0.0,
     for _ in range(2):
         st = t.train_step(150)
     print("D=%d bits=%d reg=%g prefetch=%d: %d positions, loss/position %.4f, plan %s" % (
-        D, bits, reg, prefetch, st["positions"], st["loss"] / max(st["positions"], 1), t.warp_plan()), flush=True)
+        D, bits, reg, prefetch, st["positions"], st["loss"] / max(st["positions"], 1),
+        w2b.warp_plan(size=D, window=5, negative=8, bitlevel=bits, reg=reg, vocab_size=V + 1)), flush=True)
     t.close()
 print("sanitize_step done")

@@ -1293,6 +1293,10 @@ extern "C" int w2b_nccl_init(w2b_ctx *c, const void *id128, int rank, int nranks
   CK(cudaSetDevice(c->cfg.device));
   nccl_uid id;
   memcpy(&id, id128, sizeof id);
+  if (c->comm) {  // a second init replaces the communicator instead of leaking it
+    if (g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
   int e = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
   if (e) { w2b_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?"); return W2B_ENCCL; }
   c->rank = rank;

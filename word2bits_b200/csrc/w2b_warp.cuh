@@ -576,6 +576,7 @@ __global__ void __launch_bounds__(32, MINB) train_warp_kernel(TrainParams p, int
 
     // ---- staging job: the error goes to every context row of u (:494-503)
     {
+      mbar_wait(c_bar, c_par);  // armed with 0 bytes, long complete: every job observes its slot's phase (synccheck-clean)
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
         if ((j < NJ - 1) || on_last) sts128(c_row + W2B_COFF(j), make_float4(e[j][0].x, e[j][0].y, e[j][1].x, e[j][1].y));
