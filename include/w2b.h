@@ -104,7 +104,7 @@ typedef struct {
   int32_t device;      /* CUDA device ordinal */
   int32_t mode;        /* W2B_MODE_FAST | W2B_MODE_STRICT */
   int32_t group;       /* register kernel: target rows in flight per CTA step (0 = default) */
-  int32_t plain_store; /* register kernel only: 1 = racy load/add/store like the reference, 0 = red.add */
+  int32_t plain_store; /* reserved, must be 0 (round 1's racy load/add/store variant of the register kernel is gone) */
   int32_t kernel;      /* fast mode: 0 = warp-per-shard kernel when applicable (default; csrc/w2b_warp.cuh),
                           1 = register kernel (one CTA per shard; also serves strict mode and D > 1024) */
   int32_t slots;       /* warp kernel: shared-memory row slots per warp (0 = as many as fit, at most 16) */

@@ -441,7 +441,7 @@ static void emu_setup(const EmuRun *r, std::vector<w2b::ShardState> &shards, w2b
   p.alpha_denom = (float)(r->iter * r->train_words + 1);
   p.shard_word_limit = r->train_words / r->num_shards;
   p.word_budget = r->word_budget; p.max_iters = r->max_iters; p.shard_base = 0; p.train = r->train;
-  p.plain_store = 0; p.serial = r->serial; p.wca_scale = 1;
+  p.serial = r->serial; p.wca_scale = 1;
   p.trace = r->trace; p.trace_cap = r->trace_cap; p.trace_n = (unsigned long long *)r->trace_n;
 }
 

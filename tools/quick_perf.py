@@ -26,14 +26,14 @@ def main():
     N = int(sys.argv[5]) if len(sys.argv) > 5 else 30_000_000
     groups = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0]
     threads_list = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [0]
-    plain = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+    plain = 0  # (argv[8] was the removed plain_store knob; kept so that later positions do not shift)
     kernel = int(sys.argv[9]) if len(sys.argv) > 9 else 0
     slots = int(sys.argv[10]) if len(sys.argv) > 10 else 0
     ids, cn = synth(V, N)
     for group in groups:
       for threads in threads_list:
         t = w2b.Trainer(None, vocab_size=V + 1, size=D, window=10, negative=neg, bitlevel=b, iter=1,
-                        threads=threads or None, group=group, plain_store=plain, kernel=kernel, slots=slots)
+                        threads=threads or None, group=group, kernel=kernel, slots=slots)
         S = t.threads
         t.set_vocab_counts(cn, int(N))
         start = (np.arange(S, dtype=np.int64) * (N // S))

@@ -339,7 +339,6 @@ static TrainParams base_params(const w2b_ctx *c) {
   p.max_iters = -1;
   p.shard_base = 0;
   p.train = 1;
-  p.plain_store = c->cfg.plain_store;
   p.serial = c->cfg.prefetch ? 0 : 1;  // default: the positions of a shard strictly one after another
   p.wca_scale = c->nranks;
   p.sen = c->d_sen;
@@ -368,6 +367,7 @@ static int validate(const w2b_config *c) {
   if (c->bitlevel > 24) { w2b_set_error("bitlevel must be <= 24"); return W2B_EINVAL; }
   if (c->num_shards < 1) { w2b_set_error("num_shards must be >= 1"); return W2B_EINVAL; }
   if (c->iter < 1) { w2b_set_error("iter must be >= 1"); return W2B_EINVAL; }
+  if (c->plain_store != 0) { w2b_set_error("plain_store: the racy load/add/store variant was removed; must be 0"); return W2B_EINVAL; }
   const long long D = c->layer1_size;
   // production kernel: any D <= 2048 (rows padded to whole float4s); register kernel: D <= 4096 when divisible by 4
   // (a thread per float4), else D <= 1024 (a thread per float) — strict mode and kernel = 1 always run the latter

@@ -74,7 +74,6 @@ struct TrainParams {
   long long max_iters;          // test hook: stop after this many window draws (<0: none)
   int shard_base;               // first local shard handled by blockIdx 0
   int train;                    // 0: draws only (trace)
-  int plain_store;
   int serial;                   // warp kernel: 1 = position p+1 is fetched after every update of p completed
   int wca_scale;                // multi-GPU: local words stand for wca_scale x as many globally
   int *sen;                     // warp kernel: global sentence buffers (kMaxS ints per local shard + 1) when they do not fit shared memory
@@ -450,10 +449,10 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
             } else {
               dv = g * avg[i];
             }
-            upd.a[i] = (STRICT || p.plain_store) ? __fadd_rn(x[k].a[i], dv) : dv;
+            upd.a[i] = STRICT ? __fadd_rn(x[k].a[i], dv) : dv;
           }
           float *row = p.v + (long long)d->tg[g0 + k] * p.pitch + col;
-          if (STRICT || p.plain_store) upd.store(row);
+          if (STRICT) upd.store(row);
           else upd.red_add(row);
         }
       }
@@ -464,7 +463,7 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
   if (active) {
     for (int k = 0; k < cw; ++k) {
       float *row = p.u + (long long)d->ctx[k] * p.pitch + col;
-      if (STRICT || HAS_REG || p.plain_store) {
+      if (STRICT || HAS_REG) {
         Vec<VEC> x;
         x.load(row);
         Vec<VEC> upd;
@@ -472,9 +471,9 @@ __device__ __forceinline__ void process_position(const TrainParams &p, const Pos
         for (int i = 0; i < VEC; ++i) {
           float t2 = (STRICT || HAS_REG) ? __fmul_rn(__fmul_rn(__fmul_rn(2.f, alpha), p.reg), x.a[i]) : 0.f;
           float du = (STRICT || HAS_REG) ? __fsub_rn(err[i], t2) : err[i];
-          upd.a[i] = (STRICT || p.plain_store) ? __fadd_rn(x.a[i], du) : du;
+          upd.a[i] = STRICT ? __fadd_rn(x.a[i], du) : du;
         }
-        if (STRICT || p.plain_store) upd.store(row);
+        if (STRICT) upd.store(row);
         else upd.red_add(row);
       } else {
         Vec<VEC> upd;
