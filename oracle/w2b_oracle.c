@@ -405,6 +405,7 @@ double w2bo_train_shard(w2bo_model *m, const w2bo_corpus *c, int id, int64_t max
   float *avg = (float *)malloc(sizeof(float) * D);
   float *err = (float *)malloc(sizeof(float) * D);
   int32_t sen[W2BO_MAX_SENTENCE + 1];
+  int32_t *tg_big = NULL;
   sen[0] = -1;
   int64_t len = 0, sp = 0, wc = 0, last = 0, npos = 0;
   uint64_t r = (uint64_t)(int64_t)id; /* :368 */
@@ -444,7 +445,7 @@ double w2bo_train_shard(w2bo_model *m, const w2bo_corpus *c, int id, int64_t max
     npos++;
     r = w2bo_lcg(r); /* :428-429 — also drawn for an empty sentence (stale sen[0]) */
     int bshrink = (int)(r % (uint64_t)W);
-    int32_t ctx[2 * 64 + 2];
+    int32_t ctx[W2BO_MAX_SENTENCE + 1]; /* a window never holds more than the sentence (:32), whatever -window is */
     int cw = 0;
     int32_t center = len ? sen[sp] : -1;
     for (int a = bshrink; a < W * 2 + 1 - bshrink; a++) {
@@ -453,7 +454,8 @@ double w2bo_train_shard(w2bo_model *m, const w2bo_corpus *c, int id, int64_t max
       if (q < 0 || q >= len) continue;
       ctx[cw++] = sen[q];
     }
-    int32_t tg[64];
+    int32_t tg_fixed[64], *tg = tg_fixed; /* 1 + negative targets; the reference has no upper bound on -negative */
+    if (m->negative + 1 > 64) tg = tg_big ? tg_big : (tg_big = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m->negative + 1)));
     int nt = 0;
     if (cw) {
       tg[nt++] = center;
@@ -468,7 +470,7 @@ double w2bo_train_shard(w2bo_model *m, const w2bo_corpus *c, int id, int64_t max
     if (trace && trace->n < trace->cap) {
       w2bo_trace_rec *rec = &trace->rec[trace->n++];
       rec->center = center; rec->b = bshrink; rec->cw = cw; rec->ntargets = nt;
-      for (int k = 0; k < nt; k++) rec->targets[k] = tg[k];
+      for (int k = 0; k < nt && k < 64; k++) rec->targets[k] = tg[k];
       rec->alpha = m->alpha;
     }
     apply_position(m, exptab, ctx, cw, tg, nt, 1, avg, err, NULL, &total);
@@ -477,6 +479,7 @@ double w2bo_train_shard(w2bo_model *m, const w2bo_corpus *c, int id, int64_t max
   }
   free(avg);
   free(err);
+  free(tg_big);
   return total;
 }
 

@@ -506,9 +506,14 @@ def test_production_kernel_odd_shapes(D, W, neg, b, medium):
     tol = 0.05 if D >= 512 else 0.02
     if W <= 64:
         assert abs(lg - lo) <= tol * abs(lo) + 1.0, (D, W, neg, b, lg, lo)
-    # else: the algorithm itself is unstable at this setting (a sentence-wide window adds the same error vector to
-    # hundreds of context rows per position; the oracle's |u| reaches 1e2 .. 1e3 with 1 or 6 threads alike and its
-    # loss moves by 30 % between sequential and concurrent shards) — only the counters are compared
+    else:
+        # Windows wider than 64: when these cases were last run on a GPU the oracle port still kept a position's context
+        # ids in a 130-entry buffer (fixed since; pinned at window 300 by tests/test_oracle_vs_ref.py), so its loss was
+        # garbage there and only the counters were compared.  With the fixed oracle the kernel's own source matches
+        # it to 1e-4 .. 4e-4 at windows 200 .. 512 on the emulator (tests/test_warp_emulation.py::
+        # test_sentence_wide_windows_track_the_oracle) and the oracle's concurrent-vs-sequential spread is 0.4 - 0.7 %;
+        # the gap is printed here, the bar stays on the counters until a GPU run has confirmed it.
+        print("wide window D=%d W=%d neg=%d: GPU loss %.1f, oracle %.1f (rel. gap %.4f)" % (D, W, neg, lg, lo, abs(lg - lo) / abs(lo)))
     u, v = t.download_raw()
     assert np.isfinite(u).all() and np.isfinite(v).all()
 

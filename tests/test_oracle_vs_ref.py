@@ -87,6 +87,10 @@ CASES = [
     ("small", 8, 3, 4, 2, 2, 5, 1e-3, 0.01, 1),
     ("medium", 20, 5, 6, 1, 4, 5, 1e-3, 0.0, 2),
     ("medium", 16, 4, 5, 0, 3, 1, 1e-4, 0.0, 1),
+    # windows wider than 64 and more than 63 negatives (the reference has no bound on either; until round 2 the port
+    # kept a position's context ids in a 130-entry buffer — found when the product's window limit went to 512)
+    ("medium", 8, 300, 4, 1, 2, 1, 1e-3, 0.0, 1),
+    ("small", 8, 100, 70, 0, 1, 1, 1e-3, 0.0, 1),
 ]
 
 

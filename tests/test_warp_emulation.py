@@ -105,6 +105,27 @@ def test_regularised_training_tracks_the_oracle(b, D, medium):
     assert np.abs(m0.u - m.u).max() > 1e-3  # the regulariser really moved the weights: the comparison above is not vacuous
 
 
+@pytest.mark.parametrize("D,W,neg,b", [(32, 512, 63, 1), (47, 200, 5, 2), (20, 300, 8, 1)])
+def test_sentence_wide_windows_track_the_oracle(D, W, neg, b, tmp_path):
+    """Windows as wide as a 1000-word sentence (hundreds of context rows per position, job queue of thousands of
+    entries, sentence buffer outside shared memory): one shard, sequential mode, loss and counters against the oracle.
+    (The oracle itself is pinned to the reference at such windows by tests/test_oracle_vs_ref.py; until round 2 its
+    context buffer held 130 ids, which is why wide windows used to be compared on counters only.)"""
+    path = zipf_corpus(str(tmp_path / "long.txt"), 3000, 300, seed=11, newline_every=0)  # three 1000-word sentences
+    c, o = w2b.Corpus(path, 1), po.Corpus(path, 1)
+    table = po.unigram_table(o.counts)
+    m = po.OracleModel(o, D, W, neg, b, shards=1, iters=1, table=table)
+    lo, tr = m.train_shard(0, trace_cap=10000)
+    assert max(t[2] for t in tr) > 2 * 64  # more context rows in one position than any window <= 64 can give
+    u, v, out = _run(c, table, D, W, neg, b, 1, serial=1, async_mode=2, seed=5)
+    assert out["n_ctx"].sum() == sum(t[2] for t in tr) and out["n_tgt"].sum() == sum(len(t[3]) for t in tr if t[2] > 0)
+    # (63 negatives out of a 300-word vocabulary: most positions hold duplicate targets, which both read the old row
+    # in this kernel — documented deviation 1 — hence the wider bar for that case)
+    assert abs(out["loss"].sum() - lo) <= (1e-2 if neg > 32 else 2e-3) * abs(lo), (out["loss"].sum(), lo)
+    bar = 0.95 if neg > 32 else 0.99
+    assert np.corrcoef(u.ravel(), m.u.ravel())[0, 1] > bar and np.corrcoef(v.ravel(), m.v.ravel())[0, 1] > bar
+
+
 def test_sampler_trace_equals_oracle(tiny):
     c, o, table = tiny
     for neg, shard in ((40, 0), (40, 2), (5, 1)):
