@@ -105,6 +105,20 @@ def test_regularised_training_tracks_the_oracle(b, D, medium):
     assert np.abs(m0.u - m.u).max() > 1e-3  # the regulariser really moved the weights: the comparison above is not vacuous
 
 
+@pytest.mark.parametrize("D,neg", [(400, 1), (1185, 0), (50, 1)])
+def test_fp32_without_duplicate_targets_is_exact_to_rounding(D, neg, tiny):
+    """What separates the production kernel from one reference thread in sequential mode is (a) reduction order / FMA
+    and (b) duplicate targets inside a position reading the same old row (DESIGN: deviation 1).  With at most one
+    negative a position cannot hold a duplicate (a draw equal to the centre is skipped, :458), so at bitlevel 0 only
+    (a) is left: the epoch loss agrees to 1e-6 relative and the tables to 1e-4 (measured 1e-9 .. 1e-8 and <= 5e-6)."""
+    c, o, table = tiny
+    m = po.OracleModel(o, D, 4, neg, 0, shards=1, iters=1, table=table)
+    lo = m.train_shard(0)
+    u, v, out = _run(c, table, D, 4, neg, 0, 1, serial=1, async_mode=2, seed=9)
+    assert abs(out["loss"].sum() - lo) <= 1e-6 * abs(lo), (out["loss"].sum(), lo)
+    assert np.abs(u - m.u).max() < 1e-4 and np.abs(v - m.v).max() < 1e-4
+
+
 @pytest.mark.parametrize("D,W,neg,b", [(32, 512, 63, 1), (47, 200, 5, 2), (20, 300, 8, 1)])
 def test_sentence_wide_windows_track_the_oracle(D, W, neg, b, tmp_path):
     """Windows as wide as a 1000-word sentence (hundreds of context rows per position, job queue of thousands of
